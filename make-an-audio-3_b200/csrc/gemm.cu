@@ -1,0 +1,498 @@
+// Tap-GEMM for sm_100a: persistent, warp-specialised, TMA -> smem ring -> tcgen05.mma -> TMEM (double-buffered
+// accumulator) -> fused epilogue.  One kernel serves nn.Linear, Conv1d (any k / dilation, channels-last) and the
+// phases of ConvTranspose1d; see include/ma3_b200.h for the contract and the reference code it replaces.
+//
+// Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one elected
+// lane), warps 2..5 = epilogue (TMEM lane quarter = warp % 4; thread <-> accumulator row).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace ma3 {
+
+constexpr int kBM = 128;
+constexpr int kGemmThreads = 192;
+constexpr int kMaxStages = 8;
+
+struct GemmKParams {
+  CUtensorMap tmA, tmB;
+  int M, N, K, taps;
+  int a_shift[MA3_MAX_TAPS], b_row[MA3_MAX_TAPS];
+  int a_batched, b_batched;
+  int BN, BK, stages;
+  int tiles_m, tiles_n, batch;
+  uint32_t idesc, tmem_cols, tmem_stage_cols;
+  // epilogue
+  void* out;
+  int out_dtype;
+  long long out_ld, out_batch_stride;
+  int out_row_mul, out_row_off;
+  const float* bias;
+  int bias_per_row;
+  const void* res;
+  int res_dtype;
+  long long res_ld, res_batch_stride;
+  float alpha;
+  int accumulate;
+  int vec_ok;
+  const float* gate;
+  long long gate_ld;
+  int rows_per_sample;
+  void *q_out, *k_out, *vt_out;
+  const float* rope;
+  int model_dim, head_dim, head_dim_pad, heads, tokens, tokens_pad;
+  float q_scale;
+  int op_dtype;
+};
+
+// ------------------------------------------------------------------------------------------------ epilogues
+__device__ __forceinline__ void load8(const void* base, int dtype, long long idx, bool vec, int n, float (&v)[8]) {
+  if (dtype == MA3_F32) {
+    const float* p = reinterpret_cast<const float*>(base) + idx;
+    if (vec && n == 8) {
+      float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = e < n ? p[e] : 0.f;
+    }
+  } else if (dtype == MA3_BF16) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + idx;
+    if (vec && n == 8) {
+      uint4 u = *reinterpret_cast<const uint4*>(p);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = e < n ? __bfloat162float(p[e]) : 0.f;
+    }
+  } else {
+    const __half* p = reinterpret_cast<const __half*>(base) + idx;
+    if (vec && n == 8) {
+      uint4 u = *reinterpret_cast<const uint4*>(p);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = e < n ? __half2float(p[e]) : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void store8(void* base, int dtype, long long idx, bool vec, int n, const float (&v)[8]) {
+  if (dtype == MA3_F32) {
+    float* p = reinterpret_cast<float*>(base) + idx;
+    if (vec && n == 8) {
+      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) if (e < n) p[e] = v[e];
+    }
+  } else if (dtype == MA3_BF16) {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + idx;
+    if (vec && n == 8) {
+      uint4 u = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      *reinterpret_cast<uint4*>(p) = u;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) if (e < n) p[e] = __float2bfloat16_rn(v[e]);
+    }
+  } else {
+    __half* p = reinterpret_cast<__half*>(base) + idx;
+    if (vec && n == 8) {
+      uint4 u = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
+      *reinterpret_cast<uint4*>(p) = u;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) if (e < n) p[e] = __float2half_rn(v[e]);
+    }
+  }
+}
+
+// One thread owns accumulator row m of batch z and `w` (16 or 32) consecutive columns starting at n0.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int m, int n0, int w, const uint32_t* r) {
+  if (m >= p.M) return;
+  if constexpr (EPI == MA3_EPI_STORE) {
+    const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
+    const long long obase = (long long)z * p.out_batch_stride + orow * p.out_ld;
+    const long long rbase = (long long)z * p.res_batch_stride + orow * p.res_ld;
+    const bool vec = p.vec_ok != 0;
+    const float brow = (p.bias && p.bias_per_row) ? p.bias[m] : 0.f;
+    for (int g = 0; g < w; g += 8) {
+      const int col = n0 + g;
+      if (col >= p.N) break;
+      const int n = min(8, p.N - col);
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g + e]) + brow;
+      if (p.bias && !p.bias_per_row) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (e < n) v[e] += p.bias[col + e];
+      }
+      if (p.res) {
+        float t[8];
+        load8(p.res, p.res_dtype, rbase + col, vec, n, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += t[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
+      if (p.accumulate) {
+        float t[8];
+        load8(p.out, p.out_dtype, obase + col, vec, n, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += t[e];
+      }
+      store8(p.out, p.out_dtype, obase + col, vec, n, v);
+    }
+  } else if constexpr (EPI == MA3_EPI_GATE_RES) {
+    float* out = reinterpret_cast<float*>(p.out);
+    const int sample = m / p.rows_per_sample;
+    const float* gate = p.gate + (long long)sample * p.gate_ld;
+    const long long obase = (long long)m * p.out_ld;
+    for (int g = 0; g < w; g += 4) {
+      const int col = n0 + g;
+      if (col >= p.N) break;  // N % 4 == 0 enforced on the host
+      float4 h = *reinterpret_cast<const float4*>(out + obase + col);
+      const float4 gt = *reinterpret_cast<const float4*>(gate + col);
+      h.x += gt.x * __uint_as_float(r[g + 0]);
+      h.y += gt.y * __uint_as_float(r[g + 1]);
+      h.z += gt.z * __uint_as_float(r[g + 2]);
+      h.w += gt.w * __uint_as_float(r[g + 3]);
+      *reinterpret_cast<float4*>(out + obase + col) = h;
+    }
+  } else if constexpr (EPI == MA3_EPI_SWIGLU) {
+    // B rows interleave w1 (even) and w3 (odd): out[m, n/2] = silu(acc[n]) * acc[n+1]
+    const long long obase = (long long)m * p.out_ld;
+    for (int g = 0; g < w; g += 16) {
+      const int col = n0 + g;
+      if (col >= p.N) break;  // N % 16 == 0 enforced on the host
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = silu_f(__uint_as_float(r[g + 2 * e])) * __uint_as_float(r[g + 2 * e + 1]);
+      store8(p.out, p.out_dtype, obase + (col >> 1), true, 8, v);
+    }
+  } else if constexpr (EPI == MA3_EPI_QKV_ROPE) {
+    const int sample = m / p.tokens, t = m - sample * p.tokens;
+    const int half_hd = p.head_dim >> 1;
+    for (int g = 0; g < w; g += 8) {
+      const int col = n0 + g;
+      if (col >= p.N) break;
+      const int which = col / p.model_dim;
+      const int within = col - which * p.model_dim;
+      const int head = within / p.head_dim;
+      const int d = within - head * p.head_dim;  // multiple of 8 (head_dim % 8 == 0 enforced on the host)
+      const long long sh = (long long)sample * p.heads + head;
+      if (which < 2) {
+        const float2* cs = reinterpret_cast<const float2*>(p.rope) + (long long)t * half_hd + (d >> 1);
+        const float sc = which == 0 ? p.q_scale : 1.0f;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = cs[e];
+          const float x0 = __uint_as_float(r[g + 2 * e]), x1 = __uint_as_float(r[g + 2 * e + 1]);
+          v[2 * e] = (x0 * f.x - x1 * f.y) * sc;
+          v[2 * e + 1] = (x0 * f.y + x1 * f.x) * sc;
+        }
+        void* dst = which == 0 ? p.q_out : p.k_out;
+        store8(dst, p.op_dtype, (sh * p.tokens + t) * p.head_dim_pad + d, true, 8, v);
+      } else {
+        const long long base = (sh * p.head_dim_pad + d) * p.tokens_pad + t;
+        if (p.op_dtype == MA3_BF16) {
+          __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(p.vt_out);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) vt[base + (long long)e * p.tokens_pad] = __float2bfloat16_rn(__uint_as_float(r[g + e]));
+        } else {
+          __half* vt = reinterpret_cast<__half*>(p.vt_out);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) vt[base + (long long)e * p.tokens_pad] = __float2half_rn(__uint_as_float(r[g + e]));
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_constant__ GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = kBM * p.BK * 2, b_bytes = p.BN * p.BK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(&full[i], 1);
+        mbar_init(&empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull[i], 1);
+        mbar_init(&tempty[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.tiles_m * p.tiles_n * p.batch;
+  const int kchunks = p.K / p.BK;
+  const int iters = p.taps * kchunks;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_t = tile % p.tiles_n;
+        const int rest = tile / p.tiles_n;
+        const int m_t = rest % p.tiles_m;
+        const int z = rest / p.tiles_m;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int arow = m_t * kBM + p.a_shift[tap];
+          const int brow = n_t * p.BN + p.b_row[tap];
+          for (int kc = 0; kc < kchunks; ++kc, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], stage_bytes);
+            uint8_t* dst = tiles + (size_t)s * stage_bytes;
+            tma_load_3d(dst, &p.tmA, &full[s], kc * p.BK, arow, p.a_batched ? z : 0);
+            tma_load_3d(dst + a_bytes, &p.tmB, &full[s], kc * p.BK, brow, p.b_batched ? z : 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      int it = 0, lt = 0;
+      const int sw = p.BK * 2;
+      const int ksteps = p.BK / 16;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int as = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * p.tmem_stage_cols;
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
+          const uint64_t da = umma_desc_kmajor(a_addr, sw);
+          const uint64_t db = umma_desc_kmajor(a_addr + a_bytes, sw);
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (i | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int n_t = tile % p.tiles_n;
+      const int rest = tile / p.tiles_n;
+      const int m_t = rest % p.tiles_m;
+      const int z = rest / p.tiles_m;
+      const int as = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const int m = m_t * kBM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.tmem_stage_cols;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        const int w = min(32, p.BN - c0);
+        if (w == 32) {
+          tmem_ld32(taddr + c0, r);
+        } else {
+          uint32_t r16[16];
+          tmem_ld16(taddr + c0, r16);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] = r16[e];
+        }
+        tmem_ld_wait();
+        epilogue_chunk<EPI>(p, z, m, n_t * p.BN + c0, w, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+static uint32_t pow2_cols(int n) {
+  uint32_t c = 32;
+  while ((int)c < n) c <<= 1;
+  return c;
+}
+
+template <int EPI>
+static int launch(const GemmKParams& kp, size_t smem, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(tap_gemm): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  tap_gemm_kernel<EPI><<<grid, kGemmThreads, smem, st>>>(kp);
+  MA3_LAUNCH_CHECK("tap_gemm");
+  return 0;
+}
+
+}  // namespace ma3
+
+extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
+  using namespace ma3;
+  MA3_REQUIRE(g != nullptr, "gemm: null descriptor");
+  MA3_REQUIRE(g->a && g->b, "gemm: null operand");
+  MA3_REQUIRE(g->dtype == MA3_BF16 || g->dtype == MA3_F16, "gemm: operand dtype must be bf16 or f16");
+  MA3_REQUIRE(g->M > 0 && g->N > 0 && g->batch > 0, "gemm: empty problem M=%d N=%d batch=%d", g->M, g->N, g->batch);
+  MA3_REQUIRE(g->K > 0 && g->K % 16 == 0, "gemm: K=%d must be a positive multiple of 16", g->K);
+  MA3_REQUIRE(g->taps >= 1 && g->taps <= MA3_MAX_TAPS, "gemm: taps=%d out of range", g->taps);
+  MA3_REQUIRE(aligned16(g->a) && aligned16(g->b), "gemm: operands must be 16-byte aligned");
+  MA3_REQUIRE(g->a_ld % 8 == 0 && g->b_ld % 8 == 0, "gemm: leading dimensions must be multiples of 8 elements");
+  MA3_REQUIRE(g->a_batch_stride % 8 == 0 && g->b_batch_stride % 8 == 0, "gemm: batch strides must be multiples of 8");
+  MA3_REQUIRE(g->a_ld >= g->K && g->b_ld >= g->K, "gemm: leading dimension smaller than K");
+
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const int BK = g->K % 64 == 0 ? 64 : (g->K % 32 == 0 ? 32 : 16);
+  int BN = g->tile_n;
+  if (BN <= 0) {
+    if (g->N <= 256) {
+      BN = (g->N + 15) / 16 * 16;
+    } else {
+      const int cands[3] = {256, 192, 128};
+      long best = -1;
+      for (int c : cands) {
+        long padded = (long)((g->N + c - 1) / c) * c;
+        if (best < 0 || padded < best) { best = padded; BN = c; }
+      }
+    }
+  }
+  MA3_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm: tile_n=%d must be a multiple of 16 in [16,256]", BN);
+  const size_t stage_bytes = (size_t)(kBM + BN) * BK * 2;
+  const size_t budget = 232448 - 1024 - 512;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  MA3_REQUIRE(stages >= 2, "gemm: tile does not fit shared memory");
+  // keep one CTA per SM (TMEM is allocated per CTA): request more than half of the SM's shared memory
+  size_t smem = 1024 + stages * stage_bytes + 512;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+
+  kp.M = g->M; kp.N = g->N; kp.K = g->K; kp.taps = g->taps;
+  for (int i = 0; i < g->taps; ++i) { kp.a_shift[i] = g->a_shift[i]; kp.b_row[i] = g->b_row[i]; }
+  kp.a_batched = g->a_batch_stride != 0; kp.b_batched = g->b_batch_stride != 0;
+  kp.BN = BN; kp.BK = BK; kp.stages = stages;
+  kp.tiles_m = (g->M + kBM - 1) / kBM; kp.tiles_n = (g->N + BN - 1) / BN; kp.batch = g->batch;
+  kp.idesc = umma_idesc(kBM, BN, g->dtype == MA3_BF16 ? 1 : 0);
+  kp.tmem_stage_cols = pow2_cols(BN);
+  kp.tmem_cols = 2 * kp.tmem_stage_cols;
+  kp.op_dtype = g->dtype;
+
+  {
+    uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->a_rows, (uint64_t)(kp.a_batched ? g->batch : 1)};
+    uint64_t str[2] = {(uint64_t)g->a_ld * 2, (uint64_t)(kp.a_batched ? g->a_batch_stride : g->a_rows * g->a_ld) * 2};
+    uint32_t box[3] = {(uint32_t)BK, (uint32_t)kBM, 1};
+    int rc = encode_tmap(&kp.tmA, g->a, 2, 3, dims, str, box, BK * 2);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->b_rows, (uint64_t)(kp.b_batched ? g->batch : 1)};
+    uint64_t str[2] = {(uint64_t)g->b_ld * 2, (uint64_t)(kp.b_batched ? g->b_batch_stride : g->b_rows * g->b_ld) * 2};
+    uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1};
+    int rc = encode_tmap(&kp.tmB, g->b, 2, 3, dims, str, box, BK * 2);
+    if (rc) return rc;
+  }
+
+  kp.out = g->out; kp.out_dtype = g->out_dtype; kp.out_ld = g->out_ld; kp.out_batch_stride = g->out_batch_stride;
+  kp.out_row_mul = g->out_row_mul == 0 ? 1 : g->out_row_mul; kp.out_row_off = g->out_row_off;
+  kp.bias = g->bias; kp.bias_per_row = g->bias_per_row;
+  kp.res = g->res; kp.res_dtype = g->res_dtype; kp.res_ld = g->res_ld; kp.res_batch_stride = g->res_batch_stride;
+  kp.alpha = g->alpha; kp.accumulate = g->accumulate;
+  kp.gate = g->gate; kp.gate_ld = g->gate_ld; kp.rows_per_sample = g->rows_per_sample;
+  kp.q_out = g->q_out; kp.k_out = g->k_out; kp.vt_out = g->vt_out; kp.rope = g->rope;
+  kp.model_dim = g->model_dim; kp.head_dim = g->head_dim; kp.head_dim_pad = g->head_dim_pad;
+  kp.heads = g->head_dim > 0 ? g->model_dim / g->head_dim : 0;
+  kp.tokens = g->tokens; kp.tokens_pad = g->tokens_pad; kp.q_scale = g->q_scale;
+
+  const int total_tiles = kp.tiles_m * kp.tiles_n * kp.batch;
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  switch (g->epi) {
+    case MA3_EPI_STORE: {
+      MA3_REQUIRE(g->out, "gemm/store: null out");
+      MA3_REQUIRE(g->out_dtype >= MA3_F32 && g->out_dtype <= MA3_F16, "gemm/store: bad out dtype");
+      const size_t ob = dtype_bytes(g->out_dtype);
+      bool vec = aligned16(g->out) && (g->out_ld * ob) % 16 == 0 && (g->out_batch_stride * ob) % 16 == 0 &&
+                 (g->out_dtype != MA3_F32 || (g->out_ld % 8 == 0 && g->out_batch_stride % 8 == 0));
+      if (g->out_dtype == MA3_F32)
+        vec = aligned16(g->out) && g->out_ld % 4 == 0 && g->out_batch_stride % 4 == 0;
+      else
+        vec = aligned16(g->out) && g->out_ld % 8 == 0 && g->out_batch_stride % 8 == 0;
+      if (g->res) {
+        if (g->res_dtype == MA3_F32)
+          vec = vec && aligned16(g->res) && g->res_ld % 4 == 0 && g->res_batch_stride % 4 == 0;
+        else
+          vec = vec && aligned16(g->res) && g->res_ld % 8 == 0 && g->res_batch_stride % 8 == 0;
+      }
+      kp.vec_ok = vec ? 1 : 0;
+      if (kp.alpha == 0.f) kp.alpha = 1.f;
+      return launch<MA3_EPI_STORE>(kp, smem, grid, st);
+    }
+    case MA3_EPI_GATE_RES:
+      MA3_REQUIRE(g->out && g->gate && g->rows_per_sample > 0, "gemm/gate_res: out, gate, rows_per_sample required");
+      MA3_REQUIRE(g->batch == 1, "gemm/gate_res: batch must be 1 (flatten samples into M)");
+      MA3_REQUIRE(g->N % 4 == 0 && g->out_ld % 4 == 0 && g->gate_ld % 4 == 0 && aligned16(g->out) && aligned16(g->gate),
+                  "gemm/gate_res: N, out_ld, gate_ld must be multiples of 4 and pointers 16-byte aligned");
+      return launch<MA3_EPI_GATE_RES>(kp, smem, grid, st);
+    case MA3_EPI_SWIGLU:
+      MA3_REQUIRE(g->out && g->batch == 1, "gemm/swiglu: out required, batch must be 1");
+      MA3_REQUIRE(g->N % 16 == 0 && g->out_ld % 8 == 0 && aligned16(g->out) && g->out_dtype != MA3_F32,
+                  "gemm/swiglu: N %% 16, out_ld %% 8, 16-bit out required");
+      return launch<MA3_EPI_SWIGLU>(kp, smem, grid, st);
+    case MA3_EPI_QKV_ROPE:
+      MA3_REQUIRE(g->q_out && g->k_out && g->vt_out && g->rope, "gemm/qkv_rope: q_out, k_out, vt_out, rope required");
+      MA3_REQUIRE(g->batch == 1 && g->N == 3 * g->model_dim, "gemm/qkv_rope: N must be 3*model_dim, batch 1");
+      MA3_REQUIRE(g->head_dim % 8 == 0 && g->head_dim_pad % 8 == 0 && g->model_dim % g->head_dim == 0 &&
+                      g->head_dim_pad >= g->head_dim,
+                  "gemm/qkv_rope: head_dim must be a multiple of 8 dividing model_dim");
+      MA3_REQUIRE(g->tokens > 0 && g->M % g->tokens == 0 && g->tokens_pad >= g->tokens,
+                  "gemm/qkv_rope: M must be samples*tokens");
+      MA3_REQUIRE(aligned16(g->q_out) && aligned16(g->k_out), "gemm/qkv_rope: outputs must be 16-byte aligned");
+      return launch<MA3_EPI_QKV_ROPE>(kp, smem, grid, st);
+    default:
+      MA3_FAIL(MA3_EINVAL, "gemm: unknown epilogue %d", g->epi);
+  }
+}

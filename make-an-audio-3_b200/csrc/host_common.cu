@@ -1,0 +1,92 @@
+// Library-wide state and the TMA descriptor encoder (driver entry point resolved at run time so the .so loads on a
+// machine without libcuda, e.g. the CPU-only CI container).
+#include "host_common.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace ma3 {
+
+std::atomic<int64_t> g_launches{0};
+thread_local char g_err[512] = {0};
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  auto fn = get_encode();
+  if (!fn) MA3_FAIL(MA3_ENOSYS, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    MA3_FAIL(MA3_EINVAL,
+             "cuTensorMapEncodeTiled failed (%d): base=%p rank=%d dims=[%llu,%llu,%llu] strides=[%llu,%llu] "
+             "box=[%u,%u,%u] sw=%d",
+             (int)r, base, rank, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),
+             (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 1 ? gstr[0] : 0),
+             (unsigned long long)(rank > 2 ? gstr[1] : 0), bdim[0], rank > 1 ? bdim[1] : 0, rank > 2 ? bdim[2] : 0,
+             swizzle_bytes);
+  return 0;
+}
+
+}  // namespace ma3
+
+extern "C" {
+
+int ma3_version(void) { return 100; }
+
+int64_t ma3_launch_count(void) { return ma3::g_launches.load(); }
+
+const char* ma3_last_error(void) { return ma3::g_err; }
+
+int ma3_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) MA3_FAIL(MA3_ENOSYS, "no CUDA device: %s", cudaGetErrorString(e));
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) MA3_FAIL(MA3_ENOSYS, "device is sm_%d%d; this library is sm_100a only", major, minor);
+  if (!ma3::get_encode()) MA3_FAIL(MA3_ENOSYS, "driver lacks cuTensorMapEncodeTiled");
+  return 0;
+}
+
+}  // extern "C"

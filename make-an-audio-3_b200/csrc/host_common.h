@@ -1,0 +1,45 @@
+// Host-side helpers shared by the C-ABI entry points: error reporting, launch accounting, TMA descriptor encode.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "ma3_b200.h"
+
+namespace ma3 {
+
+extern std::atomic<int64_t> g_launches;
+extern thread_local char g_err[512];
+
+#define MA3_FAIL(code, ...)                       \
+  do {                                            \
+    snprintf(::ma3::g_err, sizeof(::ma3::g_err), __VA_ARGS__); \
+    return (code);                                \
+  } while (0)
+
+#define MA3_REQUIRE(cond, ...)                    \
+  do {                                            \
+    if (!(cond)) MA3_FAIL(MA3_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+// Call after every kernel launch: counts it and converts launch errors to a return code.
+#define MA3_LAUNCH_CHECK(name)                                                         \
+  do {                                                                                 \
+    ::ma3::g_launches.fetch_add(1, std::memory_order_relaxed);                         \
+    cudaError_t e__ = cudaGetLastError();                                              \
+    if (e__ != cudaSuccess) MA3_FAIL((int)e__, "%s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+int num_sms();
+
+// elem_bytes = 2 (bf16/f16) or 4 (f32).  dims/strides innermost first; strides[i] = byte pitch of dim i+1.
+// swizzle_bytes in {0, 32, 64, 128}.  Returns 0 or an error code (message in g_err).
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
+inline size_t dtype_bytes(int dt) { return dt == MA3_F32 ? 4 : 2; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace ma3
