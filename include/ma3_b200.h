@@ -52,13 +52,13 @@ const char* ma3_last_error(void);
  * torch.nn.Conv1d in autoencoder1d.py:176-295,415-517; Conv1d/ConvTranspose1d in vocoder/bigvgan/models.py:32-205.
  *
  * Epilogues (`epi`):
- *   MA3_EPI_STORE      v = acc (+ bias[n] or bias[m]) (+ res[z,m,n]) ; v *= alpha ; (+ out_old if accumulate) -> out
+ *   MA3_EPI_STORE      v = acc (+ bias[n] or bias[m]) (+ res[z,m,n]) ; v = act(alpha*v) ; (+ out_old if accumulate) -> out
  *                      out row = m*out_row_mul + out_row_off (strided rows: transposed-conv phases)
  *   MA3_EPI_GATE_RES   out(f32)[m,n] += gate[(m / rows_per_sample), n] * acc        (flag_large_dit.py:83-91)
  *   MA3_EPI_SWIGLU     out[m, n/2] = silu(acc[m, n]) * acc[m, n+1], n even         (flag_large_dit_moe.py:484-489;
  *                      w1 rows interleaved with w3 rows in B)
  *   MA3_EPI_QKV_ROPE   columns [0,D) q, [D,2D) k, [2D,3D) v of one fused projection; rotary embedding on q,k
- *                      (flag_large_dit_moe.py:240-271), q pre-multiplied by q_scale; scatter to
+ *                      (flag_large_dit_moe.py:240-271; rope == NULL: no rotation), q pre-multiplied by q_scale; scatter to
  *                      q,k: [sample, head, t, hd_pad]   v: [sample, head, hd_pad, t_pad] (transposed)
  * ------------------------------------------------------------------------------------------------------------------ */
 #define MA3_EPI_STORE 0
@@ -92,6 +92,7 @@ typedef struct ma3_gemm {
   int32_t res_dtype;
   int64_t res_ld, res_batch_stride;
   float alpha;
+  int32_t act;            /* STORE: activation after alpha: 0 none, 1 SiLU, 2 GELU(erf), 3 tanh */
   int32_t accumulate;     /* 1: add previous contents of out */
   /* GATE_RES */
   const float* gate;      /* [samples][gate_ld] fp32 */
@@ -102,6 +103,7 @@ typedef struct ma3_gemm {
   const float* rope;      /* [T_max][hd/2][2] (cos, sin) fp32 */
   int32_t model_dim, head_dim, head_dim_pad, tokens, tokens_pad;
   float q_scale;
+  int32_t first_section;  /* 0: columns are q|k|v (N = 3*model_dim); 1: k|v only (cross K/V, N = 2*model_dim) */
   /* tiling override: 0 = library heuristic */
   int32_t tile_n;
 } ma3_gemm_t;

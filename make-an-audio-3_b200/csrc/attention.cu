@@ -1,0 +1,329 @@
+// Flash attention for the Next-DiT block on tcgen05: self-attention over the T latent tokens plus gated
+// cross-attention over the L context tokens in ONE launch, sharing the rotary-embedded Q tile:
+//     out = softmax(q k^T) v  +  tanh(gate_h) * softmax(q ky^T) vy
+// (flag_large_dit_moe.py:382-406; q is pre-multiplied by log2(e)/sqrt(hd) in the QKV GEMM epilogue, q and k already
+// carry RoPE; the all-ones masks of the reference are dropped).
+//
+// CTA = (128-query tile, head, sample).  Warp 4 (one elected lane) feeds TMA and issues the MMAs
+// S = Q K^T  and  O_tile = P V  into TMEM; warps 0-3 (thread <-> query row <-> TMEM lane) run the online softmax,
+// write P (bf16) into shared memory in the 128B-swizzled K-major layout the tensor core reads, and accumulate the
+// O tiles in registers with the usual rescaling.  K / V^T tiles stream through a 2-stage TMA ring.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace ma3 {
+
+constexpr int kAttnThreads = 160;
+
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmVt, tmKy, tmVyt;
+  int T, L, H, D;  // D = H * hd (row pitch of out)
+  void* out;
+  const float* gate;
+  int dtype;
+};
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t addr, uint32_t* r);
+template <>
+__device__ __forceinline__ void tmem_ld_n<32>(uint32_t addr, uint32_t* r) { tmem_ld32(addr, *reinterpret_cast<uint32_t(*)[32]>(r)); }
+template <>
+__device__ __forceinline__ void tmem_ld_n<16>(uint32_t addr, uint32_t* r) { tmem_ld16(addr, *reinterpret_cast<uint32_t(*)[16]>(r)); }
+template <>
+__device__ __forceinline__ void tmem_ld_n<8>(uint32_t addr, uint32_t* r) { tmem_ld8(addr, *reinterpret_cast<uint32_t(*)[8]>(r)); }
+
+// acc[0..HD) = acc * alpha + O_tile(row)  reading HD fp32 columns in pieces of 32 / 16 / 8
+template <int HD, int OFF = 0>
+__device__ __forceinline__ void accumulate_o(uint32_t taddr, float (&acc)[HD], float alpha) {
+  if constexpr (OFF < HD) {
+    constexpr int W = (HD - OFF >= 32) ? 32 : ((HD - OFF >= 16) ? 16 : 8);
+    uint32_t r[W];
+    tmem_ld_n<W>(taddr + OFF, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < W; ++e) acc[OFF + e] = fmaf(acc[OFF + e], alpha, __uint_as_float(r[e]));
+    accumulate_o<HD, OFF + W>(taddr, acc, alpha);
+  }
+}
+
+template <int HDP, int HD, int BKV>
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int HDC = HDP / 64;              // 64-element chunks along head dim
+  constexpr int KVC = BKV / 64;              // 64-key chunks per KV tile
+  constexpr uint32_t kQBytes = 128 * HDP * 2;
+  constexpr uint32_t kKBytes = BKV * HDP * 2;
+  constexpr uint32_t kStageBytes = 2 * kKBytes;  // K tile + V^T tile
+  constexpr uint32_t kPBytes = 128 * BKV * 2;
+  constexpr uint32_t kTmemCols = 256;        // S: [0, BKV)  O: [BKV, BKV + HDP)
+  static_assert(BKV + HDP <= 256, "TMEM budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = sm;
+  uint8_t* sKV = sQ + kQBytes;
+  uint8_t* sP = sKV + 2 * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* kv_full = bars + 1;     // 2
+  uint64_t* kv_empty = bars + 3;    // 2
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, ns = blockIdx.z;
+  const int bh = ns * p.H + h;
+  const int n_self = (p.T + BKV - 1) / BKV, n_cross = (p.L + BKV - 1) / BKV;
+  const int n_tiles = n_self + n_cross;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmVt);
+      prefetch_tmap(&p.tmKy); prefetch_tmap(&p.tmVyt);
+      mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+      mbar_init(s_full, 1);
+      mbar_init(p_full, 128);
+      mbar_init(o_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + BKV;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      auto load_kv = [&](int i) {
+        const int st = i & 1;
+        const bool cross = i >= n_self;
+        const int kv0 = (cross ? i - n_self : i) * BKV;
+        uint8_t* dK = sKV + st * kStageBytes;
+        uint8_t* dV = dK + kKBytes;
+        mbar_arrive_expect_tx(&kv_full[st], kStageBytes);
+#pragma unroll
+        for (int c = 0; c < HDC; ++c)
+          tma_load_3d(dK + c * (BKV * 128), cross ? &p.tmKy : &p.tmK, &kv_full[st], c * 64, kv0, bh);
+#pragma unroll
+        for (int c = 0; c < KVC; ++c)
+          tma_load_3d(dV + c * (HDP * 128), cross ? &p.tmVyt : &p.tmVt, &kv_full[st], kv0 + c * 64, 0, bh);
+      };
+      const uint32_t idesc_s = umma_idesc(128, BKV, p.dtype == MA3_BF16 ? 1 : 0);
+      const uint32_t idesc_o = umma_idesc(128, HDP, p.dtype == MA3_BF16 ? 1 : 0);
+      auto issue_s = [&](int i) {
+        const int st = i & 1;
+        mbar_wait(&kv_full[st], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sKV + st * kStageBytes);
+#pragma unroll
+        for (int k = 0; k < HDP / 16; ++k) {
+          const uint64_t da = umma_desc_kmajor(qa + (k / 4) * (128 * 128) + (k % 4) * 32, 128);
+          const uint64_t db = umma_desc_kmajor(ka + (k / 4) * (BKV * 128) + (k % 4) * 32, 128);
+          umma_f16(tmem_S, da, db, idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+      };
+
+      mbar_arrive_expect_tx(q_full, kQBytes);
+#pragma unroll
+      for (int c = 0; c < HDC; ++c) tma_load_3d(sQ + c * (128 * 128), &p.tmQ, q_full, c * 64, q0, bh);
+      load_kv(0);
+      if (n_tiles > 1) load_kv(1);
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int st = i & 1;
+        mbar_wait(p_full, i & 1);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP), va = smem_u32(sKV + st * kStageBytes + kKBytes);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint64_t da = umma_desc_kmajor(pa + (k / 4) * (128 * 128) + (k % 4) * 32, 128);
+          const uint64_t db = umma_desc_kmajor(va + (k / 4) * (HDP * 128) + (k % 4) * 32, 128);
+          umma_f16(tmem_O, da, db, idesc_o, k != 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+        if (i + 1 < n_tiles) issue_s(i + 1);
+        if (i + 2 < n_tiles) {
+          mbar_wait(&kv_empty[st], (i >> 1) & 1);
+          load_kv(i + 2);
+        }
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float tot[HD];
+#pragma unroll
+    for (int e = 0; e < HD; ++e) tot[e] = 0.f;
+    int it = 0;
+    for (int seg = 0; seg < 2; ++seg) {
+      const int ntl = seg ? n_cross : n_self;
+      const int kvlen = seg ? p.L : p.T;
+      if (ntl == 0) continue;
+      float acc[HD];
+#pragma unroll
+      for (int e = 0; e < HD; ++e) acc[e] = 0.f;
+      float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+      for (int j = 0; j < ntl; ++j, ++it) {
+        mbar_wait(s_full, it & 1);
+        tc_fence_after();
+        const int kv0 = j * BKV;
+        float mx = m;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BKV; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_S + lane_base + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float v = (kv0 + c0 + e < kvlen) ? __uint_as_float(r[e]) : -INFINITY;
+            mx = fmaxf(mx, v);
+          }
+        }
+        const float alpha = exp2f(m - mx);
+        if (j > 0) {
+          mbar_wait(o_full, (it - 1) & 1);
+          tc_fence_after();
+          accumulate_o<HD>(tmem_O + lane_base, acc, alpha_prev);
+        }
+        float rowsum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BKV; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_S + lane_base + c0, r);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = (kv0 + c0 + e < kvlen) ? exp2f(__uint_as_float(r[e]) - mx) : 0.f;
+            const float p1 = (kv0 + c0 + e + 1 < kvlen) ? exp2f(__uint_as_float(r[e + 1]) - mx) : 0.f;
+            rowsum += p0 + p1;
+            pk[e >> 1] = (p.dtype == MA3_BF16) ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+          }
+          // 32 keys = 64 B = four 16-byte units of this row inside the 64-key chunk (128 B per row)
+          uint8_t* chunk = sP + (c0 >> 6) * (128 * 128) + row * 128;
+          const int u0 = (c0 & 63) >> 3;  // first 16-byte unit
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int pos = (u0 + u) ^ (row & 7);
+            *reinterpret_cast<uint4*>(chunk + pos * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          }
+        }
+        l = l * alpha + rowsum;
+        m = mx;
+        alpha_prev = alpha;
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(p_full);
+      }
+      mbar_wait(o_full, (it - 1) & 1);
+      tc_fence_after();
+      accumulate_o<HD>(tmem_O + lane_base, acc, alpha_prev);
+      const float f = (seg ? tanhf(p.gate[h]) : 1.f) / l;
+#pragma unroll
+      for (int e = 0; e < HD; ++e) tot[e] = fmaf(acc[e], f, tot[e]);
+    }
+    if (q0 + row < p.T) {
+      const long long o = ((long long)ns * p.T + q0 + row) * p.D + (long long)h * HD;
+#pragma unroll
+      for (int e = 0; e < HD; e += 8) {
+        uint4 u;
+        if (p.dtype == MA3_BF16)
+          u = make_uint4(pack_bf16(tot[e], tot[e + 1]), pack_bf16(tot[e + 2], tot[e + 3]),
+                         pack_bf16(tot[e + 4], tot[e + 5]), pack_bf16(tot[e + 6], tot[e + 7]));
+        else
+          u = make_uint4(pack_f16(tot[e], tot[e + 1]), pack_f16(tot[e + 2], tot[e + 3]),
+                         pack_f16(tot[e + 4], tot[e + 5]), pack_f16(tot[e + 6], tot[e + 7]));
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + o + e) = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int HDP, int HD, int BKV>
+static int launch_attn(const AttnParams& p, int NS, cudaStream_t st) {
+  constexpr size_t smem = 1024 + 128 * HDP * 2 + 2 * (2 * BKV * HDP * 2) + 128 * BKV * 2 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<HDP, HD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid((unsigned)((p.T + 127) / 128), (unsigned)p.H, (unsigned)NS);
+  attn_kernel<HDP, HD, BKV><<<grid, kAttnThreads, smem, st>>>(p);
+  MA3_LAUNCH_CHECK("attention");
+  return 0;
+}
+
+}  // namespace ma3
+
+using namespace ma3;
+
+// q, k: [NS*H, T, hdp]; vt: [NS*H, hdp, Tp]; ky: [NS*H, L, hdp]; vyt: [NS*H, hdp, Lp]; gate: [H] fp32 (raw, tanh is
+// applied here); out: [NS, T, H*hd] (16-bit, same dtype as the operands).
+extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const void* ky, const void* vyt,
+                             const float* gate, void* out, int dtype, int NS, int H, int T, int Tp, int L, int Lp,
+                             int hd, int hdp, void* stream) {
+  MA3_REQUIRE(q && k && vt && out, "attention: null pointer");
+  MA3_REQUIRE(dtype == MA3_BF16 || dtype == MA3_F16, "attention: 16-bit operands only");
+  MA3_REQUIRE(NS > 0 && H > 0 && T > 0 && L >= 0, "attention: empty problem");
+  MA3_REQUIRE(L == 0 || (ky && vyt && gate), "attention: cross operands required when L > 0");
+  MA3_REQUIRE(Tp % 8 == 0 && Tp >= T && (L == 0 || (Lp % 8 == 0 && Lp >= L)), "attention: padded lengths must be multiples of 8");
+  MA3_REQUIRE(hd % 8 == 0 && (hdp == 64 || hdp == 128) && hdp >= hd, "attention: hd %% 8 == 0 and hd_pad in {64,128}");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = T; p.L = L; p.H = H; p.D = H * hd; p.out = out; p.gate = gate; p.dtype = dtype;
+  const int BKV = hdp == 64 ? 128 : 64;
+  const uint64_t nbh = (uint64_t)NS * H;
+  int rc;
+  {
+    uint64_t dims[3] = {(uint64_t)hdp, (uint64_t)T, nbh};
+    uint64_t str[2] = {(uint64_t)hdp * 2, (uint64_t)T * hdp * 2};
+    uint32_t boxq[3] = {64, 128, 1}, boxk[3] = {64, (uint32_t)BKV, 1};
+    if ((rc = encode_tmap(&p.tmQ, q, 2, 3, dims, str, boxq, 128))) return rc;
+    if ((rc = encode_tmap(&p.tmK, k, 2, 3, dims, str, boxk, 128))) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)T, (uint64_t)hdp, nbh};
+    uint64_t str[2] = {(uint64_t)Tp * 2, (uint64_t)hdp * Tp * 2};
+    uint32_t box[3] = {64, (uint32_t)hdp, 1};
+    if ((rc = encode_tmap(&p.tmVt, vt, 2, 3, dims, str, box, 128))) return rc;
+  }
+  if (L > 0) {
+    uint64_t dims[3] = {(uint64_t)hdp, (uint64_t)L, nbh};
+    uint64_t str[2] = {(uint64_t)hdp * 2, (uint64_t)L * hdp * 2};
+    uint32_t boxk[3] = {64, (uint32_t)BKV, 1};
+    if ((rc = encode_tmap(&p.tmKy, ky, 2, 3, dims, str, boxk, 128))) return rc;
+    uint64_t dimv[3] = {(uint64_t)L, (uint64_t)hdp, nbh};
+    uint64_t strv[2] = {(uint64_t)Lp * 2, (uint64_t)hdp * Lp * 2};
+    uint32_t boxv[3] = {64, (uint32_t)hdp, 1};
+    if ((rc = encode_tmap(&p.tmVyt, vyt, 2, 3, dimv, strv, boxv, 128))) return rc;
+  } else {
+    p.tmKy = p.tmK;
+    p.tmVyt = p.tmVt;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (hdp == 64 && hd == 24) return launch_attn<64, 24, 128>(p, NS, st);
+  if (hdp == 64 && hd == 16) return launch_attn<64, 16, 128>(p, NS, st);
+  if (hdp == 64 && hd == 32) return launch_attn<64, 32, 128>(p, NS, st);
+  if (hdp == 64 && hd == 48) return launch_attn<64, 48, 128>(p, NS, st);
+  if (hdp == 64 && hd == 64) return launch_attn<64, 64, 128>(p, NS, st);
+  if (hdp == 128 && hd == 72) return launch_attn<128, 72, 64>(p, NS, st);
+  if (hdp == 128 && hd == 96) return launch_attn<128, 96, 64>(p, NS, st);
+  if (hdp == 128 && hd == 128) return launch_attn<128, 128, 64>(p, NS, st);
+  MA3_FAIL(MA3_EINVAL, "attention: head_dim %d (pad %d) not instantiated", hd, hdp);
+}

@@ -1,0 +1,599 @@
+// HBM-bound kernels of the sampling path: adaLN-modulated RMSNorm, final layer (+ fused CFG combine and Euler
+// update), latent projection, conditioning pool + LayerNorm, timestep embedding, GroupNorm+swish, row softmax,
+// layout changes.  All are judged by achieved HBM GB/s; see include/ma3_b200.h for the reference lines.
+#include "host_common.h"
+#include "ptx.cuh"
+
+#include <type_traits>
+
+namespace ma3 {
+
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+  static __device__ __forceinline__ float to(float v) { return v; }
+  static __device__ __forceinline__ float from(float v) { return v; }
+};
+template <> struct Cvt<__nv_bfloat16> {
+  static __device__ __forceinline__ __nv_bfloat16 to(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ float from(__nv_bfloat16 v) { return __bfloat162float(v); }
+};
+template <> struct Cvt<__half> {
+  static __device__ __forceinline__ __half to(float v) { return __float2half_rn(v); }
+  static __device__ __forceinline__ float from(__half v) { return __half2float(v); }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = lane < nw ? red[lane] : 0.f;
+  return warp_sum(t);
+}
+
+// ---------------------------------------------------------------------------------------- rmsnorm + modulate
+// out[m, :] = rms(x[m, :]) * w * (1 + scale[sample]) + shift[sample]     (one warp per row, row cached in registers)
+constexpr int kMaxVecPerLane = 16;  // D <= 2048
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ mod, long long mod_ld,
+                                                               int shift_off, int scale_off, int rows_per_sample,
+                                                               TOut* __restrict__ out, int M, int D, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+  const int nvec = D >> 2;
+  float4 v[kMaxVecPerLane];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVecPerLane; ++i) {
+    const int j = i * 32 + lane;
+    if (j < nvec) {
+      v[i] = xr[j];
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+  ss = warp_sum(ss);
+  const float r = rsqrtf(ss / (float)D + eps);
+  const float* sc = nullptr;
+  const float* sh = nullptr;
+  if (mod) {
+    const long long base = (long long)(row / rows_per_sample) * mod_ld;
+    sc = mod + base + scale_off;
+    sh = mod + base + shift_off;
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxVecPerLane; ++i) {
+    const int j = i * 32 + lane;
+    if (j < nvec) {
+      float4 a = v[i];
+      a.x *= r; a.y *= r; a.z *= r; a.w *= r;
+      if (w) {
+        const float4 ww = reinterpret_cast<const float4*>(w)[j];
+        a.x *= ww.x; a.y *= ww.y; a.z *= ww.z; a.w *= ww.w;
+      }
+      if (mod) {
+        const float4 s1 = reinterpret_cast<const float4*>(sc)[j];
+        const float4 s0 = reinterpret_cast<const float4*>(sh)[j];
+        a.x = a.x * (1.f + s1.x) + s0.x; a.y = a.y * (1.f + s1.y) + s0.y;
+        a.z = a.z * (1.f + s1.z) + s0.z; a.w = a.w * (1.f + s1.w) + s0.w;
+      }
+      TOut* o = out + (long long)row * D + j * 4;
+      if constexpr (sizeof(TOut) == 2) {
+        uint2 u;
+        if constexpr (std::is_same<TOut, __nv_bfloat16>::value) {
+          u.x = pack_bf16(a.x, a.y); u.y = pack_bf16(a.z, a.w);
+        } else {
+          u.x = pack_f16(a.x, a.y); u.y = pack_f16(a.z, a.w);
+        }
+        *reinterpret_cast<uint2*>(o) = u;
+      } else {
+        *reinterpret_cast<float4*>(o) = a;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- final layer
+// LayerNorm(no affine, eps) -> modulate -> Linear(D -> Cout) ; output transposed to [N, Cout, T].
+// kCfg: rows come in (uncond n, cond n+B) pairs; the guided velocity v = vu + s (vc - vu) is formed in-kernel and
+// the Euler update x <- x + dt v applied (cfm1_audio.py:154-161 + torchdyn Euler), so no velocity round trip.
+constexpr int kMaxCout = 32;
+
+__device__ __forceinline__ void final_row(const float* __restrict__ hrow, const float* __restrict__ sc,
+                                          const float* __restrict__ sh, const float* __restrict__ W,
+                                          const float* __restrict__ bias, int D, int Cout, float eps, int lane,
+                                          float& result) {
+  // returns in `result` the output channel `lane` (valid for lane < Cout); the normalised row lives in registers
+  constexpr int kMaxPerLane = 64;  // D <= 2048
+  float xn[kMaxPerLane];
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int j = i * 32 + lane;
+    xn[i] = j < D ? hrow[j] : 0.f;
+    s += xn[i];
+    s2 += xn[i] * xn[i];
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  const float mean = s / (float)D;
+  const float rstd = rsqrtf(fmaxf(s2 / (float)D - mean * mean, 0.f) + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int j = i * 32 + lane;
+    xn[i] = j < D ? (xn[i] - mean) * rstd * (1.f + sc[j]) + sh[j] : 0.f;
+  }
+  float mine = 0.f;
+  for (int c = 0; c < Cout; ++c) {
+    const float* wr = W + (long long)c * D;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int j = i * 32 + lane;
+      if (j < D) acc += xn[i] * wr[j];
+    }
+    acc = warp_sum(acc);
+    if (lane == c) mine = acc + bias[c];
+  }
+  result = mine;
+}
+
+template <bool kCfg>
+__global__ void __launch_bounds__(256) final_layer_kernel(const float* __restrict__ h, const float* __restrict__ mod,
+                                                          long long mod_ld, int shift_off, int scale_off,
+                                                          const float* __restrict__ W, const float* __restrict__ bias,
+                                                          int N, int T, int D, int Cout, float eps,
+                                                          float* __restrict__ v_out,  // [N or B, Cout, T] (nullable if kCfg)
+                                                          const float* __restrict__ x_in, float* __restrict__ x_out,
+                                                          float dt, float guidance) {
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if constexpr (!kCfg) {
+    if (wid >= N * T) return;
+    const int n = wid / T, t = wid - n * T;
+    float r;
+    final_row(h + (long long)wid * D, mod + (long long)n * mod_ld + scale_off, mod + (long long)n * mod_ld + shift_off,
+              W, bias, D, Cout, eps, lane, r);
+    if (lane < Cout) v_out[((long long)n * Cout + lane) * T + t] = r;
+  } else {
+    const int B = N >> 1;
+    if (wid >= B * T) return;
+    const int b = wid / T, t = wid - b * T;
+    float ru, rc;
+    final_row(h + (long long)wid * D, mod + (long long)b * mod_ld + scale_off, mod + (long long)b * mod_ld + shift_off,
+              W, bias, D, Cout, eps, lane, ru);
+    const int nc = b + B;
+    final_row(h + ((long long)nc * T + t) * D, mod + (long long)nc * mod_ld + scale_off,
+              mod + (long long)nc * mod_ld + shift_off, W, bias, D, Cout, eps, lane, rc);
+    if (lane < Cout) {
+      const float vg = ru + guidance * (rc - ru);
+      const long long idx = ((long long)b * Cout + lane) * T + t;
+      if (v_out) v_out[idx] = vg;
+      if (x_out) x_out[idx] = x_in[idx] + dt * vg;
+    }
+  }
+}
+
+// x <- x + dt * (vu + s (vc - vu)) as a stand-alone elementwise kernel (drop-in forward() path).
+__global__ void cfg_euler_kernel(const float* __restrict__ v, const float* __restrict__ x, float* __restrict__ out,
+                                 long long half_elems, float dt, float guidance, int cfg) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= half_elems) return;
+  float vg;
+  if (cfg) {
+    const float vu = v[i], vc = v[i + half_elems];
+    vg = vu + guidance * (vc - vu);
+  } else {
+    vg = v[i];
+  }
+  out[i] = x[i] + dt * vg;
+}
+
+// ---------------------------------------------------------------------------------------- proj_in
+// h[n*T + t, d] = sum_c x[n, c, t] * W[d, c] + b[d]      (flag_large_dit.py:186-187); x row n % x_batch (CFG halves
+// share x).
+__global__ void proj_in_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+                               float* __restrict__ h, int N, int xB, int C, int T, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * T * D) return;
+  const int d = (int)(i % D);
+  const long long row = i / D;
+  const int t = (int)(row % T);
+  const int n = (int)(row / T) % xB;
+  const float* xr = x + (long long)n * C * T + t;
+  const float* wr = W + (long long)d * C;
+  float acc = b[d];
+  for (int c = 0; c < C; ++c) acc += xr[(long long)c * T] * wr[c];
+  h[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------- timestep embedding
+// out[m, 0:half] = cos(t f_i), out[m, half:] = sin(t f_i), f_i = exp(-ln(max_period) i / half)
+// (flag_large_dit_moe.py:110-127).  Accurate sincosf: arguments reach 1000 rad.
+template <typename TOut>
+__global__ void timestep_embed_kernel(const long long* __restrict__ t, TOut* __restrict__ out, int M, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim >> 1;
+  if (i >= M * half) return;
+  const int m = i / half, j = i - m * half;
+  const float f = expf(-logf(10000.f) * (float)j / (float)half);
+  const float a = (float)t[m] * f;
+  float s, c;
+  sincosf(a, &s, &c);
+  out[(long long)m * dim + j] = Cvt<TOut>::to(c);
+  out[(long long)m * dim + half + j] = Cvt<TOut>::to(s);
+}
+
+// ---------------------------------------------------------------------------------------- pool + LayerNorm
+// out[n, :] = LayerNorm_affine(mean_L(ctx[n, :, :]))    (flag_large_dit.py:193-198); one block per sample.
+// TIn: fp32 context, or the 16-bit embedded context of the video variant.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) pool_layernorm_kernel(const TIn* __restrict__ ctx, const float* __restrict__ w,
+                                                             const float* __restrict__ b, TOut* __restrict__ out,
+                                                             int L, int Cd, float eps) {
+  extern __shared__ float pooled[];
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  const TIn* base = ctx + (long long)n * L * Cd;
+  float s = 0.f, s2 = 0.f;
+  for (int c = threadIdx.x; c < Cd; c += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < L; ++l) acc += Cvt<TIn>::from(base[(long long)l * Cd + c]);
+    acc /= (float)L;
+    pooled[c] = acc;
+    s += acc;
+  }
+  const float mean = block_sum(s, red) / (float)Cd;
+  for (int c = threadIdx.x; c < Cd; c += blockDim.x) {
+    const float d = pooled[c] - mean;
+    s2 += d * d;
+  }
+  const float var = block_sum(s2, red) / (float)Cd;
+  const float rstd = rsqrtf(var + eps);
+  for (int c = threadIdx.x; c < Cd; c += blockDim.x)
+    out[(long long)n * Cd + c] = Cvt<TOut>::to((pooled[c] - mean) * rstd * w[c] + b[c]);
+}
+
+// Row LayerNorm with affine (the ConditionEmbedder's trailing nn.LayerNorm, flag_large_dit_moe.py:151-162).
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ b, TOut* __restrict__ out,
+                                                             int M, int D, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const TIn* xr = x + (long long)row * D;
+  float s = 0.f;
+  for (int j = lane; j < D; j += 32) s += Cvt<TIn>::from(xr[j]);
+  const float mean = warp_sum(s) / (float)D;
+  float s2 = 0.f;
+  for (int j = lane; j < D; j += 32) {
+    const float d = Cvt<TIn>::from(xr[j]) - mean;
+    s2 += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(s2) / (float)D + eps);
+  for (int j = lane; j < D; j += 32)
+    out[(long long)row * D + j] = Cvt<TOut>::to((Cvt<TIn>::from(xr[j]) - mean) * rstd * w[j] + b[j]);
+}
+
+// ---------------------------------------------------------------------------------------- GroupNorm (+ swish)
+// channels-last x[B, T, C]; one block per (b, group).  autoencoder1d.py:169-175 (eps 1e-6, affine, swish = x*sigmoid).
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(512) groupnorm_swish_kernel(const TIn* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ b, TOut* __restrict__ out,
+                                                              int T, int C, int groups, float eps, int swish) {
+  __shared__ float red[32];
+  const int cg = C / groups;
+  const int bidx = blockIdx.x / groups, g = blockIdx.x - bidx * groups;
+  const TIn* xb = x + (long long)bidx * T * C + g * cg;
+  TOut* ob = out + (long long)bidx * T * C + g * cg;
+  const int n = T * cg;
+  float s = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int t = i / cg, c = i - t * cg;
+    const float v = Cvt<TIn>::from(xb[(long long)t * C + c]);
+    s += v;
+    s2 += v * v;
+  }
+  s = block_sum(s, red);
+  s2 = block_sum(s2, red);
+  const float mean = s / (float)n;
+  const float rstd = rsqrtf(fmaxf(s2 / (float)n - mean * mean, 0.f) + eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int t = i / cg, c = i - t * cg;
+    float v = (Cvt<TIn>::from(xb[(long long)t * C + c]) - mean) * rstd * w[g * cg + c] + b[g * cg + c];
+    if (swish) v = v / (1.f + __expf(-v));
+    ob[(long long)t * C + c] = Cvt<TOut>::to(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- row softmax
+// P[z, i, 0:n] = softmax(scale * S[z, i, 0:n]); P[z, i, n:ld_out] = 0     (autoencoder1d.py:265-270)
+template <typename TOut>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, TOut* __restrict__ P, int rows,
+                                                           int n, long long ld_in, long long ld_out, float scale) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* s = S + (long long)row * ld_in;
+  float mx = -INFINITY;
+  for (int j = lane; j < n; j += 32) mx = fmaxf(mx, s[j] * scale);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < n; j += 32) sum += __expf(s[j] * scale - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  TOut* p = P + (long long)row * ld_out;
+  for (int j = lane; j < ld_out; j += 32) p[j] = Cvt<TOut>::to(j < n ? __expf(s[j] * scale - mx) * inv : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------- layout changes
+// [B, C, T] fp32 -> [B, T, Cp] 16-bit, scaled, zero-padded channels (latent z / mel in)
+template <typename TOut>
+__global__ void nct_to_ntc_kernel(const float* __restrict__ x, TOut* __restrict__ out, int B, int C, int T, int Cp,
+                                  float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * T * Cp) return;
+  const int c = (int)(i % Cp);
+  const long long r = i / Cp;
+  const int t = (int)(r % T), b = (int)(r / T);
+  out[i] = Cvt<TOut>::to(c < C ? x[((long long)b * C + c) * T + t] * scale : 0.f);
+}
+
+// [B, T, ld] (first C channels) -> [B, C, T] fp32 (mel out)
+template <typename TIn>
+__global__ void ntc_to_nct_kernel(const TIn* __restrict__ x, float* __restrict__ out, int B, int C, int T, long long ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * C * T) return;
+  const int t = (int)(i % T);
+  const long long r = i / T;
+  const int c = (int)(r % C), b = (int)(r / C);
+  out[i] = Cvt<TIn>::from(x[((long long)b * T + t) * ld + c]);
+}
+
+// nearest x2 along T on channels-last 16-bit data (autoencoder1d.py:291-292), 16-byte vectors
+__global__ void upsample2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long long rows, int vec_per_row) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 2 * vec_per_row) return;
+  const int v = (int)(i % vec_per_row);
+  const long long orow = i / vec_per_row;
+  out[i] = x[(orow >> 1) * vec_per_row + v];
+}
+
+template <typename TIn, typename TOut>
+__global__ void cast_kernel(const TIn* __restrict__ x, TOut* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = Cvt<TOut>::to(Cvt<TIn>::from(x[i]));
+}
+
+}  // namespace ma3
+
+using namespace ma3;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+static inline unsigned nblk(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+extern "C" {
+
+int ma3_rmsnorm_modulate(const float* x, const float* w, const float* mod, int64_t mod_ld, int shift_off,
+                         int scale_off, int rows_per_sample, void* out, int out_dtype, int M, int D, float eps,
+                         void* stream) {
+  MA3_REQUIRE(x && out && M > 0, "rmsnorm_modulate: null pointer or empty");
+  MA3_REQUIRE(D % 4 == 0 && D <= 128 * kMaxVecPerLane, "rmsnorm_modulate: D=%d must be a multiple of 4 and <= 2048", D);
+  MA3_REQUIRE(!mod || (rows_per_sample > 0 && mod_ld % 4 == 0 && shift_off % 4 == 0 && scale_off % 4 == 0),
+              "rmsnorm_modulate: modulation offsets must be multiples of 4");
+  MA3_REQUIRE(aligned16(x) && aligned16(out) && (!w || aligned16(w)) && (!mod || aligned16(mod)),
+              "rmsnorm_modulate: pointers must be 16-byte aligned");
+  const unsigned grid = nblk(M, 8);
+  if (out_dtype == MA3_BF16)
+    rmsnorm_modulate_kernel<__nv_bfloat16><<<grid, 256, 0, ST(stream)>>>(x, w, mod, mod_ld, shift_off, scale_off,
+                                                                        rows_per_sample, (__nv_bfloat16*)out, M, D, eps);
+  else if (out_dtype == MA3_F16)
+    rmsnorm_modulate_kernel<__half><<<grid, 256, 0, ST(stream)>>>(x, w, mod, mod_ld, shift_off, scale_off,
+                                                                 rows_per_sample, (__half*)out, M, D, eps);
+  else
+    rmsnorm_modulate_kernel<float><<<grid, 256, 0, ST(stream)>>>(x, w, mod, mod_ld, shift_off, scale_off,
+                                                                rows_per_sample, (float*)out, M, D, eps);
+  MA3_LAUNCH_CHECK("rmsnorm_modulate");
+  return 0;
+}
+
+int ma3_final_layer(const float* h, const float* mod, int64_t mod_ld, int shift_off, int scale_off, const float* W,
+                    const float* bias, int N, int T, int D, int Cout, float eps, float* v_out, void* stream) {
+  MA3_REQUIRE(h && mod && W && bias && v_out, "final_layer: null pointer");
+  MA3_REQUIRE(Cout <= kMaxCout && N > 0 && T > 0 && D <= 2048, "final_layer: Cout=%d must be <= 32, D <= 2048", Cout);
+  final_layer_kernel<false><<<nblk((long long)N * T, 8), 256, 0, ST(stream)>>>(
+      h, mod, mod_ld, shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, nullptr, nullptr, 0.f, 0.f);
+  MA3_LAUNCH_CHECK("final_layer");
+  return 0;
+}
+
+int ma3_final_layer_cfg_euler(const float* h, const float* mod, int64_t mod_ld, int shift_off, int scale_off,
+                              const float* W, const float* bias, int N, int T, int D, int Cout, float eps,
+                              float guidance, float dt, const float* x_in, float* x_out, float* v_out,
+                              void* stream) {
+  MA3_REQUIRE(h && mod && W && bias && x_in && x_out, "final_layer_cfg_euler: null pointer");
+  MA3_REQUIRE(Cout <= kMaxCout && N > 0 && N % 2 == 0 && T > 0 && D <= 2048, "final_layer_cfg_euler: N must be even, Cout <= 32, D <= 2048");
+  final_layer_kernel<true><<<nblk((long long)(N / 2) * T, 8), 256, 0, ST(stream)>>>(
+      h, mod, mod_ld, shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, x_in, x_out, dt, guidance);
+  MA3_LAUNCH_CHECK("final_layer_cfg_euler");
+  return 0;
+}
+
+int ma3_cfg_euler_update(const float* v, const float* x, float* out, int64_t elems, float dt, float guidance, int cfg,
+                         void* stream) {
+  MA3_REQUIRE(v && x && out && elems > 0, "cfg_euler_update: null pointer or empty");
+  cfg_euler_kernel<<<nblk(elems, 256), 256, 0, ST(stream)>>>(v, x, out, elems, dt, guidance, cfg);
+  MA3_LAUNCH_CHECK("cfg_euler_update");
+  return 0;
+}
+
+int ma3_proj_in(const float* x, const float* W, const float* b, float* h, int N, int x_batch, int C, int T, int D,
+                void* stream) {
+  MA3_REQUIRE(x && W && b && h && N > 0 && x_batch > 0, "proj_in: null pointer or empty");
+  proj_in_kernel<<<nblk((long long)N * T * D, 256), 256, 0, ST(stream)>>>(x, W, b, h, N, x_batch, C, T, D);
+  MA3_LAUNCH_CHECK("proj_in");
+  return 0;
+}
+
+int ma3_timestep_embed(const int64_t* t, void* out, int out_dtype, int M, int dim, void* stream) {
+  MA3_REQUIRE(t && out && M > 0 && dim % 2 == 0, "timestep_embed: bad arguments");
+  const unsigned grid = nblk((long long)M * (dim / 2), 128);
+  if (out_dtype == MA3_BF16)
+    timestep_embed_kernel<__nv_bfloat16><<<grid, 128, 0, ST(stream)>>>((const long long*)t, (__nv_bfloat16*)out, M, dim);
+  else if (out_dtype == MA3_F32)
+    timestep_embed_kernel<float><<<grid, 128, 0, ST(stream)>>>((const long long*)t, (float*)out, M, dim);
+  else
+    MA3_FAIL(MA3_EINVAL, "timestep_embed: out dtype must be bf16 or f32");
+  MA3_LAUNCH_CHECK("timestep_embed");
+  return 0;
+}
+
+int ma3_pool_layernorm(const void* ctx, int in_dtype, const float* w, const float* b, void* out, int out_dtype, int N,
+                       int L, int Cd, float eps, void* stream) {
+  MA3_REQUIRE(ctx && w && b && out && N > 0 && L > 0 && Cd > 0, "pool_layernorm: bad arguments");
+  MA3_REQUIRE(out_dtype == MA3_BF16 && (in_dtype == MA3_F32 || in_dtype == MA3_BF16),
+              "pool_layernorm: in f32/bf16, out bf16 only");
+  const size_t smem = (size_t)Cd * sizeof(float);
+  if (in_dtype == MA3_F32)
+    pool_layernorm_kernel<float, __nv_bfloat16><<<N, 256, smem, ST(stream)>>>((const float*)ctx, w, b,
+                                                                               (__nv_bfloat16*)out, L, Cd, eps);
+  else
+    pool_layernorm_kernel<__nv_bfloat16, __nv_bfloat16><<<N, 256, smem, ST(stream)>>>(
+        (const __nv_bfloat16*)ctx, w, b, (__nv_bfloat16*)out, L, Cd, eps);
+  MA3_LAUNCH_CHECK("pool_layernorm");
+  return 0;
+}
+
+int ma3_layernorm_rows(const void* x, int in_dtype, const float* w, const float* b, void* out, int out_dtype, int M,
+                       int D, float eps, void* stream) {
+  MA3_REQUIRE(x && w && b && out && M > 0, "layernorm_rows: bad arguments");
+  MA3_REQUIRE(in_dtype == MA3_F32 && (out_dtype == MA3_F32 || out_dtype == MA3_BF16), "layernorm_rows: f32 in");
+  if (out_dtype == MA3_F32)
+    layernorm_rows_kernel<float, float><<<nblk(M, 8), 256, 0, ST(stream)>>>((const float*)x, w, b, (float*)out, M, D, eps);
+  else
+    layernorm_rows_kernel<float, __nv_bfloat16><<<nblk(M, 8), 256, 0, ST(stream)>>>((const float*)x, w, b,
+                                                                                   (__nv_bfloat16*)out, M, D, eps);
+  MA3_LAUNCH_CHECK("layernorm_rows");
+  return 0;
+}
+
+int ma3_groupnorm_swish(const void* x, int in_dtype, const float* w, const float* b, void* out, int out_dtype, int B,
+                        int T, int C, int groups, float eps, int swish, void* stream) {
+  MA3_REQUIRE(x && w && b && out && B > 0 && T > 0 && C % groups == 0, "groupnorm_swish: bad arguments");
+  const unsigned grid = (unsigned)(B * groups);
+#define GN_CASE(TI, TO) \
+  groupnorm_swish_kernel<TI, TO><<<grid, 512, 0, ST(stream)>>>((const TI*)x, w, b, (TO*)out, T, C, groups, eps, swish)
+  if (in_dtype == MA3_BF16 && out_dtype == MA3_BF16) GN_CASE(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == MA3_F32 && out_dtype == MA3_BF16) GN_CASE(float, __nv_bfloat16);
+  else if (in_dtype == MA3_F16 && out_dtype == MA3_F16) GN_CASE(__half, __half);
+  else if (in_dtype == MA3_F32 && out_dtype == MA3_F16) GN_CASE(float, __half);
+  else MA3_FAIL(MA3_EINVAL, "groupnorm_swish: unsupported dtype pair %d -> %d", in_dtype, out_dtype);
+#undef GN_CASE
+  MA3_LAUNCH_CHECK("groupnorm_swish");
+  return 0;
+}
+
+int ma3_softmax_rows(const float* S, void* P, int out_dtype, int rows, int n, int64_t ld_in, int64_t ld_out,
+                     float scale, void* stream) {
+  MA3_REQUIRE(S && P && rows > 0 && n > 0 && ld_out >= n, "softmax_rows: bad arguments");
+  if (out_dtype == MA3_BF16)
+    softmax_rows_kernel<__nv_bfloat16><<<nblk(rows, 8), 256, 0, ST(stream)>>>(S, (__nv_bfloat16*)P, rows, n, ld_in, ld_out, scale);
+  else if (out_dtype == MA3_F16)
+    softmax_rows_kernel<__half><<<nblk(rows, 8), 256, 0, ST(stream)>>>(S, (__half*)P, rows, n, ld_in, ld_out, scale);
+  else
+    MA3_FAIL(MA3_EINVAL, "softmax_rows: 16-bit output only");
+  MA3_LAUNCH_CHECK("softmax_rows");
+  return 0;
+}
+
+int ma3_nct_to_ntc(const float* x, void* out, int out_dtype, int B, int C, int T, int Cp, float scale, void* stream) {
+  MA3_REQUIRE(x && out && B > 0 && Cp >= C, "nct_to_ntc: bad arguments");
+  const unsigned grid = nblk((long long)B * T * Cp, 256);
+  if (out_dtype == MA3_BF16)
+    nct_to_ntc_kernel<__nv_bfloat16><<<grid, 256, 0, ST(stream)>>>(x, (__nv_bfloat16*)out, B, C, T, Cp, scale);
+  else if (out_dtype == MA3_F16)
+    nct_to_ntc_kernel<__half><<<grid, 256, 0, ST(stream)>>>(x, (__half*)out, B, C, T, Cp, scale);
+  else
+    MA3_FAIL(MA3_EINVAL, "nct_to_ntc: 16-bit output only");
+  MA3_LAUNCH_CHECK("nct_to_ntc");
+  return 0;
+}
+
+int ma3_ntc_to_nct(const void* x, int in_dtype, float* out, int B, int C, int T, int64_t ld, void* stream) {
+  MA3_REQUIRE(x && out && B > 0 && ld >= C, "ntc_to_nct: bad arguments");
+  const unsigned grid = nblk((long long)B * C * T, 256);
+  if (in_dtype == MA3_BF16)
+    ntc_to_nct_kernel<__nv_bfloat16><<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)x, out, B, C, T, ld);
+  else if (in_dtype == MA3_F16)
+    ntc_to_nct_kernel<__half><<<grid, 256, 0, ST(stream)>>>((const __half*)x, out, B, C, T, ld);
+  else
+    ntc_to_nct_kernel<float><<<grid, 256, 0, ST(stream)>>>((const float*)x, out, B, C, T, ld);
+  MA3_LAUNCH_CHECK("ntc_to_nct");
+  return 0;
+}
+
+int ma3_upsample_nearest2(const void* x, void* out, int64_t rows, int C, void* stream) {
+  MA3_REQUIRE(x && out && rows > 0 && C % 8 == 0 && aligned16(x) && aligned16(out), "upsample_nearest2: C %% 8, aligned");
+  upsample2_kernel<<<nblk(rows * 2 * (C / 8), 256), 256, 0, ST(stream)>>>((const uint4*)x, (uint4*)out, rows, C / 8);
+  MA3_LAUNCH_CHECK("upsample_nearest2");
+  return 0;
+}
+
+int ma3_cast(const void* x, int in_dtype, void* out, int out_dtype, int64_t n, void* stream) {
+  MA3_REQUIRE(x && out && n > 0, "cast: bad arguments");
+  const unsigned grid = nblk(n, 256);
+#define CAST_CASE(TI, TO) cast_kernel<TI, TO><<<grid, 256, 0, ST(stream)>>>((const TI*)x, (TO*)out, n)
+  if (in_dtype == MA3_F32 && out_dtype == MA3_BF16) CAST_CASE(float, __nv_bfloat16);
+  else if (in_dtype == MA3_F32 && out_dtype == MA3_F16) CAST_CASE(float, __half);
+  else if (in_dtype == MA3_BF16 && out_dtype == MA3_F32) CAST_CASE(__nv_bfloat16, float);
+  else if (in_dtype == MA3_F16 && out_dtype == MA3_F32) CAST_CASE(__half, float);
+  else MA3_FAIL(MA3_EINVAL, "cast: unsupported dtype pair");
+#undef CAST_CASE
+  MA3_LAUNCH_CHECK("cast");
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------- adaLN input
+// out[s*N + n, :] = silu(temb[s*ts_s + n*ts_n, :] + cap[n, :])  (flag_large_dit.py:200 then the SiLU of :50-51);
+// sampler: one timestep row per step (ts_s = 1, ts_n = 0); drop-in forward(): one row per sample (ts_s = 0, ts_n = 1).
+namespace ma3 {
+template <typename TOut>
+__global__ void adaln_input_kernel(const float* __restrict__ temb, const float* __restrict__ cap, TOut* __restrict__ out,
+                                   int S, int N, int D, int ts_s, int ts_n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)S * N * D) return;
+  const int d = (int)(i % D);
+  const long long r = i / D;
+  const int n = (int)(r % N), s = (int)(r / N);
+  const float a = temb[(long long)(s * ts_s + n * ts_n) * D + d] + cap[(long long)n * D + d];
+  out[i] = Cvt<TOut>::to(a / (1.f + __expf(-a)));
+}
+}  // namespace ma3
+
+extern "C" int ma3_adaln_input(const float* temb, const float* cap, void* out, int out_dtype, int S, int N, int D,
+                               int ts_s, int ts_n, void* stream) {
+  MA3_REQUIRE(temb && cap && out && S > 0 && N > 0 && D > 0, "adaln_input: bad arguments");
+  MA3_REQUIRE(out_dtype == MA3_BF16 || out_dtype == MA3_F16, "adaln_input: 16-bit output only");
+  const unsigned grid = nblk((long long)S * N * D, 256);
+  if (out_dtype == MA3_BF16)
+    ma3::adaln_input_kernel<__nv_bfloat16><<<grid, 256, 0, ST(stream)>>>(temb, cap, (__nv_bfloat16*)out, S, N, D, ts_s, ts_n);
+  else
+    ma3::adaln_input_kernel<__half><<<grid, 256, 0, ST(stream)>>>(temb, cap, (__half*)out, S, N, D, ts_s, ts_n);
+  MA3_LAUNCH_CHECK("adaln_input");
+  return 0;
+}

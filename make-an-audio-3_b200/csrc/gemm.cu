@@ -32,6 +32,7 @@ struct GemmKParams {
   int res_dtype;
   long long res_ld, res_batch_stride;
   float alpha;
+  int act;
   int accumulate;
   int vec_ok;
   const float* gate;
@@ -41,6 +42,7 @@ struct GemmKParams {
   const float* rope;
   int model_dim, head_dim, head_dim_pad, heads, tokens, tokens_pad;
   float q_scale;
+  int first_section;
   int op_dtype;
 };
 
@@ -140,6 +142,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int 
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
+      if (p.act == 1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.5f * v[e] * (1.f + erff(v[e] * 0.70710678118654752f));
+      } else if (p.act == 3) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = tanhf(v[e]);
+      }
       if (p.accumulate) {
         float t[8];
         load8(p.out, p.out_dtype, obase + col, vec, n, t);
@@ -181,8 +193,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int 
     for (int g = 0; g < w; g += 8) {
       const int col = n0 + g;
       if (col >= p.N) break;
-      const int which = col / p.model_dim;
-      const int within = col - which * p.model_dim;
+      const int sec = col / p.model_dim;
+      const int within = col - sec * p.model_dim;
+      const int which = sec + p.first_section;  // 0 q, 1 k, 2 v
       const int head = within / p.head_dim;
       const int d = within - head * p.head_dim;  // multiple of 8 (head_dim % 8 == 0 enforced on the host)
       const long long sh = (long long)sample * p.heads + head;
@@ -192,7 +205,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int 
         float v[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = cs[e];
+          const float2 f = p.rope ? cs[e] : make_float2(1.f, 0.f);
           const float x0 = __uint_as_float(r[g + 2 * e]), x1 = __uint_as_float(r[g + 2 * e + 1]);
           v[2 * e] = (x0 * f.x - x1 * f.y) * sc;
           v[2 * e + 1] = (x0 * f.y + x1 * f.x) * sc;
@@ -439,7 +452,7 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   kp.out_row_mul = g->out_row_mul == 0 ? 1 : g->out_row_mul; kp.out_row_off = g->out_row_off;
   kp.bias = g->bias; kp.bias_per_row = g->bias_per_row;
   kp.res = g->res; kp.res_dtype = g->res_dtype; kp.res_ld = g->res_ld; kp.res_batch_stride = g->res_batch_stride;
-  kp.alpha = g->alpha; kp.accumulate = g->accumulate;
+  kp.alpha = g->alpha; kp.accumulate = g->accumulate; kp.act = g->act; kp.first_section = g->first_section;
   kp.gate = g->gate; kp.gate_ld = g->gate_ld; kp.rows_per_sample = g->rows_per_sample;
   kp.q_out = g->q_out; kp.k_out = g->k_out; kp.vt_out = g->vt_out; kp.rope = g->rope;
   kp.model_dim = g->model_dim; kp.head_dim = g->head_dim; kp.head_dim_pad = g->head_dim_pad;
@@ -483,8 +496,10 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
                   "gemm/swiglu: N %% 16, out_ld %% 8, 16-bit out required");
       return launch<MA3_EPI_SWIGLU>(kp, smem, grid, st);
     case MA3_EPI_QKV_ROPE:
-      MA3_REQUIRE(g->q_out && g->k_out && g->vt_out && g->rope, "gemm/qkv_rope: q_out, k_out, vt_out, rope required");
-      MA3_REQUIRE(g->batch == 1 && g->N == 3 * g->model_dim, "gemm/qkv_rope: N must be 3*model_dim, batch 1");
+      MA3_REQUIRE(g->q_out && g->k_out && g->vt_out, "gemm/qkv_rope: q_out, k_out, vt_out required");
+      MA3_REQUIRE(g->first_section == 0 || g->first_section == 1, "gemm/qkv_rope: first_section must be 0 or 1");
+      MA3_REQUIRE(g->batch == 1 && g->N == (3 - g->first_section) * g->model_dim,
+                  "gemm/qkv_rope: N must be (3 - first_section)*model_dim, batch 1");
       MA3_REQUIRE(g->head_dim % 8 == 0 && g->head_dim_pad % 8 == 0 && g->model_dim % g->head_dim == 0 &&
                       g->head_dim_pad >= g->head_dim,
                   "gemm/qkv_rope: head_dim must be a multiple of 8 dividing model_dim");

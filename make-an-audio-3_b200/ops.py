@@ -10,6 +10,24 @@ from . import lib as L
 def declare(lib):
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     protos = {
+        "ma3_rmsnorm_modulate": [vp, vp, vp, i64, i32, i32, i32, vp, i32, i32, i32, f32, vp],
+        "ma3_final_layer": [vp, vp, i64, i32, i32, vp, vp, i32, i32, i32, i32, f32, vp, vp],
+        "ma3_final_layer_cfg_euler": [vp, vp, i64, i32, i32, vp, vp, i32, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp],
+        "ma3_cfg_euler_update": [vp, vp, vp, i64, f32, f32, i32, vp],
+        "ma3_proj_in": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "ma3_timestep_embed": [vp, vp, i32, i32, i32, vp],
+        "ma3_pool_layernorm": [vp, i32, vp, vp, vp, i32, i32, i32, i32, f32, vp],
+        "ma3_layernorm_rows": [vp, i32, vp, vp, vp, i32, i32, i32, f32, vp],
+        "ma3_groupnorm_swish": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp],
+        "ma3_softmax_rows": [vp, vp, i32, i32, i32, i64, i64, f32, vp],
+        "ma3_nct_to_ntc": [vp, vp, i32, i32, i32, i32, i32, f32, vp],
+        "ma3_ntc_to_nct": [vp, i32, vp, i32, i32, i32, i64, vp],
+        "ma3_upsample_nearest2": [vp, vp, i64, i32, vp],
+        "ma3_cast": [vp, i32, vp, i32, i64, vp],
+        "ma3_adaln_input": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+        "ma3_act1d_set_filter": [vp, vp],
+        "ma3_act1d": [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, vp],
+        "ma3_attention": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -22,7 +40,8 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
          b_batch_stride=0, taps=((0, 0),), epi=L.EPI_STORE, out=None, out_ld=None, out_batch_stride=0,
          out_row_mul=1, out_row_off=0, bias=None, bias_per_row=False, res=None, res_ld=None, res_batch_stride=0,
          alpha=1.0, accumulate=False, gate=None, rows_per_sample=0, q_out=None, k_out=None, vt_out=None, rope=None,
-         model_dim=0, head_dim=0, head_dim_pad=0, tokens=0, tokens_pad=0, q_scale=1.0, tile_n=0):
+         model_dim=0, head_dim=0, head_dim_pad=0, tokens=0, tokens_pad=0, q_scale=1.0, first_section=0, act=0,
+         tile_n=0):
     """acc[z,m,n] = sum_taps sum_k A[z, m + a_shift, k] * B[z, n + b_row, k]; see include/ma3_b200.h."""
     lib = L.require_device()
     assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float16)
@@ -66,10 +85,153 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
     d.rows_per_sample = rows_per_sample
     if q_out is not None:
         d.q_out, d.k_out, d.vt_out = q_out.data_ptr(), k_out.data_ptr(), vt_out.data_ptr()
-        d.rope = rope.data_ptr()
+        d.rope = rope.data_ptr() if rope is not None else None
     d.model_dim, d.head_dim, d.head_dim_pad = model_dim, head_dim, head_dim_pad
     d.tokens, d.tokens_pad = tokens, tokens_pad
     d.q_scale = q_scale
+    d.first_section = first_section
+    d.act = act
     d.tile_n = tile_n
     L.check(lib.ma3_gemm(C.byref(d), L.stream_ptr()), "ma3_gemm")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- other ops
+def _call(name, *args):
+    lib = L.require_device()
+    L.check(getattr(lib, name)(*args, L.stream_ptr()), name)
+
+
+def rmsnorm_modulate(x, w, out, *, mod=None, shift_off=0, scale_off=0, rows_per_sample=1, eps=1e-5):
+    """out = rms(x) * w * (1 + scale) + shift; x fp32 [M, D]; mod fp32 [samples, ld] or None (plain RMSNorm)."""
+    M, D = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    _call("ma3_rmsnorm_modulate", L.ptr(x), L.ptr(w), L.ptr(mod), mod.stride(0) if mod is not None else 0,
+          shift_off, scale_off, rows_per_sample, L.ptr(out), L.dt(out), M, D, eps)
+    return out
+
+
+def final_layer(h, mod, shift_off, scale_off, W, bias, N, T, v_out, eps=1e-6):
+    D, Cout = h.shape[-1], W.shape[0]
+    _call("ma3_final_layer", L.ptr(h), L.ptr(mod), mod.stride(0), shift_off, scale_off, L.ptr(W), L.ptr(bias), N, T, D,
+          Cout, eps, L.ptr(v_out))
+    return v_out
+
+
+def final_layer_cfg_euler(h, mod, shift_off, scale_off, W, bias, N, T, guidance, dt, x_in, x_out, v_out=None,
+                          eps=1e-6):
+    D, Cout = h.shape[-1], W.shape[0]
+    _call("ma3_final_layer_cfg_euler", L.ptr(h), L.ptr(mod), mod.stride(0), shift_off, scale_off, L.ptr(W),
+          L.ptr(bias), N, T, D, Cout, eps, guidance, dt, L.ptr(x_in), L.ptr(x_out), L.ptr(v_out))
+    return x_out
+
+
+def cfg_euler_update(v, x, out, dt, guidance, cfg=True):
+    _call("ma3_cfg_euler_update", L.ptr(v), L.ptr(x), L.ptr(out), x.numel(), dt, guidance, int(cfg))
+    return out
+
+
+def proj_in(x, W, b, h, N):
+    xB, Cc, T = x.shape
+    _call("ma3_proj_in", L.ptr(x), L.ptr(W), L.ptr(b), L.ptr(h), N, xB, Cc, T, W.shape[0])
+    return h
+
+
+def timestep_embed(t, out):
+    assert t.dtype == torch.int64
+    _call("ma3_timestep_embed", L.ptr(t), L.ptr(out), L.dt(out), t.numel(), out.shape[-1])
+    return out
+
+
+def pool_layernorm(ctx, w, b, out, eps=1e-5):
+    N, Lc, Cd = ctx.shape
+    _call("ma3_pool_layernorm", L.ptr(ctx), L.dt(ctx), L.ptr(w), L.ptr(b), L.ptr(out), L.dt(out), N, Lc, Cd, eps)
+    return out
+
+
+def layernorm_rows(x, w, b, out, eps=1e-5):
+    M, D = x.shape
+    _call("ma3_layernorm_rows", L.ptr(x), L.dt(x), L.ptr(w), L.ptr(b), L.ptr(out), L.dt(out), M, D, eps)
+    return out
+
+
+def groupnorm_swish(x, w, b, out, *, groups=32, eps=1e-6, swish=True):
+    B, T, Cc = x.shape
+    _call("ma3_groupnorm_swish", L.ptr(x), L.dt(x), L.ptr(w), L.ptr(b), L.ptr(out), L.dt(out), B, T, Cc, groups, eps,
+          int(swish))
+    return out
+
+
+def softmax_rows(S, P, n, scale):
+    rows = S.numel() // S.shape[-1]
+    _call("ma3_softmax_rows", L.ptr(S), L.ptr(P), L.dt(P), rows, n, S.shape[-1], P.shape[-1], scale)
+    return P
+
+
+def nct_to_ntc(x, out, scale=1.0):
+    B, Cc, T = x.shape
+    _call("ma3_nct_to_ntc", L.ptr(x), L.ptr(out), L.dt(out), B, Cc, T, out.shape[-1], scale)
+    return out
+
+
+def ntc_to_nct(x, out):
+    B, Cc, T = out.shape
+    _call("ma3_ntc_to_nct", L.ptr(x), L.dt(x), L.ptr(out), B, Cc, T, x.shape[-1])
+    return out
+
+
+def upsample_nearest2(x, out):
+    B, T, Cc = x.shape
+    _call("ma3_upsample_nearest2", L.ptr(x), L.ptr(out), B * T, Cc)
+    return out
+
+
+def cast(x, out):
+    _call("ma3_cast", L.ptr(x), L.dt(x), L.ptr(out), L.dt(out), x.numel())
+    return out
+
+
+_filter_set = False
+
+
+def act1d(x, out, alpha, beta, logscale=True):
+    """Fused Activation1d on channels-last x [B, T, C]."""
+    global _filter_set
+    if not _filter_set:
+        taps = (C.c_float * 12)(*kaiser_sinc_taps())
+        _call("ma3_act1d_set_filter", taps)
+        _filter_set = True
+    B, T, Cc = x.shape
+    _call("ma3_act1d", L.ptr(x), L.dt(x), L.ptr(out), L.dt(out), L.ptr(alpha), L.ptr(beta), B, T, Cc, int(logscale))
+    return out
+
+
+def kaiser_sinc_taps(cutoff=0.25, half_width=0.3, kernel_size=12):
+    """Host-side filter design, run once (vocoder/bigvgan/alias_free_torch/filter.py:28-57)."""
+    import math
+    half = kernel_size // 2
+    A = 2.285 * (half - 1) * math.pi * (4 * half_width) + 7.95
+    beta = 0.1102 * (A - 8.7) if A > 50.0 else (0.5842 * (A - 21) ** 0.4 + 0.07886 * (A - 21.0) if A >= 21.0 else 0.0)
+    win = torch.kaiser_window(kernel_size, periodic=False, beta=beta, dtype=torch.float64)
+    t = torch.arange(-half, half, dtype=torch.float64) + 0.5 if kernel_size % 2 == 0 else \
+        torch.arange(kernel_size, dtype=torch.float64) - half
+    f = 2 * cutoff * win * torch.sinc(2 * cutoff * t)
+    f = f / f.sum()
+    return [float(v) for v in f]
+
+
+def attention(q, k, vt, ky, vyt, gate, out, *, hd):
+    """q,k [NS,H,T,hdp]; vt [NS,H,hdp,Tp]; ky [NS,H,L,hdp]; vyt [NS,H,hdp,Lp]; out [NS,T,H*hd]."""
+    NS, H, T, hdp = q.shape
+    Tp = vt.shape[-1]
+    Lc = ky.shape[2] if ky is not None else 0
+    Lp = vyt.shape[-1] if vyt is not None else 0
+    _call("ma3_attention", L.ptr(q), L.ptr(k), L.ptr(vt), L.ptr(ky), L.ptr(vyt), L.ptr(gate), L.ptr(out), L.dt(q), NS, H,
+          T, Tp, Lc, Lp, hd, hdp)
+    return out
+
+
+def adaln_input(temb, cap, out, S, N, ts_s, ts_n):
+    """out[s*N + n] = silu(temb[s*ts_s + n*ts_n] + cap[n]) as 16-bit GEMM operand."""
+    _call("ma3_adaln_input", L.ptr(temb), L.ptr(cap), L.ptr(out), L.dt(out), S, N, cap.shape[-1], ts_s, ts_n)
     return out

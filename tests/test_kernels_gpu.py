@@ -1,0 +1,279 @@
+"""Per-kernel parity on a B200: each C-ABI entry point against the oracle (oracle/restated.py) or a plain torch fp32
+expression of the same op, on seeded inputs.  Tolerances are stated per test (bf16/fp16 storage => ~2^-8 relative)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cases as Cs, restated as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ma3_b200 import lib, ops as _ops
+    lib.require_device()
+    return _ops
+
+
+def rel(a, b):
+    return O.max_rel_err(a.float().cpu(), b.float().cpu())
+
+
+def g(seed):
+    return Cs.gen(seed)
+
+
+# ------------------------------------------------------------------------------------------------ tap-GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1000, 1152, 1152), (300, 80, 96), (300, 48, 48), (77, 16, 32),
+                                   (4992, 3456, 1152)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_gemm_plain(ops, M, N, K, dt):
+    a = torch.randn(M, K, generator=g(1)).to(dt).cuda()
+    b = (torch.randn(N, K, generator=g(2)) / K ** 0.5).to(dt).cuda()
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, M=M, N=N, K=K, out=out)
+    assert rel(out, a.float() @ b.float().t()) < 1e-4  # fp32 accumulate of identical 16-bit operands
+
+
+def test_gemm_epilogue_store_variants(ops):
+    from ma3_b200 import lib as L
+    M, N, K = 500, 384, 384
+    a = torch.randn(M, K, generator=g(3)).bfloat16().cuda()
+    b = (torch.randn(N, K, generator=g(4)) / K ** .5).bfloat16().cuda()
+    bias = torch.randn(N, generator=g(5)).cuda()
+    res = torch.randn(M, N, generator=g(6)).bfloat16().cuda()
+    out = torch.randn(M, N, generator=g(7)).bfloat16().cuda()
+    old = out.clone()
+    ops.gemm(a, b, M=M, N=N, K=K, out=out, bias=bias, res=res, alpha=0.5, accumulate=True)
+    ref = (a.float() @ b.float().t() + bias + res.float()) * 0.5 + old.float()
+    assert rel(out, ref) < 8e-3
+    # per-row bias, ragged N (scalar tail path), fp16 out
+    N2 = 20
+    b2 = (torch.randn(N2, K, generator=g(8)) / K ** .5).bfloat16().cuda()
+    brow = torch.randn(M, generator=g(9)).cuda()
+    o2 = torch.zeros(M, 64, device="cuda", dtype=torch.float16)
+    ops.gemm(a, b2, M=M, N=N2, K=K, out=o2, out_ld=64, bias=brow, bias_per_row=True)
+    assert rel(o2[:, :N2], a.float() @ b2.float().t() + brow[:, None]) < 2e-3
+    assert bool((o2[:, N2:] == 0).all())
+    # activation epilogues
+    for act, fn in ((1, torch.nn.functional.silu), (2, torch.nn.functional.gelu), (3, torch.tanh)):
+        o3 = torch.empty(M, N, device="cuda", dtype=torch.float32)
+        ops.gemm(a, b, M=M, N=N, K=K, out=o3, bias=bias, act=act)
+        assert rel(o3, fn(a.float() @ b.float().t() + bias)) < 1e-3
+
+
+@pytest.mark.parametrize("k,dil", [(3, 1), (3, 5), (7, 3), (11, 1), (5, 1), (1, 1)])
+def test_gemm_as_conv1d(ops, k, dil):
+    B, T, Ci, Co = 3, 300, 128, 192
+    pad = (k * dil - dil) // 2
+    x = torch.randn(B, T, Ci, generator=g(10)).bfloat16().cuda()
+    w = (torch.randn(Co, Ci, k, generator=g(11)) / (Ci * k) ** .5).bfloat16().cuda()
+    wp = w.permute(2, 0, 1).contiguous().view(k * Co, Ci)
+    bias = torch.randn(Co, generator=g(12)).cuda()
+    y = torch.empty(B, T, Co, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, wp, M=T, N=Co, K=Ci, batch=B, a_rows=T, a_batch_stride=T * Ci, b_rows=k * Co,
+             taps=[(j * dil - pad, j * Co) for j in range(k)], out=y, out_batch_stride=T * Co, bias=bias)
+    ref = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.float(), bias, padding=pad, dilation=dil)
+    assert rel(y, ref.transpose(1, 2)) < 8e-3
+
+
+def test_gemm_gate_residual_and_swiglu(ops):
+    from ma3_b200 import lib as L
+    M, N, K, T = 624, 768, 768, 312
+    a = torch.randn(M, K, generator=g(13)).bfloat16().cuda()
+    b = (torch.randn(N, K, generator=g(14)) / K ** .5).bfloat16().cuda()
+    h = torch.randn(M, N, generator=g(15)).cuda()
+    h0 = h.clone()
+    gate = torch.randn(2, N, generator=g(16)).cuda()
+    ops.gemm(a, b, M=M, N=N, K=K, epi=L.EPI_GATE_RES, out=h, gate=gate, rows_per_sample=T)
+    assert rel(h, h0 + gate.repeat_interleave(T, 0) * (a.float() @ b.float().t())) < 1e-4
+    F = 2048
+    w1 = (torch.randn(F, K, generator=g(17)) / K ** .5).bfloat16().cuda()
+    w3 = (torch.randn(F, K, generator=g(18)) / K ** .5).bfloat16().cuda()
+    w13 = torch.stack([w1, w3], 1).reshape(2 * F, K).contiguous()
+    o = torch.empty(M, F, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w13, M=M, N=2 * F, K=K, epi=L.EPI_SWIGLU, out=o, out_ld=F)
+    ref = torch.nn.functional.silu(a.float() @ w1.float().t()) * (a.float() @ w3.float().t())
+    assert rel(o, ref) < 8e-3
+
+
+# ------------------------------------------------------------------------------------------------ QKV+RoPE, attention
+def _qkv_attention_case(ops, D, H, T, L, Ns, seed):
+    """QKV GEMM with RoPE scatter followed by the fused self+cross attention, against oracle.attention pieces."""
+    from ma3_b200 import lib as L_
+    hd = D // H
+    hdp = 64 if hd <= 64 else 128
+    Tp, Lp = (T + 7) // 8 * 8, (L + 7) // 8 * 8
+    gg = g(seed)
+    x = torch.randn(Ns, T, D, generator=gg)
+    y = torch.randn(Ns, L, D, generator=gg)
+    sd = {"wq.weight": torch.randn(D, D, generator=gg) / D ** .5, "wk.weight": torch.randn(D, D, generator=gg) / D ** .5,
+          "wv.weight": torch.randn(D, D, generator=gg) / D ** .5, "wk_y.weight": torch.randn(D, D, generator=gg) / D ** .5,
+          "wv_y.weight": torch.randn(D, D, generator=gg) / D ** .5, "gate": torch.randn(H, generator=gg),
+          "wo.weight": torch.eye(D)}
+    # oracle on bf16-rounded inputs/weights (the kernels see bf16 operands)
+    r = lambda t: t.bfloat16().float()
+    sdr = {k: (r(v) if k != "gate" else v) for k, v in sd.items()}
+    cos, sin = O.rope_table(hd, T)
+    ref = O.attention(sdr, "", r(x), r(y), cos, sin, H)  # [Ns, T, D] (wo = identity)
+
+    dev = "cuda"
+    xb = x.bfloat16().to(dev).view(Ns * T, D)
+    wqkv = torch.cat([sd["wq.weight"], sd["wk.weight"], sd["wv.weight"]]).bfloat16().to(dev)
+    rope = torch.stack([cos, sin], -1).contiguous().to(dev)
+    q = torch.zeros(Ns, H, T, hdp, device=dev, dtype=torch.bfloat16)
+    k = torch.zeros_like(q)
+    vt = torch.zeros(Ns, H, hdp, Tp, device=dev, dtype=torch.bfloat16)
+    ops.gemm(xb, wqkv, M=Ns * T, N=3 * D, K=D, epi=L_.EPI_QKV_ROPE, q_out=q, k_out=k, vt_out=vt, rope=rope,
+             model_dim=D, head_dim=hd, head_dim_pad=hdp, tokens=T, tokens_pad=Tp,
+             q_scale=math.log2(math.e) / math.sqrt(hd))
+    yb = y.bfloat16().to(dev).view(Ns * L, D)
+    wkv = torch.cat([sd["wk_y.weight"], sd["wv_y.weight"]]).bfloat16().to(dev)
+    ky = torch.zeros(Ns, H, L, hdp, device=dev, dtype=torch.bfloat16)
+    vyt = torch.zeros(Ns, H, hdp, Lp, device=dev, dtype=torch.bfloat16)
+    ops.gemm(yb, wkv, M=Ns * L, N=2 * D, K=D, epi=L_.EPI_QKV_ROPE, q_out=ky, k_out=ky, vt_out=vyt, rope=None,
+             model_dim=D, head_dim=hd, head_dim_pad=hdp, tokens=L, tokens_pad=Lp, first_section=1)
+    out = torch.empty(Ns, T, D, device=dev, dtype=torch.bfloat16)
+    ops.attention(q, k, vt, ky, vyt, sd["gate"].to(dev), out, hd=hd)
+    torch.cuda.synchronize()
+    return rel(out, ref)
+
+
+@pytest.mark.parametrize("D,H,T,L,Ns", [(768, 32, 312, 154, 2), (1152, 16, 312, 154, 2), (768, 16, 936, 154, 1),
+                                        (768, 32, 256, 40, 2), (256, 16, 100, 7, 3), (128, 2, 130, 77, 1)])
+def test_qkv_rope_attention(ops, D, H, T, L, Ns):
+    # bf16 q/k/v/p storage: 2^-8 relative per rounding, a handful of roundings
+    assert _qkv_attention_case(ops, D, H, T, L, Ns, seed=20) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def test_rmsnorm_modulate(ops):
+    M, D, T = 624, 1152, 312
+    x = torch.randn(M, D, generator=g(30)) * 3
+    w = torch.randn(D, generator=g(31))
+    mod = torch.randn(2, 6 * D, generator=g(32)) * 0.3
+    out = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    ops.rmsnorm_modulate(x.cuda(), w.cuda(), out, mod=mod.cuda(), shift_off=3 * D, scale_off=4 * D, rows_per_sample=T)
+    sc = mod[:, 4 * D:5 * D].repeat_interleave(T, 0)
+    sh = mod[:, 3 * D:4 * D].repeat_interleave(T, 0)
+    assert rel(out, O.rmsnorm(x, w) * (1 + sc) + sh) < 5e-3
+    out32 = torch.empty(M, D, device="cuda", dtype=torch.float32)
+    ops.rmsnorm_modulate(x.cuda(), None, out32)
+    assert rel(out32, O.rmsnorm(x, torch.ones(D))) < 1e-5
+
+
+def test_final_layer_and_cfg_euler(ops):
+    B, T, D, Cc = 3, 50, 768, 20
+    N = 2 * B
+    h = torch.randn(N * T, D, generator=g(33)) * 2 + 0.3
+    mod = torch.randn(N, 2 * D, generator=g(34)) * 0.3
+    W = torch.randn(Cc, D, generator=g(35)) / D ** .5
+    bias = torch.randn(Cc, generator=g(36))
+    x = torch.randn(B, Cc, T, generator=g(37))
+    hn = torch.nn.functional.layer_norm(h.view(N, T, D), (D,), None, None, 1e-6)
+    v = (hn * (1 + mod[:, None, D:]) + mod[:, None, :D]) @ W.t() + bias
+    v = v.transpose(1, 2)  # [N, C, T]
+    vout = torch.empty(N, Cc, T, device="cuda")
+    ops.final_layer(h.cuda(), mod.cuda(), 0, D, W.cuda(), bias.cuda(), N, T, vout)
+    assert rel(vout, v) < 1e-4
+    vg = v[:B] + 3.0 * (v[B:] - v[:B])
+    xo = torch.empty(B, Cc, T, device="cuda")
+    vgo = torch.empty(B, Cc, T, device="cuda")
+    ops.final_layer_cfg_euler(h.cuda(), mod.cuda(), 0, D, W.cuda(), bias.cuda(), N, T, 3.0, 1 / 24, x.cuda(), xo, vgo)
+    assert rel(vgo, vg) < 1e-4 and rel(xo, x + vg / 24) < 1e-4
+    x2 = torch.empty(B, Cc, T, device="cuda")
+    ops.cfg_euler_update(vout, x.cuda(), x2, 1 / 24, 3.0, cfg=True)
+    assert rel(x2, x + vg / 24) < 1e-4
+
+
+def test_proj_in_timestep_pool(ops):
+    N, Cc, T, D = 4, 20, 37, 192
+    x = torch.randn(2, Cc, T, generator=g(38))
+    W = torch.randn(D, Cc, generator=g(39))
+    b = torch.randn(D, generator=g(40))
+    h = torch.empty(N * T, D, device="cuda")
+    ops.proj_in(x.cuda(), W.cuda(), b.cuda(), h, N)
+    ref = (x.transpose(1, 2) @ W.t() + b).repeat(2, 1, 1).view(N * T, D)
+    assert rel(h, ref) < 1e-5
+    t = torch.tensor([0, 41, 500, 958, 999])
+    e = torch.empty(5, 256, device="cuda", dtype=torch.float32)
+    ops.timestep_embed(t.cuda(), e)
+    assert (e.cpu() - O.timestep_embedding(t)).abs().max() < 2e-4
+    ctx = torch.randn(3, 11, 96, generator=g(41))
+    w = torch.randn(96, generator=g(42))
+    bb = torch.randn(96, generator=g(43))
+    o = torch.empty(3, 96, device="cuda", dtype=torch.bfloat16)
+    ops.pool_layernorm(ctx.cuda(), w.cuda(), bb.cuda(), o)
+    assert rel(o, torch.nn.functional.layer_norm(ctx.mean(1), (96,), w, bb, 1e-5)) < 8e-3
+
+
+def test_groupnorm_softmax_layout(ops):
+    B, T, Cc = 2, 60, 384
+    x = torch.randn(B, Cc, T, generator=g(44)) * 2 + 0.5
+    w = torch.randn(Cc, generator=g(45))
+    b = torch.randn(Cc, generator=g(46))
+    ref = torch.nn.functional.group_norm(x, 32, w, b, 1e-6)
+    ref = ref * torch.sigmoid(ref)
+    xin = x.transpose(1, 2).contiguous().cuda()
+    o = torch.empty(B, T, Cc, device="cuda", dtype=torch.bfloat16)
+    ops.groupnorm_swish(xin, w.cuda(), b.cuda(), o)
+    assert rel(o.transpose(1, 2), ref) < 8e-3
+    S = torch.randn(2, 50, 50, generator=g(47)) * 4
+    P = torch.full((2, 50, 64), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.softmax_rows(S.cuda(), P, 50, 0.25)
+    assert rel(P[..., :50], torch.softmax(S * 0.25, -1)) < 8e-3 and bool((P[..., 50:] == 0).all())
+    z = torch.randn(2, 20, 24, generator=g(48))
+    zz = torch.empty(2, 24, 64, device="cuda", dtype=torch.bfloat16)
+    ops.nct_to_ntc(z.cuda(), zz, 0.5)
+    assert rel(zz[..., :20], 0.5 * z.transpose(1, 2)) < 5e-3 and bool((zz[..., 20:] == 0).all())
+    back = torch.empty(2, 20, 24, device="cuda")
+    ops.ntc_to_nct(zz, back)
+    assert rel(back, 0.5 * z) < 5e-3
+    up = torch.empty(2, 48, 64, device="cuda", dtype=torch.bfloat16)
+    ops.upsample_nearest2(zz, up)
+    assert torch.equal(up, zz.repeat_interleave(2, dim=1))
+
+
+# ------------------------------------------------------------------------------------------------ Activation1d
+@pytest.mark.parametrize("B,Cc,T", [(2, 32, 50), (1, 64, 3), (2, 96, 513), (1, 48, 1000), (1, 1536, 130), (1, 32, 16),
+                                    (1, 16, 17), (2, 192, 2496)])
+@pytest.mark.parametrize("dt_in", [torch.float32, torch.float16])
+def test_act1d(ops, B, Cc, T, dt_in):
+    gg = g(50)
+    x = torch.randn(B, Cc, T, generator=gg) * 1.5
+    al = torch.randn(Cc, generator=gg) * 0.3
+    be = torch.randn(Cc, generator=gg) * 0.3
+    xin = x.to(dt_in)
+    sd = {"a.act.alpha": al, "a.act.beta": be}
+    ref = O.activation1d(xin.float(), sd, "a", dict(activation="snakebeta", snake_logscale=True))
+    out = torch.empty(B, T, Cc, device="cuda", dtype=torch.float16)
+    ops.act1d(xin.transpose(1, 2).contiguous().cuda(), out, al.cuda(), be.cuda(), logscale=True)
+    assert rel(out.transpose(1, 2), ref) < 2e-3  # fp16 output rounding 2^-11, fast sin
+    # plain Snake, linear-scale alpha
+    ref2 = O.activation1d(xin.float(), {"a.act.alpha": al.abs() + 0.5}, "a", dict(activation="snake", snake_logscale=False))
+    ops.act1d(xin.transpose(1, 2).contiguous().cuda(), out, (al.abs() + 0.5).cuda(), None, logscale=False)
+    assert rel(out.transpose(1, 2), ref2) < 2e-3
+
+
+def test_act1d_golden(ops, golden):
+    x, al, be = Cs.act_inputs()
+    xp = torch.zeros(2, 50, 32)
+    xp[..., :24] = x.transpose(1, 2)
+    alp, bep = torch.zeros(32), torch.zeros(32)
+    alp[:24], bep[:24] = al, be
+    out = torch.empty(2, 50, 32, device="cuda", dtype=torch.float32)
+    ops.act1d(xp.cuda(), out, alp.cuda(), bep.cuda())
+    assert rel(out[..., :24].transpose(1, 2), golden["act1d"]) < 1e-4
+    assert bool((out[..., 24:] == 0).all())  # padded channels stay exactly zero
+
+
+def test_errors(ops):
+    from ma3_b200 import lib as L
+    a = torch.zeros(16, 24, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(L.Ma3Error):
+        ops.gemm(a, a, M=16, N=16, K=24, out=torch.empty(16, 16, device="cuda"))  # K not a multiple of 16
+    with pytest.raises(L.Ma3Error):
+        ops.act1d(torch.zeros(1, 8, 24, device="cuda"), torch.zeros(1, 8, 24, device="cuda", dtype=torch.float16),
+                  torch.zeros(24, device="cuda"), None)  # C not a multiple of 16
