@@ -110,6 +110,87 @@ typedef struct ma3_gemm {
 
 int ma3_gemm(const ma3_gemm_t* g, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused flash attention of one Next-DiT block: self-attention over the T latent tokens plus tanh-gated
+ * cross-attention over the L context tokens, sharing the rotary-embedded Q tile.
+ *   out[ns, t, h*hd + d] = softmax(q k^T) v + tanh(gate[h]) * softmax(q ky^T) vy
+ * Replaces Attention.forward's two F.scaled_dot_product_attention calls and the gate combine
+ * (flag_large_dit_moe.py:382-406).  q must already carry RoPE and the factor log2(e)/sqrt(hd) (MA3_EPI_QKV_ROPE).
+ * Layouts (16-bit, `dtype`): q,k [NS*H, T, hdp]; vt [NS*H, hdp, Tp]; ky [NS*H, L, hdp]; vyt [NS*H, hdp, Lp];
+ * gate [H] fp32 (raw parameter); out [NS, T, H*hd].  hdp in {64,128}; Tp, Lp multiples of 8.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int ma3_attention(const void* q, const void* k, const void* vt, const void* ky, const void* vyt, const float* gate,
+                  void* out, int dtype, int NS, int H, int T, int Tp, int L, int Lp, int hd, int hdp, void* stream);
+
+/* out[m,:] = x[m,:] * rsqrt(mean(x^2)+eps) * w * (1 + scale[s,:]) + shift[s,:],  s = m / rows_per_sample, with
+ * shift = mod[s, shift_off : shift_off+D], scale = mod[s, scale_off : ...] (fp32).  w == NULL: no weight;
+ * mod == NULL: plain RMSNorm.  x fp32 [M, D].  Replaces RMSNorm + modulate (flag_large_dit_moe.py:34-81) as used at
+ * flag_large_dit.py:83-91. */
+int ma3_rmsnorm_modulate(const float* x, const float* w, const float* mod, int64_t mod_ld, int shift_off,
+                         int scale_off, int rows_per_sample, void* out, int out_dtype, int M, int D, float eps,
+                         void* stream);
+
+/* FinalLayer (flag_large_dit.py:101-124): LayerNorm(no affine, eps) -> modulate -> Linear(D -> Cout), written
+ * transposed as v_out[N, Cout, T] fp32 (the 'b t c -> b c t' rearrange of flag_large_dit.py:209). */
+int ma3_final_layer(const float* h, const float* mod, int64_t mod_ld, int shift_off, int scale_off, const float* W,
+                    const float* bias, int N, int T, int D, int Cout, float eps, float* v_out, void* stream);
+
+/* FinalLayer fused with the classifier-free-guidance combine and the Euler update: rows [0, N/2) are the
+ * unconditional half, [N/2, N) the conditional half (cfm1_audio.py:154-161);
+ *   v = v_u + guidance (v_c - v_u);  x_out = x_in + dt v;   v_out (nullable) receives v.   x, v: [N/2, Cout, T]. */
+int ma3_final_layer_cfg_euler(const float* h, const float* mod, int64_t mod_ld, int shift_off, int scale_off,
+                              const float* W, const float* bias, int N, int T, int D, int Cout, float eps,
+                              float guidance, float dt, const float* x_in, float* x_out, float* v_out, void* stream);
+
+/* Stand-alone guidance combine + Euler update on velocities v [2*B or B, ...] (cfg = 1 / 0); elems = numel(x). */
+int ma3_cfg_euler_update(const float* v, const float* x, float* out, int64_t elems, float dt, float guidance, int cfg,
+                         void* stream);
+
+/* h[n*T + t, :] = W x[n % x_batch, :, t] + b   (proj_in on the 'b c t -> b t c' view, flag_large_dit.py:186-187). */
+int ma3_proj_in(const float* x, const float* W, const float* b, float* h, int N, int x_batch, int C, int T, int D,
+                void* stream);
+
+/* Sinusoidal timestep embedding [cos | sin] (flag_large_dit_moe.py:110-127); t int64 [M] -> out [M, dim]. */
+int ma3_timestep_embed(const int64_t* t, void* out, int out_dtype, int M, int dim, void* stream);
+
+/* out[n,:] = LayerNorm_affine(mean over L of ctx[n,:,:])   (flag_large_dit.py:193-198, first half of cap_embedder). */
+int ma3_pool_layernorm(const void* ctx, int in_dtype, const float* w, const float* b, void* out, int out_dtype, int N,
+                       int L, int Cd, float eps, void* stream);
+
+/* Row-wise affine LayerNorm (trailing nn.LayerNorm of ConditionEmbedder, flag_large_dit_moe.py:151-162). */
+int ma3_layernorm_rows(const void* x, int in_dtype, const float* w, const float* b, void* out, int out_dtype, int M,
+                       int D, float eps, void* stream);
+
+/* out[s*N + n, :] = silu(temb[s*ts_s + n*ts_n, :] + cap[n, :])  -- adaln_input = t_emb + cap_emb followed by the SiLU
+ * at the head of every adaLN_modulation (flag_large_dit.py:50-51,200). */
+int ma3_adaln_input(const float* temb, const float* cap, void* out, int out_dtype, int S, int N, int D, int ts_s,
+                    int ts_n, void* stream);
+
+/* GroupNorm(groups, eps, affine) optionally followed by swish on channels-last x [B, T, C]
+ * (Normalize + nonlinearity, autoencoder1d.py:169-175). */
+int ma3_groupnorm_swish(const void* x, int in_dtype, const float* w, const float* b, void* out, int out_dtype, int B,
+                        int T, int C, int groups, float eps, int swish, void* stream);
+
+/* P[r, 0:n] = softmax(scale * S[r, 0:n]), P[r, n:ld_out] = 0   (AttnBlock1D, autoencoder1d.py:265-270). */
+int ma3_softmax_rows(const float* S, void* P, int out_dtype, int rows, int n, int64_t ld_in, int64_t ld_out,
+                     float scale, void* stream);
+
+/* Layout changes between the reference's [B, C, T] fp32 tensors and channels-last 16-bit activations. */
+int ma3_nct_to_ntc(const float* x, void* out, int out_dtype, int B, int C, int T, int Cp, float scale, void* stream);
+int ma3_ntc_to_nct(const void* x, int in_dtype, float* out, int B, int C, int T, int64_t ld, void* stream);
+/* nearest-neighbour x2 along T (Upsample1D, autoencoder1d.py:291-292) on channels-last 16-bit rows. */
+int ma3_upsample_nearest2(const void* x, void* out, int64_t rows, int C, void* stream);
+int ma3_cast(const void* x, int in_dtype, void* out, int out_dtype, int64_t n, void* stream);
+
+/* Fused anti-aliased periodic activation (Activation1d.forward, vocoder/bigvgan/alias_free_torch/act.py:23-28):
+ * replicate-pad -> x2 up-sampling with the 12-tap Kaiser-sinc filter (resample.py:25-33) -> SnakeBeta / Snake
+ * (activations.py:48-59,107-119; beta == NULL selects Snake) -> replicate-pad -> low-pass, stride 2
+ * (filter.py:86-95), one pass over HBM on channels-last x [B, T, C], C % 16 == 0.
+ * ma3_act1d_set_filter uploads the 12 taps (host pointer) once per process. */
+int ma3_act1d_set_filter(const float* taps12, void* stream);
+int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float* alpha, const float* beta, int B,
+              int T, int C, int logscale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

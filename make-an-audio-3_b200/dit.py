@@ -1,0 +1,433 @@
+"""Drop-in Next-DiT backbones for the reference's `unet_config.target`.
+
+`TxtFlagLargeImprovedDiTV2` / `TxtFlagLargeDiT` mirror ldm/modules/diffusionmodules/flag_large_dit.py:128-299 and
+`VideoFlagLargeDiT` mirrors ldm/modules/diffusionmodules/flag_large_dit_moe.py:613-740: same constructor arguments,
+`forward(x, t, context)` signature, `freqs_cis` attribute / `precompute_freqs_cis` static method and `state_dict`
+key names.  The nn.Module tree below only *holds* the fp32 parameters (so reference checkpoints load with
+load_state_dict); all arithmetic runs in the sm_100a kernels of libma3b200.so on packed bf16 copies of the weights.
+
+Step-invariant work is hoisted: the normalised context and every layer's cross-attention
+K/V are computed once per call to `prepare_context`, the adaLN modulation of every layer for a whole list of
+timesteps in one GEMM by `prepare_timesteps`; `run_blocks` then costs 7 launches per block.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import lib as L
+from . import ops
+
+
+def _ffn_hidden(dim, multiple_of=256, ffn_dim_multiplier=None):
+    hidden = int(2 * (4 * dim) / 3)
+    if ffn_dim_multiplier is not None:
+        hidden = int(ffn_dim_multiplier * hidden)
+    return multiple_of * ((hidden + multiple_of - 1) // multiple_of)
+
+
+class _Weight(nn.Module):
+    """Parameter holder with a `.weight` (RMSNorm scale)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+class _Lin(nn.Module):
+    """Parameter holder shaped like nn.Linear (never called)."""
+
+    def __init__(self, fin, fout, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(fout, fin).uniform_(-1, 1) * math.sqrt(3.0 / fin))
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(fout))
+        else:
+            self.register_parameter("bias", None)
+
+
+class _LN(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+
+
+class _Seq(nn.Module):
+    """Holder reproducing nn.Sequential's integer child names at chosen indices."""
+
+    def __init__(self, **children):
+        super().__init__()
+        for k, v in children.items():
+            self.add_module(k.lstrip("_"), v)
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, n_heads, y_dim):
+        super().__init__()
+        self.wq, self.wk, self.wv = _Lin(dim, dim, False), _Lin(dim, dim, False), _Lin(dim, dim, False)
+        self.wk_y, self.wv_y = _Lin(y_dim, dim, False), _Lin(y_dim, dim, False)
+        self.gate = nn.Parameter(torch.zeros(n_heads))
+        self.wo = _Lin(dim, dim, False)
+
+
+class _FFN(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.w1, self.w2, self.w3 = _Lin(dim, hidden, False), _Lin(hidden, dim, False), _Lin(dim, hidden, False)
+
+
+class _MoE(nn.Module):
+    def __init__(self, dim, hidden, num_experts):
+        super().__init__()
+        self.time_experts = nn.ModuleDict({str(i): _FFN(dim, hidden) for i in range(num_experts)})
+        self.freq_experts = nn.ModuleDict({str(i): _FFN(dim, hidden) for i in range(num_experts)})
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, n_heads, y_dim, hidden, num_experts):
+        super().__init__()
+        self.attention = _Attention(dim, n_heads, y_dim)
+        self.feed_forward = _MoE(dim, hidden, num_experts) if num_experts else _FFN(dim, hidden)
+        self.attention_norm, self.ffn_norm = _Weight(dim), _Weight(dim)
+        self.adaLN_modulation = _Seq(_1=_Lin(dim, 6 * dim))
+        self.attention_y_norm = _Weight(y_dim)
+
+
+class _Final(nn.Module):
+    def __init__(self, dim, out_channels):
+        super().__init__()
+        self.linear = _Lin(dim, out_channels)
+        self.adaLN_modulation = _Seq(_1=_Lin(dim, 2 * dim))
+
+
+class _Work:
+    """Device buffers for one (N, T, L) problem size."""
+    pass
+
+
+class TxtFlagLargeDiT(nn.Module):
+    """B200 drop-in for flag_large_dit.py:128-251 (same ctor / forward / freqs_cis surface)."""
+
+    _video = False
+
+    def __init__(self, in_channels, context_dim, hidden_size=1152, depth=28, num_heads=16, max_len=1000,
+                 n_kv_heads=None, multiple_of: int = 256, ffn_dim_multiplier=None, norm_eps=1e-5, qk_norm=None,
+                 rope_scaling_factor: float = 1.0, ntk_factor: float = 1.0, num_experts=0):
+        super().__init__()
+        if qk_norm:
+            raise NotImplementedError("qk_norm=True is not used by any shipped config (flag_large_dit.py:145,270)")
+        if n_kv_heads not in (None, num_heads):
+            raise NotImplementedError("grouped KV heads are not used by any shipped config")
+        if hidden_size % num_heads or (hidden_size // num_heads) % 8:
+            raise ValueError("head_dim must be a multiple of 8")
+        self.in_channels = self.out_channels = in_channels
+        self.context_dim, self.hidden_size, self.depth, self.num_heads = context_dim, hidden_size, depth, num_heads
+        self.head_dim = hidden_size // num_heads
+        self.norm_eps = norm_eps
+        self.num_experts = num_experts if self._video else 0
+        self.ffn_hidden = _ffn_hidden(hidden_size, multiple_of, ffn_dim_multiplier)
+        D = hidden_size
+        y_dim = D if self._video else context_dim
+        self.y_dim = y_dim
+        self.t_embedder = nn.Module()
+        self.t_embedder.mlp = _Seq(_0=_Lin(256, D), _2=_Lin(D, D))
+        if self._video:
+            self.c_embedder = nn.Module()
+            self.c_embedder.mlp = _Seq(_0=_Lin(context_dim, D), _2=_Lin(D, D), _3=_LN(D))
+        self.proj_in = _Lin(in_channels, D)
+        self.cap_embedder = _Seq(_0=_LN(y_dim), _1=_Lin(y_dim, D))
+        self.blocks = nn.ModuleList([_Block(D, num_heads, y_dim, self.ffn_hidden, self.num_experts)
+                                     for _ in range(depth)])
+        self.final_layer = _Final(D, in_channels)
+        self.rope_scaling_factor, self.ntk_factor = rope_scaling_factor, ntk_factor
+        self.freqs_cis = self.precompute_freqs_cis(self.head_dim, max_len, rope_scaling_factor=rope_scaling_factor,
+                                                   ntk_factor=ntk_factor)
+        self._packed = None
+        self._rope_src = None
+        self._work = {}
+        self._ctx = None
+        self.register_load_state_dict_post_hook(lambda m, k: m.invalidate())
+
+    # ---------------------------------------------------------------- reference surface
+    @staticmethod
+    def precompute_freqs_cis(dim: int, end: int, theta: float = 10000.0, rope_scaling_factor: float = 1.0,
+                             ntk_factor: float = 1.0):
+        """complex64 [end, dim/2] = exp(i * pos/rope_scaling * (theta*ntk)^(-2j/dim)) (flag_large_dit.py:212-251)."""
+        theta = theta * ntk_factor
+        inv = 1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+        pos = torch.arange(end, dtype=torch.float32) / rope_scaling_factor
+        ang = torch.outer(pos, inv).float()
+        return torch.polar(torch.ones_like(ang), ang)
+
+    def invalidate(self):
+        self._packed = None
+        self._ctx = None
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    @torch.no_grad()
+    def forward(self, x, t, context):
+        """x [N, C, T] fp32, t [N] int64, context [N, L, Cd] fp32 -> [N, C, T] fp32."""
+        x = x.contiguous().float()
+        N, _, T = x.shape
+        self.prepare_context(context)
+        mod = self.prepare_timesteps(t.reshape(-1).to(torch.int64), per_sample=True)
+        w = self.run_blocks(x, mod[0], t_ints=[int(v) for v in t.reshape(-1).tolist()] if self.num_experts else None)
+        p = self._packed
+        v = torch.empty(N, self.out_channels, T, device=x.device, dtype=torch.float32)
+        ops.final_layer(w.h, mod[0], p["final_off"], p["final_off"] + self.hidden_size, p["final_w"], p["final_b"],
+                        N, T, v)
+        return v
+
+    # ---------------------------------------------------------------- packing
+    def _pack(self):
+        dev = self.proj_in.weight.device
+        if dev.type != "cuda":
+            raise L.Ma3Error("ma3_b200 modules run on CUDA only (no CPU fallback): call .cuda() first")
+        L.require_device()
+        D, H, F = self.hidden_size, self.num_heads, self.ffn_hidden
+        bf = torch.bfloat16
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        b16 = lambda t: t.detach().to(device=dev, dtype=bf).contiguous()
+        il = lambda w1, w3: torch.stack([w1.detach(), w3.detach()], 1).reshape(2 * w1.shape[0], w1.shape[1])
+        p = {}
+        p["proj_w"], p["proj_b"] = f32(self.proj_in.weight), f32(self.proj_in.bias)
+        m = self.t_embedder.mlp
+        p["t_w1"], p["t_b1"] = b16(getattr(m, "0").weight), f32(getattr(m, "0").bias)
+        p["t_w2"], p["t_b2"] = b16(getattr(m, "2").weight), f32(getattr(m, "2").bias)
+        ce = self.cap_embedder
+        p["cap_ln_w"], p["cap_ln_b"] = f32(getattr(ce, "0").weight), f32(getattr(ce, "0").bias)
+        p["cap_w"], p["cap_b"] = b16(getattr(ce, "1").weight), f32(getattr(ce, "1").bias)
+        if self._video:
+            cm = self.c_embedder.mlp
+            p["c_w1"], p["c_b1"] = b16(getattr(cm, "0").weight), f32(getattr(cm, "0").bias)
+            p["c_w2"], p["c_b2"] = b16(getattr(cm, "2").weight), f32(getattr(cm, "2").bias)
+            p["c_ln_w"], p["c_ln_b"] = f32(getattr(cm, "3").weight), f32(getattr(cm, "3").bias)
+        ada_w, ada_b, blocks = [], [], []
+        for blk in self.blocks:
+            a = blk.attention
+            q = {}
+            q["wqkv"] = b16(torch.cat([a.wq.weight, a.wk.weight, a.wv.weight]))
+            yw = blk.attention_y_norm.weight.detach()[None, :]  # RMSNorm_y scale folded into the projections
+            q["wkv_y"] = b16(torch.cat([a.wk_y.weight.detach() * yw, a.wv_y.weight.detach() * yw]))
+            q["wo"] = b16(a.wo.weight)
+            q["gate"] = f32(a.gate)
+            q["attn_norm"], q["ffn_norm"] = f32(blk.attention_norm.weight), f32(blk.ffn_norm.weight)
+            ff = blk.feed_forward
+            if self.num_experts:
+                band = D // self.num_experts
+                q["t_w13"] = [b16(il(e.w1.weight, e.w3.weight)) for e in ff.time_experts.values()]
+                q["t_w2"] = [b16(e.w2.weight) for e in ff.time_experts.values()]
+                # frequency expert j only sees / produces band j: slice the weights once (exact)
+                q["f_w13"] = [b16(il(e.w1.weight[:, j * band:(j + 1) * band], e.w3.weight[:, j * band:(j + 1) * band]))
+                              for j, e in enumerate(ff.freq_experts.values())]
+                q["f_w2"] = [b16(e.w2.weight[j * band:(j + 1) * band, :]) for j, e in enumerate(ff.freq_experts.values())]
+            else:
+                q["w13"] = b16(il(ff.w1.weight, ff.w3.weight))
+                q["w2"] = b16(ff.w2.weight)
+            blocks.append(q)
+            ada_w.append(getattr(blk.adaLN_modulation, "1").weight.detach())
+            ada_b.append(getattr(blk.adaLN_modulation, "1").bias.detach())
+        fl = self.final_layer
+        ada_w.append(getattr(fl.adaLN_modulation, "1").weight.detach())
+        ada_b.append(getattr(fl.adaLN_modulation, "1").bias.detach())
+        p["ada_w"], p["ada_b"] = b16(torch.cat(ada_w)), f32(torch.cat(ada_b))
+        p["final_off"] = 6 * D * self.depth
+        p["mod_cols"] = 6 * D * self.depth + 2 * D
+        p["final_w"], p["final_b"] = f32(fl.linear.weight), f32(fl.linear.bias)
+        p["blocks"] = blocks
+        self._packed = p
+        self._rope_src = None
+        self._ctx = None
+
+    def _ensure(self):
+        if self._packed is None:
+            self._pack()
+        fc = self.freqs_cis
+        if self._rope_src is not fc:  # callers overwrite the table on the live module (NTK scaling)
+            dev = self.proj_in.weight.device
+            self._packed["rope"] = torch.view_as_real(fc.to("cpu")).float().contiguous().to(dev)
+            self._rope_src = fc
+        return self._packed
+
+    def _workspace(self, N, T):
+        key = (N, T)
+        w = self._work.get(key)
+        if w is None:
+            dev = self.proj_in.weight.device
+            D, H, F = self.hidden_size, self.num_heads, self.ffn_hidden
+            hd = self.head_dim
+            hdp = 64 if hd <= 64 else 128
+            if hd > 128:
+                raise L.Ma3Error("head_dim > 128 not supported")
+            Tp = (T + 7) // 8 * 8
+            bf = torch.bfloat16
+            w = _Work()
+            w.hdp, w.Tp = hdp, Tp
+            w.h = torch.empty(N * T, D, device=dev, dtype=torch.float32)
+            w.u = torch.empty(N * T, D, device=dev, dtype=bf)
+            w.q = torch.zeros(N, H, T, hdp, device=dev, dtype=bf)
+            w.k = torch.zeros(N, H, T, hdp, device=dev, dtype=bf)
+            w.vt = torch.zeros(N, H, hdp, Tp, device=dev, dtype=bf)
+            w.att = torch.empty(N * T, D, device=dev, dtype=bf)
+            w.mid = torch.empty(N * T, F, device=dev, dtype=bf)
+            if self.num_experts:
+                w.y1 = torch.empty(N * T, D, device=dev, dtype=bf)
+            self._work[key] = w
+        return w
+
+    # ---------------------------------------------------------------- step-invariant work
+    @torch.no_grad()
+    def prepare_context(self, context):
+        """RMSNorm_y(y), every layer's cross K/V and the caption embedding -- computed once per conditioning
+        (the reference recomputes them in every block of every step, flag_large_dit_moe.py:390-392)."""
+        p = self._ensure()
+        dev = self.proj_in.weight.device
+        context = context.to(device=dev, dtype=torch.float32).contiguous()
+        N, Lc, Cd = context.shape
+        D, H, hd = self.hidden_size, self.num_heads, self.head_dim
+        hdp = 64 if hd <= 64 else 128
+        Lp = (Lc + 7) // 8 * 8
+        bf = torch.bfloat16
+        c = self._ctx
+        if c is None or c["shape"] != (N, Lc, Cd):
+            c = {"shape": (N, Lc, Cd)}
+            c["yn"] = torch.empty(N * Lc, self.y_dim, device=dev, dtype=bf)
+            c["ky"] = torch.zeros(self.depth, N, H, Lc, hdp, device=dev, dtype=bf)
+            c["vyt"] = torch.zeros(self.depth, N, H, hdp, Lp, device=dev, dtype=bf)
+            c["pool"] = torch.empty(N, self.y_dim, device=dev, dtype=bf)
+            c["cap"] = torch.empty(N, D, device=dev, dtype=torch.float32)
+            if self._video:
+                c["c1"] = torch.empty(N * Lc, D, device=dev, dtype=bf)
+                c["c2"] = torch.empty(N * Lc, D, device=dev, dtype=torch.float32)
+                c["y"] = torch.empty(N * Lc, D, device=dev, dtype=torch.float32)
+                c["ctx16"] = torch.empty(N * Lc, Cd, device=dev, dtype=bf)
+            self._ctx = c
+        if self._video:
+            # c = LayerNorm(W2 gelu(W1 ctx + b1) + b2)   (flag_large_dit_moe.py:151-162, 680)
+            ops.cast(context.view(N * Lc, Cd), c["ctx16"])
+            ops.gemm(c["ctx16"], p["c_w1"], M=N * Lc, N=D, K=Cd, out=c["c1"], bias=p["c_b1"], act=2)
+            ops.gemm(c["c1"], p["c_w2"], M=N * Lc, N=D, K=D, out=c["c2"], bias=p["c_b2"])
+            ops.layernorm_rows(c["c2"], p["c_ln_w"], p["c_ln_b"], c["y"])
+            y = c["y"].view(N, Lc, D)
+        else:
+            y = context
+        ops.pool_layernorm(y, p["cap_ln_w"], p["cap_ln_b"], c["pool"])
+        ops.gemm(c["pool"], p["cap_w"], M=N, N=D, K=self.y_dim, out=c["cap"], bias=p["cap_b"])
+        ops.rmsnorm_modulate(y.view(N * Lc, self.y_dim), None, c["yn"], eps=self.norm_eps)
+        for i, q in enumerate(p["blocks"]):
+            ops.gemm(c["yn"], q["wkv_y"], M=N * Lc, N=2 * D, K=self.y_dim, epi=L.EPI_QKV_ROPE, q_out=c["ky"][i],
+                     k_out=c["ky"][i], vt_out=c["vyt"][i], rope=None, model_dim=D, head_dim=hd, head_dim_pad=hdp,
+                     tokens=Lc, tokens_pad=Lp, first_section=1)
+        return c
+
+    @torch.no_grad()
+    def prepare_timesteps(self, t, per_sample=False):
+        """adaLN modulation of every block (+ final layer) for all requested timesteps in ONE GEMM.
+        t: int64 [S] (per_sample=False: every sample shares t[s]) or [N] (per_sample=True: one step, t per sample).
+        Returns mod fp32 [S, N, depth*6D + 2D]."""
+        p = self._ensure()
+        c = self._ctx
+        dev = self.proj_in.weight.device
+        N = c["shape"][0]
+        D = self.hidden_size
+        bf = torch.bfloat16
+        t = t.to(dev)
+        Mt = t.numel()
+        S = 1 if per_sample else Mt
+        if per_sample and Mt != N:
+            raise ValueError(f"t has {Mt} entries for a batch of {N}")
+        e0 = torch.empty(Mt, 256, device=dev, dtype=bf)
+        e1 = torch.empty(Mt, D, device=dev, dtype=bf)
+        temb = torch.empty(Mt, D, device=dev, dtype=torch.float32)
+        ops.timestep_embed(t, e0)
+        ops.gemm(e0, p["t_w1"], M=Mt, N=D, K=256, out=e1, bias=p["t_b1"], act=1)
+        ops.gemm(e1, p["t_w2"], M=Mt, N=D, K=D, out=temb, bias=p["t_b2"])
+        a = torch.empty(S * N, D, device=dev, dtype=bf)
+        ops.adaln_input(temb, c["cap"], a, S, N, 0 if per_sample else 1, 1 if per_sample else 0)
+        mod = torch.empty(S, N, p["mod_cols"], device=dev, dtype=torch.float32)
+        ops.gemm(a, p["ada_w"], M=S * N, N=p["mod_cols"], K=D, out=mod, bias=p["ada_b"])
+        return mod
+
+    # ---------------------------------------------------------------- per-step work
+    @torch.no_grad()
+    def run_blocks(self, x, mod, t_ints=None):
+        """x [xB, C, T] fp32 (xB divides N: the CFG halves share x), mod [N, mod_cols] -> workspace with w.h filled."""
+        p = self._ensure()
+        c = self._ctx
+        N = c["shape"][0]
+        Lc = c["shape"][1]
+        T = x.shape[-1]
+        D, H, hd, F = self.hidden_size, self.num_heads, self.head_dim, self.ffn_hidden
+        w = self._workspace(N, T)
+        M = N * T
+        qs = math.log2(math.e) / math.sqrt(hd)
+        if T > p["rope"].shape[0]:
+            raise ValueError(f"sequence length {T} exceeds the RoPE table ({p['rope'].shape[0]} positions)")
+        ops.proj_in(x, p["proj_w"], p["proj_b"], w.h, N)
+        for i, q in enumerate(p["blocks"]):
+            o = 6 * D * i
+            ops.rmsnorm_modulate(w.h, q["attn_norm"], w.u, mod=mod, shift_off=o, scale_off=o + D, rows_per_sample=T,
+                                 eps=self.norm_eps)
+            ops.gemm(w.u, q["wqkv"], M=M, N=3 * D, K=D, epi=L.EPI_QKV_ROPE, q_out=w.q, k_out=w.k, vt_out=w.vt,
+                     rope=p["rope"], model_dim=D, head_dim=hd, head_dim_pad=w.hdp, tokens=T, tokens_pad=w.Tp, q_scale=qs)
+            ops.attention(w.q, w.k, w.vt, c["ky"][i] if Lc else None, c["vyt"][i] if Lc else None, q["gate"], w.att,
+                          hd=hd)
+            ops.gemm(w.att, q["wo"], M=M, N=D, K=D, epi=L.EPI_GATE_RES, out=w.h, gate=mod[:, o + 2 * D:o + 3 * D],
+                     rows_per_sample=T)
+            ops.rmsnorm_modulate(w.h, q["ffn_norm"], w.u, mod=mod, shift_off=o + 3 * D, scale_off=o + 4 * D,
+                                 rows_per_sample=T, eps=self.norm_eps)
+            gate2 = mod[:, o + 5 * D:o + 6 * D]
+            if self.num_experts:
+                self._moe_ffn(q, w, gate2, t_ints, N, T)
+            else:
+                ops.gemm(w.u, q["w13"], M=M, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=w.mid, out_ld=F)
+                ops.gemm(w.mid, q["w2"], M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=w.h, gate=gate2, rows_per_sample=T)
+        return w
+
+    def _moe_ffn(self, q, w, gate2, t_ints, N, T):
+        """flag_large_dit_moe.py:516-538: time expert e = t // 250 (per sample; a pointer switch, no routing kernel),
+        then per-band frequency experts on sliced weights (exact, because masked columns contribute exact zeros)."""
+        D, F, E = self.hidden_size, self.ffn_hidden, self.num_experts
+        band = D // E
+        n = 0
+        while n < N:  # runs of consecutive samples sharing an expert
+            e = int(t_ints[n]) // 250
+            m = n + 1
+            while m < N and int(t_ints[m]) // 250 == e:
+                m += 1
+            rows = slice(n * T, m * T)
+            if 0 <= e < E:
+                ops.gemm(w.u[rows], q["t_w13"][e], M=(m - n) * T, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=w.mid[rows], out_ld=F)
+                ops.gemm(w.mid[rows], q["t_w2"][e], M=(m - n) * T, N=D, K=F, out=w.y1[rows])
+            else:
+                w.y1[rows].zero_()
+            n = m
+        M = N * T
+        for j in range(E):
+            ops.gemm(w.y1[:, j * band:], q["f_w13"][j], M=M, N=2 * F, K=band, a_ld=D, epi=L.EPI_SWIGLU, out=w.mid,
+                     out_ld=F)
+            ops.gemm(w.mid, q["f_w2"][j], M=M, N=band, K=F, epi=L.EPI_GATE_RES, out=w.h[:, j * band:], out_ld=D,
+                     gate=gate2[:, j * band:(j + 1) * band], rows_per_sample=T)
+
+
+class TxtFlagLargeImprovedDiTV2(TxtFlagLargeDiT):
+    """flag_large_dit.py:256-299 (the class every txt2audio / txt2music config targets)."""
+
+    def __init__(self, in_channels, context_dim, hidden_size=1152, depth=28, num_heads=16, max_len=1000):
+        super().__init__(in_channels, context_dim, hidden_size, depth, num_heads, max_len)
+
+
+class VideoFlagLargeDiT(TxtFlagLargeDiT):
+    """flag_large_dit_moe.py:613-740: ConditionEmbedder on the context, MoE feed-forward (time + frequency experts)."""
+
+    _video = True
+
+    def __init__(self, in_channels, context_dim, hidden_size=1152, depth=28, num_heads=16, max_len=1000,
+                 n_kv_heads=None, multiple_of: int = 256, ffn_dim_multiplier=None, norm_eps=1e-5, qk_norm=None,
+                 rope_scaling_factor: float = 1.0, ntk_factor: float = 1, num_experts=8):
+        super().__init__(in_channels, context_dim, hidden_size, depth, num_heads, max_len, n_kv_heads, multiple_of,
+                         ffn_dim_multiplier, norm_eps, qk_norm, rope_scaling_factor, ntk_factor, num_experts)

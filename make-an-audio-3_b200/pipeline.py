@@ -1,0 +1,99 @@
+"""Text/video-to-audio sampling pipeline: CFM sampling -> decode_first_stage -> vocode, the hot path of
+scripts/txt2audio_for_2cap_flow.py:151-190 (GenSamples.gen_test_sample) with the conditioner replaced by caller-
+supplied embeddings.  Everything stays on the device between the three stages (the reference round-trips the mel
+through numpy, txt2audio_for_2cap_flow.py:181-188).
+
+Multi-GPU: prompts are independent, so `shard_prompts` gives rank r the prompts r::world and `gather_waveforms` is the
+only collective (one NCCL all-gather of the finished waveforms).
+"""
+import torch
+
+from . import lib as L
+from .dit import TxtFlagLargeImprovedDiTV2, VideoFlagLargeDiT
+from .sampler import CFMSampler
+from .vae import AutoencoderKL
+from .vocoder import VocoderBigVGAN
+
+# the reference's shipped model configs (configs/*.yaml: unet_config.params), keyed by the names BASELINE.json uses
+MODEL_CONFIGS = {
+    "M": dict(in_channels=20, context_dim=1024, hidden_size=768, num_heads=32, depth=16, max_len=1000),
+    "XL": dict(in_channels=20, context_dim=1024, hidden_size=1152, num_heads=16, depth=28, max_len=1000),
+    "XXL": dict(in_channels=20, context_dim=1024, hidden_size=1536, num_heads=32, depth=32, max_len=1000),
+    "MOE": dict(in_channels=20, context_dim=768, hidden_size=768, num_heads=32, depth=16, max_len=1000, num_experts=4),
+}
+# first_stage_config.params.ddconfig of every shipped config (configs/txt2audio-cfm-cfg.yaml:50-66)
+VAE_DDCONFIG = dict(double_z=True, in_channels=80, out_ch=80, z_channels=20, kernel_size=5, ch=384, ch_mult=[1, 2, 4],
+                    num_res_blocks=2, attn_layers=[3], down_layers=[0], dropout=0.0)
+
+
+class Txt2AudioPipeline:
+    """model.sample_cfg(...) -> model.decode_first_stage(...) -> vocoder.vocode(...) on one GPU."""
+
+    def __init__(self, dit, vae, vocoder, scale_factor=1.0, mel_dim=20, mel_length=256, use_graph=True):
+        self.dit, self.first_stage_model, self.vocoder = dit, vae, vocoder
+        self.scale_factor = float(scale_factor)
+        self.mel_dim, self.mel_length, self.channels = mel_dim, mel_length, 0
+        self.sampler = CFMSampler(self, use_graph=use_graph)
+
+    # CFMSampler looks the DiT up as model.model.diffusion_model (the reference's nesting, ddpm.py:1402)
+    @property
+    def model(self):
+        return self
+
+    @property
+    def diffusion_model(self):
+        return self.dit
+
+    def sample(self, cond, batch_size=16, timesteps=None, shape=None, x_latent=None, t_start=None, **kw):
+        return self.sampler.sample(cond, batch_size, timesteps, shape, x_latent, t_start)
+
+    def sample_cfg(self, cond, unconditional_guidance_scale, unconditional_conditioning, batch_size=16, timesteps=None,
+                   shape=None, x_latent=None, t_start=None, **kw):
+        return self.sampler.sample_cfg(cond, unconditional_guidance_scale, unconditional_conditioning, batch_size,
+                                       timesteps, shape, x_latent, t_start)
+
+    @torch.no_grad()
+    def decode_first_stage(self, z):
+        """ddpm_audio.py:358-371: z / scale_factor -> first_stage_model.decode."""
+        return self.first_stage_model.decode((1.0 / self.scale_factor) * z)
+
+    @torch.no_grad()
+    def generate(self, cond, uncond, x0, scale=3.0, timesteps=25):
+        """cond/uncond [B, L, Cd], x0 [B, 20, T] (device tensors) -> waveforms [B, 2T*hop] on the device."""
+        B = x0.shape[0]
+        z, _ = self.sample_cfg(cond, scale, uncond, B, timesteps=timesteps, x_latent=x0)
+        mel = self.decode_first_stage(z)
+        return self.vocoder.vocode_tensor(mel)
+
+
+def build_random_pipeline(model="M", vocoder_h=None, seed=0, device="cuda", use_graph=True, state_dicts=None):
+    """Random-init pipeline of a shipped config (no checkpoints exist offline).  `state_dicts` = (dit, vae, vocoder)
+    state_dicts keyed like the reference's; when omitted the constructors' own random init is used."""
+    L.require_device()
+    cfg = dict(MODEL_CONFIGS[model])
+    torch.manual_seed(seed)
+    if "num_experts" in cfg:
+        dit = VideoFlagLargeDiT(**cfg)
+    else:
+        dit = TxtFlagLargeImprovedDiTV2(**cfg)
+    vae = AutoencoderKL(embed_dim=20, ddconfig=dict(VAE_DDCONFIG), lossconfig=None)
+    voc = VocoderBigVGAN(device=device, h=vocoder_h, state_dict=state_dicts[2] if state_dicts else None)
+    if state_dicts:
+        dit.load_state_dict(state_dicts[0], strict=True)
+        vae.load_state_dict(state_dicts[1], strict=True)
+    return Txt2AudioPipeline(dit.to(device), vae.to(device), voc, use_graph=use_graph)
+
+
+def shard_prompts(n_prompts, rank, world):
+    """Indices of the prompts rank `rank` generates (round-robin)."""
+    return list(range(rank, n_prompts, world))
+
+
+def gather_waveforms(wav, group=None):
+    """The path's single collective: all-gather [B_local, samples] -> [world * B_local, samples] (rank-major)."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return wav
+    out = [torch.empty_like(wav) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, wav.contiguous(), group=group)
+    return torch.cat(out)

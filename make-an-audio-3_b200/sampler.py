@@ -1,0 +1,156 @@
+"""CFM ODE sampling with the reference's operator surface.
+
+`CFMSampler(model, num_timesteps)` mirrors ldm/models/diffusion/cfm1_audio_sampler.py:26-104 and the
+`CFM.sample` / `CFM.sample_cfg` methods of ldm/models/diffusion/cfm1_audio.py:60-111: same arguments, same returns
+`(x_final [B,C,T], traj [n_points,B,C,T])`.  `model` is either a B200 DiT from ma3_b200.dit or any wrapper exposing it
+as `.model.diffusion_model` (the reference's CFM / LatentDiffusion_audio object with its `unet_config.target` swapped).
+
+The fixed-step Euler integrator of torchdyn (un-vendored dependency of the reference) is restated here:
+x_{k+1} = x_k + dt_k f(t_k, x_k), t advanced as t + dt in fp32, integer timestep = trunc(1000 t)
+(cfm1_audio.py:103,156).  What changes on B200: the cond/uncond pair is one batched pass, context K/V and all adaLN
+modulations are computed once, the guidance combine and the Euler update are fused into the final-layer kernel, and
+the whole step loop is replayed from a CUDA graph (no host synchronisation inside the loop).
+"""
+import torch
+
+from . import lib as L
+from . import ops
+from .dit import TxtFlagLargeDiT
+
+
+def euler_schedule(n_points=None, t_start=None):
+    """Integer timesteps and step sizes exactly as the reference's loop produces them (fp32 arithmetic on t)."""
+    ts = torch.linspace(0, 1, 25 if n_points is None else n_points)
+    if t_start is not None:
+        ts = ts[t_start:]
+    if len(ts) < 2:
+        raise ValueError("need at least two time points")
+    t = ts[0]
+    dt = ts[1] - t
+    ints, dts = [], []
+    for k in range(1, len(ts)):
+        ints.append(int((t * 1000).long()))
+        dts.append(float(dt))
+        t = t + dt
+        if k < len(ts) - 1:
+            dt = ts[k + 1] - t
+    return ints, dts
+
+
+def _find_dit(model):
+    if isinstance(model, TxtFlagLargeDiT):
+        return model
+    inner = getattr(getattr(model, "model", None), "diffusion_model", None)
+    if isinstance(inner, TxtFlagLargeDiT):
+        return inner
+    raise L.Ma3Error("CFMSampler needs a ma3_b200 DiT (directly or as model.model.diffusion_model)")
+
+
+def _as_context(cond):
+    """Mirror DiffusionWrapper.forward's crossattn handling (ddpm.py:1413-1420): lists are concatenated on dim 1."""
+    if isinstance(cond, dict):
+        cond = cond.get("c_crossattn", next(iter(cond.values())))
+    if isinstance(cond, (list, tuple)):
+        cond = torch.cat(list(cond), 1)
+    return cond
+
+
+class CFMSampler:
+    def __init__(self, model, num_timesteps=1000, schedule="linear", use_graph=True):
+        self.model = model
+        self.dit = _find_dit(model)
+        self.num_timesteps = num_timesteps
+        self.use_graph = use_graph
+        self._graphs = {}
+
+    # ---------------------------------------------------------------- reference surface
+    def _default_shape(self, batch_size):
+        m = self.model
+        mel_dim = getattr(m, "mel_dim", self.dit.in_channels)
+        mel_length = getattr(m, "mel_length", 256)
+        if getattr(m, "channels", 0) > 0:
+            raise L.Ma3Error("4-D latents (channels > 0) are not produced by the 1-D Next-DiT path")
+        return (batch_size, mel_dim, mel_length)
+
+    @staticmethod
+    def _slice(cond, batch_size):
+        if cond is None:
+            return None
+        if isinstance(cond, dict):
+            return {k: (v[:batch_size] if not isinstance(v, list) else [x[:batch_size] for x in v]) for k, v in cond.items()}
+        return [c[:batch_size] for c in cond] if isinstance(cond, list) else cond[:batch_size]
+
+    @torch.no_grad()
+    def sample(self, cond, batch_size=16, timesteps=None, shape=None, x_latent=None, t_start=None, **kwargs):
+        return self._run(cond, None, None, batch_size, timesteps, shape, x_latent, t_start)
+
+    @torch.no_grad()
+    def sample_cfg(self, cond, unconditional_guidance_scale, unconditional_conditioning, batch_size=16, timesteps=None,
+                   shape=None, x_latent=None, t_start=None, **kwargs):
+        return self._run(cond, float(unconditional_guidance_scale), unconditional_conditioning, batch_size, timesteps,
+                         shape, x_latent, t_start)
+
+    # ---------------------------------------------------------------- engine
+    def _run(self, cond, scale, uncond, batch_size, timesteps, shape, x_latent, t_start):
+        dit = self.dit
+        dev = dit.proj_in.weight.device
+        if shape is None:
+            shape = self._default_shape(batch_size)
+        c = _as_context(self._slice(cond, batch_size)).to(dev).float()
+        cfg = scale is not None
+        if cfg:
+            uc = _as_context(uncond).to(dev).float()
+            ctx = torch.cat([uc, c])          # batch order [uncond, cond] (cfm1_audio.py:158)
+        else:
+            ctx = c
+        x0 = torch.randn(shape, device=dev) if x_latent is None else x_latent.to(dev).float()
+        B, C, T = x0.shape
+        N = ctx.shape[0]
+        if N != (2 * B if cfg else B):
+            raise ValueError(f"conditioning batch {ctx.shape[0]} does not match latent batch {B}")
+        ints, dts = euler_schedule(timesteps, t_start)
+        S = len(ints)
+
+        cbuf = dit.prepare_context(ctx)
+        # the plan (buffers + captured graph) is valid for these shapes, this schedule and these context buffers
+        key = (cfg, B, C, T, tuple(ctx.shape), tuple(ints), scale, cbuf["ky"].data_ptr(), id(dit._packed))
+        st = self._graphs.get(key)
+        if st is None:
+            st = {"traj": torch.empty(S + 1, B, C, T, device=dev, dtype=torch.float32),
+                  "mod": torch.empty(S, N, dit._ensure()["mod_cols"], device=dev, dtype=torch.float32),
+                  "v": torch.empty(N, C, T, device=dev, dtype=torch.float32), "graph": None}
+            self._graphs = {key: st}          # keep one plan: buffers are large
+        st["mod"].copy_(dit.prepare_timesteps(torch.tensor(ints, dtype=torch.int64)))
+        st["traj"][0].copy_(x0)
+
+        def loop():
+            for k in range(S):
+                self._step(st, k, ints[k], dts[k], scale, cfg, N, T)
+
+        if not self.use_graph:
+            loop()
+        elif st["graph"] is None:
+            loop()                             # eager pass: allocates workspaces, configures kernels
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loop()
+            st["graph"] = g                    # the eager pass above already produced this call's trajectory
+        else:
+            st["graph"].replay()
+        traj = st["traj"].clone()
+        return traj[-1], traj
+
+    def _step(self, st, k, t_int, dt, scale, cfg, N, T):
+        dit = self.dit
+        p = dit._packed
+        D = dit.hidden_size
+        mod = st["mod"][k]
+        w = dit.run_blocks(st["traj"][k], mod, t_ints=[t_int] * N if dit.num_experts else None)
+        off = p["final_off"]
+        if cfg:
+            ops.final_layer_cfg_euler(w.h, mod, off, off + D, p["final_w"], p["final_b"], N, T, scale, dt,
+                                      st["traj"][k], st["traj"][k + 1])
+        else:
+            ops.final_layer(w.h, mod, off, off + D, p["final_w"], p["final_b"], N, T, st["v"])
+            ops.cfg_euler_update(st["v"], st["traj"][k], st["traj"][k + 1], dt, 0.0, cfg=False)
