@@ -7,6 +7,30 @@ import torch
 from . import lib as L
 
 
+# When set to a list, every wrapped launch is bracketed by CUDA events on the launching stream and recorded as
+# (kernel tag, start event, end event, algorithmic work: FLOPs for GEMM/attention, bytes for HBM-bound kernels).
+# bench.py uses this for the live roofline measurement; None (default) adds no overhead.
+PROFILE = None
+
+
+class _Span:
+    def __init__(self, tag, work):
+        self.tag, self.work = tag, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            self.e1.record()
+            PROFILE.append((self.tag, self.e0, self.e1, self.work))
+        return False
+
+
 def declare(lib):
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     protos = {
@@ -92,14 +116,19 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
     d.first_section = first_section
     d.act = act
     d.tile_n = tile_n
-    L.check(lib.ma3_gemm(C.byref(d), L.stream_ptr()), "ma3_gemm")
+    with _Span("tap_gemm/" + _EPI_NAMES[epi], 2.0 * M * N * K * len(taps) * batch):
+        L.check(lib.ma3_gemm(C.byref(d), L.stream_ptr()), "ma3_gemm")
     return out
 
 
+_EPI_NAMES = {L.EPI_STORE: "store", L.EPI_GATE_RES: "gate_res", L.EPI_SWIGLU: "swiglu", L.EPI_QKV_ROPE: "qkv_rope"}
+
+
 # ---------------------------------------------------------------------------------------------------- other ops
-def _call(name, *args):
+def _call(name, *args, work=0.0):
     lib = L.require_device()
-    L.check(getattr(lib, name)(*args, L.stream_ptr()), name)
+    with _Span(name[4:], work):
+        L.check(getattr(lib, name)(*args, L.stream_ptr()), name)
 
 
 def rmsnorm_modulate(x, w, out, *, mod=None, shift_off=0, scale_off=0, rows_per_sample=1, eps=1e-5):
@@ -107,7 +136,8 @@ def rmsnorm_modulate(x, w, out, *, mod=None, shift_off=0, scale_off=0, rows_per_
     M, D = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
     _call("ma3_rmsnorm_modulate", L.ptr(x), L.ptr(w), L.ptr(mod), mod.stride(0) if mod is not None else 0,
-          shift_off, scale_off, rows_per_sample, L.ptr(out), L.dt(out), M, D, eps)
+          shift_off, scale_off, rows_per_sample, L.ptr(out), L.dt(out), M, D, eps,
+          work=float(M) * D * (4 + out.element_size()))
     return out
 
 
@@ -158,7 +188,7 @@ def layernorm_rows(x, w, b, out, eps=1e-5):
 def groupnorm_swish(x, w, b, out, *, groups=32, eps=1e-6, swish=True):
     B, T, Cc = x.shape
     _call("ma3_groupnorm_swish", L.ptr(x), L.dt(x), L.ptr(w), L.ptr(b), L.ptr(out), L.dt(out), B, T, Cc, groups, eps,
-          int(swish))
+          int(swish), work=float(B) * T * Cc * (x.element_size() + out.element_size()))
     return out
 
 
@@ -202,7 +232,8 @@ def act1d(x, out, alpha, beta, logscale=True):
         _call("ma3_act1d_set_filter", taps)
         _filter_set = True
     B, T, Cc = x.shape
-    _call("ma3_act1d", L.ptr(x), L.dt(x), L.ptr(out), L.dt(out), L.ptr(alpha), L.ptr(beta), B, T, Cc, int(logscale))
+    _call("ma3_act1d", L.ptr(x), L.dt(x), L.ptr(out), L.dt(out), L.ptr(alpha), L.ptr(beta), B, T, Cc, int(logscale),
+          work=float(B) * T * Cc * (x.element_size() + out.element_size()))
     return out
 
 
@@ -227,7 +258,7 @@ def attention(q, k, vt, ky, vyt, gate, out, *, hd):
     Lc = ky.shape[2] if ky is not None else 0
     Lp = vyt.shape[-1] if vyt is not None else 0
     _call("ma3_attention", L.ptr(q), L.ptr(k), L.ptr(vt), L.ptr(ky), L.ptr(vyt), L.ptr(gate), L.ptr(out), L.dt(q), NS, H,
-          T, Tp, Lc, Lp, hd, hdp)
+          T, Tp, Lc, Lp, hd, hdp, work=4.0 * NS * H * T * (T + Lc) * hd)
     return out
 
 

@@ -78,6 +78,8 @@ def build_random_pipeline(model="M", vocoder_h=None, seed=0, device="cuda", use_
         dit = TxtFlagLargeImprovedDiTV2(**cfg)
     vae = AutoencoderKL(embed_dim=20, ddconfig=dict(VAE_DDCONFIG), lossconfig=None)
     voc = VocoderBigVGAN(device=device, h=vocoder_h, state_dict=state_dicts[2] if state_dicts else None)
+    for blk in dit.blocks:   # the constructor leaves the cross-attention gate at zero; make it count
+        blk.attention.gate.data.normal_(0.0, 0.5)
     if state_dicts:
         dit.load_state_dict(state_dicts[0], strict=True)
         vae.load_state_dict(state_dicts[1], strict=True)

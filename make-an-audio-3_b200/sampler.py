@@ -18,6 +18,10 @@ from . import ops
 from .dit import TxtFlagLargeDiT
 
 
+# kernel launches replayed from captured CUDA graphs (ma3_launch_count only sees launches enqueued through the C ABI)
+GRAPH_REPLAY_LAUNCHES = 0
+
+
 def euler_schedule(n_points=None, t_start=None):
     """Integer timesteps and step sizes exactly as the reference's loop produces them (fp32 arithmetic on t)."""
     ts = torch.linspace(0, 1, 25 if n_points is None else n_points)
@@ -133,11 +137,15 @@ class CFMSampler:
             loop()                             # eager pass: allocates workspaces, configures kernels
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
             with torch.cuda.graph(g):
                 loop()
+            st["graph_launches"] = L.launch_count() - n0
             st["graph"] = g                    # the eager pass above already produced this call's trajectory
         else:
+            global GRAPH_REPLAY_LAUNCHES
             st["graph"].replay()
+            GRAPH_REPLAY_LAUNCHES += st["graph_launches"]
         traj = st["traj"].clone()
         return traj[-1], traj
 
