@@ -47,7 +47,7 @@ __device__ __forceinline__ void accumulate_o(uint32_t taddr, float (&acc)[HD], f
 }
 
 template <int HDP, int HD, int BKV>
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_constant__ AttnParams p) {
   constexpr int HDC = HDP / 64;              // 64-element chunks along head dim
   constexpr int KVC = BKV / 64;              // 64-key chunks per KV tile
   constexpr uint32_t kQBytes = 128 * HDP * 2;
@@ -159,15 +159,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   } else {
     const int row = warp * 32 + lane;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    float tot[HD];
+    // normalised self-attention result parked as packed bf16 pairs while the cross segment accumulates
+    // (halves its register footprint so two CTAs fit per SM; it is rounded to 16 bits on output anyway)
+    uint32_t stash[HD / 2];
 #pragma unroll
-    for (int e = 0; e < HD; ++e) tot[e] = 0.f;
+    for (int e = 0; e < HD / 2; ++e) stash[e] = 0u;
     int it = 0;
+    float acc[HD];
     for (int seg = 0; seg < 2; ++seg) {
       const int ntl = seg ? n_cross : n_self;
       const int kvlen = seg ? p.L : p.T;
       if (ntl == 0) continue;
-      float acc[HD];
 #pragma unroll
       for (int e = 0; e < HD; ++e) acc[e] = 0.f;
       float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
@@ -177,17 +179,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         const int kv0 = j * BKV;
         float mx = m;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BKV; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_S + lane_base + c0, r);
+        for (int c0 = 0; c0 < BKV; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_S + lane_base + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
+          for (int e = 0; e < 16; ++e) {
             const float v = (kv0 + c0 + e < kvlen) ? __uint_as_float(r[e]) : -INFINITY;
             mx = fmaxf(mx, v);
           }
         }
-        const float alpha = exp2f(m - mx);
+        const float alpha = ex2_approx(m - mx);
         if (j > 0) {
           mbar_wait(o_full, (it - 1) & 1);
           tc_fence_after();
@@ -195,23 +197,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         }
         float rowsum = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BKV; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_S + lane_base + c0, r);
+        for (int c0 = 0; c0 < BKV; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_S + lane_base + c0, r);
           tmem_ld_wait();
-          uint32_t pk[16];
+          uint32_t pk[8];
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float p0 = (kv0 + c0 + e < kvlen) ? exp2f(__uint_as_float(r[e]) - mx) : 0.f;
-            const float p1 = (kv0 + c0 + e + 1 < kvlen) ? exp2f(__uint_as_float(r[e + 1]) - mx) : 0.f;
+          for (int e = 0; e < 16; e += 2) {
+            const float p0 = (kv0 + c0 + e < kvlen) ? ex2_approx(__uint_as_float(r[e]) - mx) : 0.f;
+            const float p1 = (kv0 + c0 + e + 1 < kvlen) ? ex2_approx(__uint_as_float(r[e + 1]) - mx) : 0.f;
             rowsum += p0 + p1;
             pk[e >> 1] = (p.dtype == MA3_BF16) ? pack_bf16(p0, p1) : pack_f16(p0, p1);
           }
-          // 32 keys = 64 B = four 16-byte units of this row inside the 64-key chunk (128 B per row)
+          // 16 keys = 32 B = two 16-byte units of this row inside the 64-key chunk (128 B per row)
           uint8_t* chunk = sP + (c0 >> 6) * (128 * 128) + row * 128;
           const int u0 = (c0 & 63) >> 3;  // first 16-byte unit
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 2; ++u) {
             const int pos = (u0 + u) ^ (row & 7);
             *reinterpret_cast<uint4*>(chunk + pos * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
           }
@@ -227,8 +229,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       tc_fence_after();
       accumulate_o<HD>(tmem_O + lane_base, acc, alpha_prev);
       const float f = (seg ? tanhf(p.gate[h]) : 1.f) / l;
+      if (seg == 0 && n_cross > 0) {
 #pragma unroll
-      for (int e = 0; e < HD; ++e) tot[e] = fmaf(acc[e], f, tot[e]);
+        for (int e = 0; e < HD; e += 2) stash[e >> 1] = pack_bf16(acc[e] * f, acc[e + 1] * f);
+      } else {
+#pragma unroll
+        for (int e = 0; e < HD; e += 2) {
+          const float2 sv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&stash[e >> 1]));
+          acc[e] = fmaf(acc[e], f, sv.x);
+          acc[e + 1] = fmaf(acc[e + 1], f, sv.y);
+        }
+      }
     }
     if (q0 + row < p.T) {
       const long long o = ((long long)ns * p.T + q0 + row) * p.D + (long long)h * HD;
@@ -236,11 +247,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
       for (int e = 0; e < HD; e += 8) {
         uint4 u;
         if (p.dtype == MA3_BF16)
-          u = make_uint4(pack_bf16(tot[e], tot[e + 1]), pack_bf16(tot[e + 2], tot[e + 3]),
-                         pack_bf16(tot[e + 4], tot[e + 5]), pack_bf16(tot[e + 6], tot[e + 7]));
+          u = make_uint4(pack_bf16(acc[e], acc[e + 1]), pack_bf16(acc[e + 2], acc[e + 3]),
+                         pack_bf16(acc[e + 4], acc[e + 5]), pack_bf16(acc[e + 6], acc[e + 7]));
         else
-          u = make_uint4(pack_f16(tot[e], tot[e + 1]), pack_f16(tot[e + 2], tot[e + 3]),
-                         pack_f16(tot[e + 4], tot[e + 5]), pack_f16(tot[e + 6], tot[e + 7]));
+          u = make_uint4(pack_f16(acc[e], acc[e + 1]), pack_f16(acc[e + 2], acc[e + 3]),
+                         pack_f16(acc[e + 4], acc[e + 5]), pack_f16(acc[e + 6], acc[e + 7]));
         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + o + e) = u;
       }
     }

@@ -42,8 +42,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // out[m, :] = rms(x[m, :]) * w * (1 + scale[sample]) + shift[sample]     (one warp per row, row cached in registers)
 constexpr int kMaxVecPerLane = 16;  // D <= 2048
 
-template <typename TOut>
-__global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(const float* __restrict__ x, const float* __restrict__ w,
+template <typename TOut, int kVec>
+__global__ void __launch_bounds__(128) rmsnorm_modulate_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ mod, long long mod_ld,
                                                                int shift_off, int scale_off, int rows_per_sample,
                                                                TOut* __restrict__ out, int M, int D, float eps) {
@@ -52,10 +52,10 @@ __global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(const float* __re
   if (row >= M) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
   const int nvec = D >> 2;
-  float4 v[kMaxVecPerLane];
+  float4 v[kVec];
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxVecPerLane; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int j = i * 32 + lane;
     if (j < nvec) {
       v[i] = xr[j];
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(const float* __re
     sh = mod + base + shift_off;
   }
 #pragma unroll
-  for (int i = 0; i < kMaxVecPerLane; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int j = i * 32 + lane;
     if (j < nvec) {
       float4 a = v[i];
@@ -396,16 +396,23 @@ int ma3_rmsnorm_modulate(const float* x, const float* w, const float* mod, int64
               "rmsnorm_modulate: modulation offsets must be multiples of 4");
   MA3_REQUIRE(aligned16(x) && aligned16(out) && (!w || aligned16(w)) && (!mod || aligned16(mod)),
               "rmsnorm_modulate: pointers must be 16-byte aligned");
-  const unsigned grid = nblk(M, 8);
-  if (out_dtype == MA3_BF16)
-    rmsnorm_modulate_kernel<__nv_bfloat16><<<grid, 256, 0, ST(stream)>>>(x, w, mod, mod_ld, shift_off, scale_off,
-                                                                        rows_per_sample, (__nv_bfloat16*)out, M, D, eps);
-  else if (out_dtype == MA3_F16)
-    rmsnorm_modulate_kernel<__half><<<grid, 256, 0, ST(stream)>>>(x, w, mod, mod_ld, shift_off, scale_off,
-                                                                 rows_per_sample, (__half*)out, M, D, eps);
-  else
-    rmsnorm_modulate_kernel<float><<<grid, 256, 0, ST(stream)>>>(x, w, mod, mod_ld, shift_off, scale_off,
-                                                                rows_per_sample, (float*)out, M, D, eps);
+  const unsigned grid = nblk(M, 4);
+  const int nv = (D / 4 + 31) / 32;  // float4 per lane
+#define RMS_LAUNCH(TO, KV)                                                                                         \
+  rmsnorm_modulate_kernel<TO, KV><<<grid, 128, 0, ST(stream)>>>(x, w, mod, mod_ld, shift_off, scale_off,           \
+                                                                  rows_per_sample, (TO*)out, M, D, eps)
+#define RMS_DISPATCH(TO)                 \
+  do {                                   \
+    if (nv <= 6) RMS_LAUNCH(TO, 6);      \
+    else if (nv <= 9) RMS_LAUNCH(TO, 9); \
+    else if (nv <= 12) RMS_LAUNCH(TO, 12); \
+    else RMS_LAUNCH(TO, 16);             \
+  } while (0)
+  if (out_dtype == MA3_BF16) RMS_DISPATCH(__nv_bfloat16);
+  else if (out_dtype == MA3_F16) RMS_DISPATCH(__half);
+  else RMS_DISPATCH(float);
+#undef RMS_DISPATCH
+#undef RMS_LAUNCH
   MA3_LAUNCH_CHECK("rmsnorm_modulate");
   return 0;
 }

@@ -113,107 +113,30 @@ __device__ __forceinline__ void store8(void* base, int dtype, long long idx, boo
   }
 }
 
-// One thread owns accumulator row m of batch z and `w` (16 or 32) consecutive columns starting at n0.
+// Epilogue of one 32-row x w-column (w = 16 or 32) accumulator chunk owned by one warp.  tcgen05.ld delivers the chunk
+// with thread <-> row; writing global memory in that mapping costs 32 wavefronts per instruction (each lane touches a
+// different row).  The chunk is therefore transposed through a per-warp shared-memory patch (pitch 33 floats, conflict
+// free both ways) and processed row-wise: a group of lanes covers contiguous columns of one row, so loads of the
+// residual / gate / RoPE table and the stores are coalesced.
+constexpr int kStagePitch = 33;
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int m, int n0, int w, const uint32_t* r) {
-  if (m >= p.M) return;
-  if constexpr (EPI == MA3_EPI_STORE) {
-    const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
-    const long long obase = (long long)z * p.out_batch_stride + orow * p.out_ld;
-    const long long rbase = (long long)z * p.res_batch_stride + orow * p.res_ld;
-    const bool vec = p.vec_ok != 0;
-    const float brow = (p.bias && p.bias_per_row) ? p.bias[m] : 0.f;
-    for (int g = 0; g < w; g += 8) {
-      const int col = n0 + g;
-      if (col >= p.N) break;
-      const int n = min(8, p.N - col);
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g + e]) + brow;
-      if (p.bias && !p.bias_per_row) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) if (e < n) v[e] += p.bias[col + e];
-      }
-      if (p.res) {
-        float t[8];
-        load8(p.res, p.res_dtype, rbase + col, vec, n, t);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += t[e];
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
-      if (p.act == 1) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
-      } else if (p.act == 2) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.5f * v[e] * (1.f + erff(v[e] * 0.70710678118654752f));
-      } else if (p.act == 3) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = tanhf(v[e]);
-      }
-      if (p.accumulate) {
-        float t[8];
-        load8(p.out, p.out_dtype, obase + col, vec, n, t);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += t[e];
-      }
-      store8(p.out, p.out_dtype, obase + col, vec, n, v);
-    }
-  } else if constexpr (EPI == MA3_EPI_GATE_RES) {
-    float* out = reinterpret_cast<float*>(p.out);
-    const int sample = m / p.rows_per_sample;
-    const float* gate = p.gate + (long long)sample * p.gate_ld;
-    const long long obase = (long long)m * p.out_ld;
-    for (int g = 0; g < w; g += 4) {
-      const int col = n0 + g;
-      if (col >= p.N) break;  // N % 4 == 0 enforced on the host
-      float4 h = *reinterpret_cast<const float4*>(out + obase + col);
-      const float4 gt = *reinterpret_cast<const float4*>(gate + col);
-      h.x += gt.x * __uint_as_float(r[g + 0]);
-      h.y += gt.y * __uint_as_float(r[g + 1]);
-      h.z += gt.z * __uint_as_float(r[g + 2]);
-      h.w += gt.w * __uint_as_float(r[g + 3]);
-      *reinterpret_cast<float4*>(out + obase + col) = h;
-    }
-  } else if constexpr (EPI == MA3_EPI_SWIGLU) {
-    // B rows interleave w1 (even) and w3 (odd): out[m, n/2] = silu(acc[n]) * acc[n+1]
-    const long long obase = (long long)m * p.out_ld;
-    for (int g = 0; g < w; g += 16) {
-      const int col = n0 + g;
-      if (col >= p.N) break;  // N % 16 == 0 enforced on the host
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = silu_f(__uint_as_float(r[g + 2 * e])) * __uint_as_float(r[g + 2 * e + 1]);
-      store8(p.out, p.out_dtype, obase + (col >> 1), true, 8, v);
-    }
-  } else if constexpr (EPI == MA3_EPI_QKV_ROPE) {
-    const int sample = m / p.tokens, t = m - sample * p.tokens;
-    const int half_hd = p.head_dim >> 1;
-    for (int g = 0; g < w; g += 8) {
-      const int col = n0 + g;
-      if (col >= p.N) break;
-      const int sec = col / p.model_dim;
-      const int within = col - sec * p.model_dim;
-      const int which = sec + p.first_section;  // 0 q, 1 k, 2 v
-      const int head = within / p.head_dim;
-      const int d = within - head * p.head_dim;  // multiple of 8 (head_dim % 8 == 0 enforced on the host)
-      const long long sh = (long long)sample * p.heads + head;
-      if (which < 2) {
-        const float2* cs = reinterpret_cast<const float2*>(p.rope) + (long long)t * half_hd + (d >> 1);
-        const float sc = which == 0 ? p.q_scale : 1.0f;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = p.rope ? cs[e] : make_float2(1.f, 0.f);
-          const float x0 = __uint_as_float(r[g + 2 * e]), x1 = __uint_as_float(r[g + 2 * e + 1]);
-          v[2 * e] = (x0 * f.x - x1 * f.y) * sc;
-          v[2 * e + 1] = (x0 * f.y + x1 * f.x) * sc;
-        }
-        void* dst = which == 0 ? p.q_out : p.k_out;
-        store8(dst, p.op_dtype, (sh * p.tokens + t) * p.head_dim_pad + d, true, 8, v);
-      } else {
-        const long long base = (sh * p.head_dim_pad + d) * p.tokens_pad + t;
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int m0, int n0, int w, const uint32_t* r,
+                                               float* stg, int lane) {
+  if constexpr (EPI == MA3_EPI_QKV_ROPE) {
+    // V^T scatter straight from registers: lanes = consecutive tokens -> contiguous 2-byte stores per column
+    const int m = m0 + lane;
+    if (m < p.M) {
+      const int sample = m / p.tokens, t = m - sample * p.tokens;
+      for (int g = 0; g < w; g += 8) {
+        const int col = n0 + g;
+        if (col >= p.N) break;
+        const int sec = col / p.model_dim;
+        if (sec + p.first_section != 2) continue;
+        const int within = col - sec * p.model_dim;
+        const int head = within / p.head_dim;
+        const int d = within - head * p.head_dim;
+        const long long base = (((long long)sample * p.heads + head) * p.head_dim_pad + d) * p.tokens_pad + t;
         if (p.op_dtype == MA3_BF16) {
           __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(p.vt_out);
 #pragma unroll
@@ -226,6 +149,130 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int 
       }
     }
   }
+  // registers (thread = row) -> staging patch
+#pragma unroll
+  for (int e = 0; e < 32; ++e)
+    if (e < w) stg[lane * kStagePitch + e] = __uint_as_float(r[e]);
+  __syncwarp();
+
+  if constexpr (EPI == MA3_EPI_GATE_RES) {
+    // 8 lanes x float4 cover 32 columns of one row; 4 rows per pass
+    float* out = reinterpret_cast<float*>(p.out);
+    const int cg = (lane & 7) * 4;
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int rr = pass * 4 + (lane >> 3);
+      const int m = m0 + rr, col = n0 + cg;
+      if (m < p.M && cg < w && col < p.N) {  // N % 4 == 0 enforced on the host
+        const float* sp = stg + rr * kStagePitch + cg;
+        const float* gate = p.gate + (long long)(m / p.rows_per_sample) * p.gate_ld + col;
+        float* hp = out + (long long)m * p.out_ld + col;
+        float4 h = *reinterpret_cast<const float4*>(hp);
+        const float4 gt = *reinterpret_cast<const float4*>(gate);
+        h.x = fmaf(gt.x, sp[0], h.x);
+        h.y = fmaf(gt.y, sp[1], h.y);
+        h.z = fmaf(gt.z, sp[2], h.z);
+        h.w = fmaf(gt.w, sp[3], h.w);
+        *reinterpret_cast<float4*>(hp) = h;
+      }
+    }
+  } else if constexpr (EPI == MA3_EPI_SWIGLU) {
+    // B rows interleave w1 (even) and w3 (odd): out[m, n/2] = silu(acc[n]) * acc[n+1]; 2 lanes x 16 columns per row
+    const int cg = (lane & 1) * 16;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int rr = pass * 16 + (lane >> 1);
+      const int m = m0 + rr, col = n0 + cg;
+      if (m < p.M && cg < w && col < p.N) {  // N % 16 == 0 enforced on the host
+        const float* sp = stg + rr * kStagePitch + cg;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = silu_f(sp[2 * e]) * sp[2 * e + 1];
+        store8(p.out, p.out_dtype, (long long)m * p.out_ld + (col >> 1), true, 8, v);
+      }
+    }
+  } else {
+    // 4 lanes x 8 columns cover 32 columns of one row; 8 rows per pass
+    const int cg = (lane & 3) * 8;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int rr = pass * 8 + (lane >> 2);
+      const int m = m0 + rr, col = n0 + cg;
+      if (m >= p.M || cg >= w || col >= p.N) continue;
+      const float* sp = stg + rr * kStagePitch + cg;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = sp[e];
+      if constexpr (EPI == MA3_EPI_STORE) {
+        const int n = min(8, p.N - col);
+        const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
+        const long long obase = (long long)z * p.out_batch_stride + orow * p.out_ld;
+        const bool vec = p.vec_ok != 0;
+        if (p.bias) {
+          if (p.bias_per_row) {
+            const float b = p.bias[m];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += b;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (e < n) v[e] += p.bias[col + e];
+          }
+        }
+        if (p.res) {
+          float t[8];
+          load8(p.res, p.res_dtype, (long long)z * p.res_batch_stride + orow * p.res_ld + col, vec, n, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] += t[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
+        if (p.act == 1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.5f * v[e] * (1.f + erff(v[e] * 0.70710678118654752f));
+        } else if (p.act == 3) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = tanhf(v[e]);
+        }
+        if (p.accumulate) {
+          float t[8];
+          load8(p.out, p.out_dtype, obase + col, vec, n, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] += t[e];
+        }
+        store8(p.out, p.out_dtype, obase + col, vec, n, v);
+      } else {  // MA3_EPI_QKV_ROPE: q / k columns (v was scattered above)
+        const int sec = col / p.model_dim;
+        const int which = sec + p.first_section;  // 0 q, 1 k, 2 v
+        if (which == 2) continue;
+        const int within = col - sec * p.model_dim;
+        const int head = within / p.head_dim;
+        const int d = within - head * p.head_dim;  // multiple of 8 (head_dim % 8 == 0 enforced on the host)
+        const int sample = m / p.tokens, t = m - sample * p.tokens;
+        const float sc = which == 0 ? p.q_scale : 1.0f;
+        if (p.rope) {
+          const float4* cs = reinterpret_cast<const float4*>(p.rope + ((long long)t * (p.head_dim >> 1) + (d >> 1)) * 2);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float4 f = cs[e];  // (cos, sin) of two consecutive pairs
+            const float x0 = v[4 * e], x1 = v[4 * e + 1], x2 = v[4 * e + 2], x3 = v[4 * e + 3];
+            v[4 * e] = (x0 * f.x - x1 * f.y) * sc;
+            v[4 * e + 1] = (x0 * f.y + x1 * f.x) * sc;
+            v[4 * e + 2] = (x2 * f.z - x3 * f.w) * sc;
+            v[4 * e + 3] = (x2 * f.w + x3 * f.z) * sc;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= sc;
+        }
+        void* dst = which == 0 ? p.q_out : p.k_out;
+        store8(dst, p.op_dtype, (((long long)sample * p.heads + head) * p.tokens + t) * p.head_dim_pad + d, true, 8, v);
+      }
+    }
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -241,6 +288,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* staging = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);  // 4 warps x 32 x 33 floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -333,7 +381,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       const uint32_t aph = (lt >> 1) & 1;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      const int m = m_t * kBM + q * 32 + lane;
+      const int m0 = m_t * kBM + q * 32;
+      float* stg = staging + q * (32 * kStagePitch);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.tmem_stage_cols;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t r[32];
@@ -347,7 +396,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
           for (int e = 0; e < 16; ++e) r[e] = r16[e];
         }
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, z, m, n_t * p.BN + c0, w, r);
+        epilogue_chunk<EPI>(p, z, m0, n_t * p.BN + c0, w, r, stg, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -415,12 +464,13 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   }
   MA3_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm: tile_n=%d must be a multiple of 16 in [16,256]", BN);
   const size_t stage_bytes = (size_t)(kBM + BN) * BK * 2;
-  const size_t budget = 232448 - 1024 - 512;
+  const size_t kTail = 256 + 4 * 32 * kStagePitch * sizeof(float);  // barriers + epilogue staging
+  const size_t budget = 232448 - 1024 - kTail;
   int stages = (int)(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   MA3_REQUIRE(stages >= 2, "gemm: tile does not fit shared memory");
   // keep one CTA per SM (TMEM is allocated per CTA): request more than half of the SM's shared memory
-  size_t smem = 1024 + stages * stage_bytes + 512;
+  size_t smem = 1024 + stages * stage_bytes + kTail;
   if (smem < 120 * 1024) smem = 120 * 1024;
 
   kp.M = g->M; kp.N = g->N; kp.K = g->K; kp.taps = g->taps;

@@ -156,6 +156,11 @@ __host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int fmt) {
 }
 
 // ---------------------------------------------------------------- misc math
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
