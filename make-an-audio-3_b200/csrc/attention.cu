@@ -57,8 +57,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   constexpr uint32_t kTmemCols = 256;        // S: [0, BKV)  O: [BKV, BKV + HDP)
   static_assert(BKV + HDP <= 256, "TMEM budget");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B swizzle atoms) comes from the declaration; no slack is added so that two CTAs
+  // (2 x ~113 KB) fit one SM
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw;
   uint8_t* sQ = sm;
   uint8_t* sKV = sQ + kQBytes;
   uint8_t* sP = sKV + 2 * kStageBytes;
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 
 template <int HDP, int HD, int BKV>
 static int launch_attn(const AttnParams& p, int NS, cudaStream_t st) {
-  constexpr size_t smem = 1024 + 128 * HDP * 2 + 2 * (2 * BKV * HDP * 2) + 128 * BKV * 2 + 256;
+  constexpr size_t smem = 128 * HDP * 2 + 2 * (2 * BKV * HDP * 2) + 128 * BKV * 2 + 128;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<HDP, HD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

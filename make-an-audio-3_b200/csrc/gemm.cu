@@ -44,7 +44,24 @@ struct GemmKParams {
   float q_scale;
   int first_section;
   int op_dtype;
+  float inv_rows_per_sample, inv_tokens, inv_head_dim;  // exact-division helpers (see fast_div)
 };
+
+// floor(a / b) for 0 <= a < 2^22 via a float reciprocal (inv = 1/b): exact because the rounding error of
+// (a + 0.5) * inv is far below the 0.5 / b margin for the sizes used here (rows < 4M, b < 64K).
+__device__ __forceinline__ int fast_div(int a, float inv) { return __float2int_rd(((float)a + 0.5f) * inv); }
+
+// residual rows of one GATE_RES chunk, fetched ahead of the accumulator (they do not depend on the MMA)
+__device__ __forceinline__ void gate_res_prefetch(const GemmKParams& p, int m0, int n0, int w, int lane, float4 (&hv)[8]) {
+  const float* out = reinterpret_cast<const float*>(p.out);
+  const int cg = (lane & 7) * 4, col = n0 + cg;
+  const bool colok = cg < w && col < p.N;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    const int m = m0 + pass * 4 + (lane >> 3);
+    if (colok && m < p.M) hv[pass] = *reinterpret_cast<const float4*>(out + (long long)m * p.out_ld + col);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ epilogues
 __device__ __forceinline__ void load8(const void* base, int dtype, long long idx, bool vec, int n, float (&v)[8]) {
@@ -122,19 +139,19 @@ constexpr int kStagePitch = 33;
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int m0, int n0, int w, const uint32_t* r,
-                                               float* stg, int lane) {
+                                               float* stg, int lane, const float4 (&hv)[8]) {
   if constexpr (EPI == MA3_EPI_QKV_ROPE) {
     // V^T scatter straight from registers: lanes = consecutive tokens -> contiguous 2-byte stores per column
     const int m = m0 + lane;
     if (m < p.M) {
-      const int sample = m / p.tokens, t = m - sample * p.tokens;
+      const int sample = fast_div(m, p.inv_tokens), t = m - sample * p.tokens;
       for (int g = 0; g < w; g += 8) {
         const int col = n0 + g;
         if (col >= p.N) break;
-        const int sec = col / p.model_dim;
+        const int sec = (col >= p.model_dim) + (col >= 2 * p.model_dim);
         if (sec + p.first_section != 2) continue;
         const int within = col - sec * p.model_dim;
-        const int head = within / p.head_dim;
+        const int head = fast_div(within, p.inv_head_dim);
         const int d = within - head * p.head_dim;
         const long long base = (((long long)sample * p.heads + head) * p.head_dim_pad + d) * p.tokens_pad + t;
         if (p.op_dtype == MA3_BF16) {
@@ -159,21 +176,28 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int 
     // 8 lanes x float4 cover 32 columns of one row; 4 rows per pass
     float* out = reinterpret_cast<float*>(p.out);
     const int cg = (lane & 7) * 4;
+    const int col = n0 + cg;
+    const bool colok = cg < w && col < p.N;  // N % 4 == 0 enforced on the host
+    // residual rows were prefetched (hv); the gate vectors are tiny and L1/L2 resident
+    float4 gv[8];
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int m = m0 + pass * 4 + (lane >> 3);
+      if (colok && m < p.M)
+        gv[pass] = *reinterpret_cast<const float4*>(p.gate + (long long)fast_div(m, p.inv_rows_per_sample) * p.gate_ld + col);
+    }
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
       const int rr = pass * 4 + (lane >> 3);
-      const int m = m0 + rr, col = n0 + cg;
-      if (m < p.M && cg < w && col < p.N) {  // N % 4 == 0 enforced on the host
+      const int m = m0 + rr;
+      if (colok && m < p.M) {
         const float* sp = stg + rr * kStagePitch + cg;
-        const float* gate = p.gate + (long long)(m / p.rows_per_sample) * p.gate_ld + col;
-        float* hp = out + (long long)m * p.out_ld + col;
-        float4 h = *reinterpret_cast<const float4*>(hp);
-        const float4 gt = *reinterpret_cast<const float4*>(gate);
-        h.x = fmaf(gt.x, sp[0], h.x);
-        h.y = fmaf(gt.y, sp[1], h.y);
-        h.z = fmaf(gt.z, sp[2], h.z);
-        h.w = fmaf(gt.w, sp[3], h.w);
-        *reinterpret_cast<float4*>(hp) = h;
+        float4 h = hv[pass];
+        h.x = fmaf(gv[pass].x, sp[0], h.x);
+        h.y = fmaf(gv[pass].y, sp[1], h.y);
+        h.z = fmaf(gv[pass].z, sp[2], h.z);
+        h.w = fmaf(gv[pass].w, sp[3], h.w);
+        *reinterpret_cast<float4*>(out + (long long)m * p.out_ld + col) = h;
       }
     }
   } else if constexpr (EPI == MA3_EPI_SWIGLU) {
@@ -194,6 +218,58 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int 
   } else {
     // 4 lanes x 8 columns cover 32 columns of one row; 8 rows per pass
     const int cg = (lane & 3) * 8;
+    [[maybe_unused]] float rv[4][8];
+    [[maybe_unused]] float ov[4][8];
+    [[maybe_unused]] float bcol[8];
+    [[maybe_unused]] float brow[4];
+    [[maybe_unused]] float4 rope_cs[4][2];
+    if constexpr (EPI == MA3_EPI_QKV_ROPE) {
+      // RoPE table entries of all 4 passes before any store (the table is L2-resident; serialising the round
+      // trips behind possibly-aliasing stores made this epilogue the bottleneck)
+      if (p.rope) {
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+          const int m = m0 + pass * 8 + (lane >> 2), col = n0 + cg;
+          if (m >= p.M || cg >= w || col >= p.N) continue;
+          const int sec = (col >= p.model_dim) + (col >= 2 * p.model_dim);
+          if (sec + p.first_section == 2) continue;
+          const int within = col - sec * p.model_dim;
+          const int d = within - fast_div(within, p.inv_head_dim) * p.head_dim;
+          const int t = m - fast_div(m, p.inv_tokens) * p.tokens;
+          const float4* cs = reinterpret_cast<const float4*>(p.rope + ((long long)t * (p.head_dim >> 1) + (d >> 1)) * 2);
+          rope_cs[pass][0] = cs[0];
+          rope_cs[pass][1] = cs[1];
+        }
+      }
+    }
+    if constexpr (EPI == MA3_EPI_STORE) {
+      if (p.bias) {
+        if (p.bias_per_row) {
+#pragma unroll
+          for (int pass = 0; pass < 4; ++pass) {
+            const int m = m0 + pass * 8 + (lane >> 2);
+            brow[pass] = m < p.M ? p.bias[m] : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) bcol[e] = (cg < w && n0 + cg + e < p.N) ? p.bias[n0 + cg + e] : 0.f;
+        }
+      }
+      // residual / accumulate operands of all 4 passes are fetched before any store (independent L2 round trips)
+      if (p.res || p.accumulate) {
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+          const int m = m0 + pass * 8 + (lane >> 2), col = n0 + cg;
+          if (m >= p.M || cg >= w || col >= p.N) continue;
+          const int n = min(8, p.N - col);
+          const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
+          if (p.res)
+            load8(p.res, p.res_dtype, (long long)z * p.res_batch_stride + orow * p.res_ld + col, p.vec_ok != 0, n, rv[pass]);
+          if (p.accumulate)
+            load8(p.out, p.out_dtype, (long long)z * p.out_batch_stride + orow * p.out_ld + col, p.vec_ok != 0, n, ov[pass]);
+        }
+      }
+    }
 #pragma unroll
     for (int pass = 0; pass < 4; ++pass) {
       const int rr = pass * 8 + (lane >> 2);
@@ -210,19 +286,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int 
         const bool vec = p.vec_ok != 0;
         if (p.bias) {
           if (p.bias_per_row) {
-            const float b = p.bias[m];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += b;
+            for (int e = 0; e < 8; ++e) v[e] += brow[pass];
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) if (e < n) v[e] += p.bias[col + e];
+            for (int e = 0; e < 8; ++e) v[e] += bcol[e];
           }
         }
         if (p.res) {
-          float t[8];
-          load8(p.res, p.res_dtype, (long long)z * p.res_batch_stride + orow * p.res_ld + col, vec, n, t);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] += t[e];
+          for (int e = 0; e < 8; ++e) v[e] += rv[pass][e];
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
@@ -237,26 +310,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int 
           for (int e = 0; e < 8; ++e) v[e] = tanhf(v[e]);
         }
         if (p.accumulate) {
-          float t[8];
-          load8(p.out, p.out_dtype, obase + col, vec, n, t);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] += t[e];
+          for (int e = 0; e < 8; ++e) v[e] += ov[pass][e];
         }
         store8(p.out, p.out_dtype, obase + col, vec, n, v);
       } else {  // MA3_EPI_QKV_ROPE: q / k columns (v was scattered above)
-        const int sec = col / p.model_dim;
+        const int sec = (col >= p.model_dim) + (col >= 2 * p.model_dim);
         const int which = sec + p.first_section;  // 0 q, 1 k, 2 v
         if (which == 2) continue;
         const int within = col - sec * p.model_dim;
-        const int head = within / p.head_dim;
+        const int head = fast_div(within, p.inv_head_dim);
         const int d = within - head * p.head_dim;  // multiple of 8 (head_dim % 8 == 0 enforced on the host)
-        const int sample = m / p.tokens, t = m - sample * p.tokens;
+        const int sample = fast_div(m, p.inv_tokens), t = m - sample * p.tokens;
         const float sc = which == 0 ? p.q_scale : 1.0f;
         if (p.rope) {
-          const float4* cs = reinterpret_cast<const float4*>(p.rope + ((long long)t * (p.head_dim >> 1) + (d >> 1)) * 2);
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const float4 f = cs[e];  // (cos, sin) of two consecutive pairs
+            const float4 f = rope_cs[pass][e];  // (cos, sin) of two consecutive pairs
             const float x0 = v[4 * e], x1 = v[4 * e + 1], x2 = v[4 * e + 2], x3 = v[4 * e + 3];
             v[4 * e] = (x0 * f.x - x1 * f.y) * sc;
             v[4 * e + 1] = (x0 * f.y + x1 * f.x) * sc;
@@ -379,10 +449,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       const int z = rest / p.tiles_m;
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
-      mbar_wait(&tfull[as], aph);
-      tc_fence_after();
       const int m0 = m_t * kBM + q * 32;
       float* stg = staging + q * (32 * kStagePitch);
+      float4 hv[8], hv_next[8];
+      if constexpr (EPI == MA3_EPI_GATE_RES) gate_res_prefetch(p, m0, n_t * p.BN, min(32, p.BN), lane, hv);
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.tmem_stage_cols;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t r[32];
@@ -395,8 +467,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
 #pragma unroll
           for (int e = 0; e < 16; ++e) r[e] = r16[e];
         }
+        if constexpr (EPI == MA3_EPI_GATE_RES) {
+          if (c0 + 32 < p.BN) gate_res_prefetch(p, m0, n_t * p.BN + c0 + 32, min(32, p.BN - c0 - 32), lane, hv_next);
+        }
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, z, m0, n_t * p.BN + c0, w, r, stg, lane);
+        epilogue_chunk<EPI>(p, z, m0, n_t * p.BN + c0, w, r, stg, lane, hv);
+        if constexpr (EPI == MA3_EPI_GATE_RES) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) hv[i] = hv_next[i];
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -508,6 +587,9 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   kp.model_dim = g->model_dim; kp.head_dim = g->head_dim; kp.head_dim_pad = g->head_dim_pad;
   kp.heads = g->head_dim > 0 ? g->model_dim / g->head_dim : 0;
   kp.tokens = g->tokens; kp.tokens_pad = g->tokens_pad; kp.q_scale = g->q_scale;
+  kp.inv_rows_per_sample = g->rows_per_sample > 0 ? 1.0f / (float)g->rows_per_sample : 0.f;
+  kp.inv_tokens = g->tokens > 0 ? 1.0f / (float)g->tokens : 0.f;
+  kp.inv_head_dim = g->head_dim > 0 ? 1.0f / (float)g->head_dim : 0.f;
 
   const int total_tiles = kp.tiles_m * kp.tiles_n * kp.batch;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
