@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   constexpr uint32_t kKBytes = BKV * HDP * 2;
   constexpr uint32_t kStageBytes = 2 * kKBytes;  // K tile + V^T tile
   constexpr uint32_t kPBytes = 128 * BKV * 2;
-  constexpr uint32_t kTmemCols = 256;        // S: [0, BKV)  O: [BKV, BKV + HDP)
-  static_assert(BKV + HDP <= 256, "TMEM budget");
+  constexpr uint32_t kTmemCols = 256;        // S0: [0, BKV)  S1: [BKV, 2 BKV)  O: [2 BKV, 2 BKV + HDP)
+  static_assert(2 * BKV + HDP <= 256, "TMEM budget");
 
   // 1024-byte alignment (128B swizzle atoms) comes from the declaration; no slack is added so that two CTAs
   // (2 x ~113 KB) fit one SM
@@ -66,12 +66,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   uint8_t* sP = sKV + 2 * kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
   uint64_t* q_full = bars;          // 1
-  uint64_t* kv_full = bars + 1;     // 2
-  uint64_t* kv_empty = bars + 3;    // 2
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;      // 2   K tile landed
+  uint64_t* k_empty = bars + 3;     // 2   S MMA that read it has completed
+  uint64_t* v_full = bars + 5;      // 2
+  uint64_t* v_empty = bars + 7;     // 2   PV MMA that read it has completed
+  uint64_t* s_full = bars + 9;      // 2   S tile (double-buffered in TMEM) ready
+  uint64_t* p_full = bars + 11;
+  uint64_t* o_full = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, ns = blockIdx.z;
@@ -84,8 +86,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
       prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmVt);
       prefetch_tmap(&p.tmKy); prefetch_tmap(&p.tmVyt);
       mbar_init(q_full, 1);
-      for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-      mbar_init(s_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+        mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+        mbar_init(&s_full[i], 1);
+      }
       mbar_init(p_full, 128);
       mbar_init(o_full, 1);
       fence_barrier_init();
@@ -97,50 +102,65 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + BKV;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * BKV;
 
   if (warp == 4) {
     if (elect_one()) {
-      auto load_kv = [&](int i) {
+      auto load_k = [&](int i) {
         const int st = i & 1;
         const bool cross = i >= n_self;
         const int kv0 = (cross ? i - n_self : i) * BKV;
         uint8_t* dK = sKV + st * kStageBytes;
-        uint8_t* dV = dK + kKBytes;
-        mbar_arrive_expect_tx(&kv_full[st], kStageBytes);
+        mbar_arrive_expect_tx(&k_full[st], kKBytes);
 #pragma unroll
         for (int c = 0; c < HDC; ++c)
-          tma_load_3d(dK + c * (BKV * 128), cross ? &p.tmKy : &p.tmK, &kv_full[st], c * 64, kv0, bh);
+          tma_load_3d(dK + c * (BKV * 128), cross ? &p.tmKy : &p.tmK, &k_full[st], c * 64, kv0, bh);
+      };
+      auto load_v = [&](int i) {
+        const int st = i & 1;
+        const bool cross = i >= n_self;
+        const int kv0 = (cross ? i - n_self : i) * BKV;
+        uint8_t* dV = sKV + st * kStageBytes + kKBytes;
+        mbar_arrive_expect_tx(&v_full[st], kKBytes);
 #pragma unroll
         for (int c = 0; c < KVC; ++c)
-          tma_load_3d(dV + c * (HDP * 128), cross ? &p.tmVyt : &p.tmVt, &kv_full[st], kv0 + c * 64, 0, bh);
+          tma_load_3d(dV + c * (HDP * 128), cross ? &p.tmVyt : &p.tmVt, &v_full[st], kv0 + c * 64, 0, bh);
       };
       const uint32_t idesc_s = umma_idesc(128, BKV, p.dtype == MA3_BF16 ? 1 : 0);
       const uint32_t idesc_o = umma_idesc(128, HDP, p.dtype == MA3_BF16 ? 1 : 0);
+      // S(i) = Q K_i^T into TMEM buffer i & 1; frees the K stage when done
       auto issue_s = [&](int i) {
         const int st = i & 1;
-        mbar_wait(&kv_full[st], (i >> 1) & 1);
+        mbar_wait(&k_full[st], (i >> 1) & 1);
         tc_fence_after();
         const uint32_t qa = smem_u32(sQ), ka = smem_u32(sKV + st * kStageBytes);
 #pragma unroll
         for (int k = 0; k < HDP / 16; ++k) {
           const uint64_t da = umma_desc_kmajor(qa + (k / 4) * (128 * 128) + (k % 4) * 32, 128);
           const uint64_t db = umma_desc_kmajor(ka + (k / 4) * (BKV * 128) + (k % 4) * 32, 128);
-          umma_f16(tmem_S, da, db, idesc_s, k != 0 ? 1u : 0u);
+          umma_f16(tmem_S + st * BKV, da, db, idesc_s, k != 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
+        umma_commit(&s_full[st]);
+        umma_commit(&k_empty[st]);
       };
 
       mbar_arrive_expect_tx(q_full, kQBytes);
 #pragma unroll
       for (int c = 0; c < HDC; ++c) tma_load_3d(sQ + c * (128 * 128), &p.tmQ, q_full, c * 64, q0, bh);
-      load_kv(0);
-      if (n_tiles > 1) load_kv(1);
+      load_k(0);
+      load_v(0);
+      if (n_tiles > 1) { load_k(1); load_v(1); }
       mbar_wait(q_full, 0);
       issue_s(0);
+      if (n_tiles > 1) issue_s(1);   // the softmax of tile i overlaps the tensor core computing S(i+1)
       for (int i = 0; i < n_tiles; ++i) {
         const int st = i & 1;
-        mbar_wait(p_full, i & 1);
+        if (i + 2 < n_tiles) {        // K stage st was released by S(i): refill it for tile i+2
+          mbar_wait(&k_empty[st], (i >> 1) & 1);
+          load_k(i + 2);
+        }
+        mbar_wait(p_full, i & 1);     // P(i) in smem, S buffer st drained, O tile of PV(i-1) consumed
+        mbar_wait(&v_full[st], (i >> 1) & 1);
         tc_fence_after();
         const uint32_t pa = smem_u32(sP), va = smem_u32(sKV + st * kStageBytes + kKBytes);
 #pragma unroll
@@ -150,11 +170,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
           umma_f16(tmem_O, da, db, idesc_o, k != 0 ? 1u : 0u);
         }
         umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
-        if (i + 1 < n_tiles) issue_s(i + 1);
+        umma_commit(&v_empty[st]);
         if (i + 2 < n_tiles) {
-          mbar_wait(&kv_empty[st], (i >> 1) & 1);
-          load_kv(i + 2);
+          issue_s(i + 2);
+          mbar_wait(&v_empty[st], (i >> 1) & 1);
+          load_v(i + 2);
         }
       }
     }
@@ -176,14 +196,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
       for (int e = 0; e < HD; ++e) acc[e] = 0.f;
       float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
       for (int j = 0; j < ntl; ++j, ++it) {
-        mbar_wait(s_full, it & 1);
+        mbar_wait(&s_full[it & 1], (it >> 1) & 1);
         tc_fence_after();
+        const uint32_t tS = tmem_S + (it & 1) * BKV + lane_base;
         const int kv0 = j * BKV;
         float mx = m;
 #pragma unroll 1
         for (int c0 = 0; c0 < BKV; c0 += 16) {
           uint32_t r[16];
-          tmem_ld16(tmem_S + lane_base + c0, r);
+          tmem_ld16(tS + c0, r);
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
@@ -201,7 +222,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 #pragma unroll 1
         for (int c0 = 0; c0 < BKV; c0 += 16) {
           uint32_t r[16];
-          tmem_ld16(tmem_S + lane_base + c0, r);
+          tmem_ld16(tS + c0, r);
           tmem_ld_wait();
           uint32_t pk[8];
 #pragma unroll
@@ -269,7 +290,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 
 template <int HDP, int HD, int BKV>
 static int launch_attn(const AttnParams& p, int NS, cudaStream_t st) {
-  constexpr size_t smem = 128 * HDP * 2 + 2 * (2 * BKV * HDP * 2) + 128 * BKV * 2 + 128;
+  constexpr size_t smem = 128 * HDP * 2 + 2 * (2 * BKV * HDP * 2) + 128 * BKV * 2 + 256;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<HDP, HD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -300,7 +321,7 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.T = T; p.L = L; p.H = H; p.D = H * hd; p.out = out; p.gate = gate; p.dtype = dtype;
-  const int BKV = hdp == 64 ? 128 : 64;
+  const int BKV = 64;
   const uint64_t nbh = (uint64_t)NS * H;
   int rc;
   {
@@ -330,11 +351,11 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
     p.tmVyt = p.tmVt;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (hdp == 64 && hd == 24) return launch_attn<64, 24, 128>(p, NS, st);
-  if (hdp == 64 && hd == 16) return launch_attn<64, 16, 128>(p, NS, st);
-  if (hdp == 64 && hd == 32) return launch_attn<64, 32, 128>(p, NS, st);
-  if (hdp == 64 && hd == 48) return launch_attn<64, 48, 128>(p, NS, st);
-  if (hdp == 64 && hd == 64) return launch_attn<64, 64, 128>(p, NS, st);
+  if (hdp == 64 && hd == 24) return launch_attn<64, 24, 64>(p, NS, st);
+  if (hdp == 64 && hd == 16) return launch_attn<64, 16, 64>(p, NS, st);
+  if (hdp == 64 && hd == 32) return launch_attn<64, 32, 64>(p, NS, st);
+  if (hdp == 64 && hd == 48) return launch_attn<64, 48, 64>(p, NS, st);
+  if (hdp == 64 && hd == 64) return launch_attn<64, 64, 64>(p, NS, st);
   if (hdp == 128 && hd == 72) return launch_attn<128, 72, 64>(p, NS, st);
   if (hdp == 128 && hd == 96) return launch_attn<128, 96, 64>(p, NS, st);
   if (hdp == 128 && hd == 128) return launch_attn<128, 128, 64>(p, NS, st);

@@ -42,62 +42,85 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // out[m, :] = rms(x[m, :]) * w * (1 + scale[sample]) + shift[sample]     (one warp per row, row cached in registers)
 constexpr int kMaxVecPerLane = 16;  // D <= 2048
 
+// grid = (row chunks of kRmsRows within a sample, samples).  The block first combines the per-sample modulation with
+// the norm weight into shared memory (a = w (1 + scale), b = shift), so the row loop touches global memory only for x
+// and the output; each warp owns two rows and issues both rows' loads before reducing (memory-level parallelism).
+constexpr int kRmsRows = 16;
+
 template <typename TOut, int kVec>
-__global__ void __launch_bounds__(128) rmsnorm_modulate_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                const float* __restrict__ mod, long long mod_ld,
                                                                int shift_off, int scale_off, int rows_per_sample,
                                                                TOut* __restrict__ out, int M, int D, float eps) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+  extern __shared__ __align__(16) float ab[];  // a[D] | b[D]
+  float* sa = ab;
+  float* sb = ab + D;
+  const int sample = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = D >> 2;
-  float4 v[kVec];
-  float ss = 0.f;
+  const int row_in_sample = blockIdx.x * kRmsRows + warp * 2;
+  const long long row0 = (long long)sample * rows_per_sample + row_in_sample;
+  const bool ok0 = row_in_sample < rows_per_sample && row0 < M;
+  const bool ok1 = row_in_sample + 1 < rows_per_sample && row0 + 1 < M;
+  // issue this warp's row loads first: they are the long-latency (HBM) part
+  float4 v0[kVec], v1[kVec];
+  const float4* x0 = reinterpret_cast<const float4*>(x + row0 * D);
+  const float4* x1 = reinterpret_cast<const float4*>(x + (row0 + 1) * D);
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
     const int j = i * 32 + lane;
-    if (j < nvec) {
-      v[i] = xr[j];
-      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    v0[i] = (ok0 && j < nvec) ? x0[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    v1[i] = (ok1 && j < nvec) ? x1[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float* sc = mod ? mod + (long long)sample * mod_ld + scale_off : nullptr;
+  const float* sh = mod ? mod + (long long)sample * mod_ld + shift_off : nullptr;
+  for (int j = threadIdx.x; j < nvec; j += blockDim.x) {
+    float4 a = w ? reinterpret_cast<const float4*>(w)[j] : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mod) {
+      const float4 s1 = reinterpret_cast<const float4*>(sc)[j];
+      b = reinterpret_cast<const float4*>(sh)[j];
+      a.x *= 1.f + s1.x; a.y *= 1.f + s1.y; a.z *= 1.f + s1.z; a.w *= 1.f + s1.w;
     }
+    reinterpret_cast<float4*>(sa)[j] = a;
+    reinterpret_cast<float4*>(sb)[j] = b;
   }
-  ss = warp_sum(ss);
-  const float r = rsqrtf(ss / (float)D + eps);
-  const float* sc = nullptr;
-  const float* sh = nullptr;
-  if (mod) {
-    const long long base = (long long)(row / rows_per_sample) * mod_ld;
-    sc = mod + base + scale_off;
-    sh = mod + base + shift_off;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    s0 += v0[i].x * v0[i].x + v0[i].y * v0[i].y + v0[i].z * v0[i].z + v0[i].w * v0[i].w;
+    s1 += v1[i].x * v1[i].x + v1[i].y * v1[i].y + v1[i].z * v1[i].z + v1[i].w * v1[i].w;
   }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  const float r0 = rsqrtf(s0 / (float)D + eps), r1 = rsqrtf(s1 / (float)D + eps);
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
     const int j = i * 32 + lane;
     if (j < nvec) {
-      float4 a = v[i];
-      a.x *= r; a.y *= r; a.z *= r; a.w *= r;
-      if (w) {
-        const float4 ww = reinterpret_cast<const float4*>(w)[j];
-        a.x *= ww.x; a.y *= ww.y; a.z *= ww.z; a.w *= ww.w;
-      }
-      if (mod) {
-        const float4 s1 = reinterpret_cast<const float4*>(sc)[j];
-        const float4 s0 = reinterpret_cast<const float4*>(sh)[j];
-        a.x = a.x * (1.f + s1.x) + s0.x; a.y = a.y * (1.f + s1.y) + s0.y;
-        a.z = a.z * (1.f + s1.z) + s0.z; a.w = a.w * (1.f + s1.w) + s0.w;
-      }
-      TOut* o = out + (long long)row * D + j * 4;
-      if constexpr (sizeof(TOut) == 2) {
-        uint2 u;
-        if constexpr (std::is_same<TOut, __nv_bfloat16>::value) {
-          u.x = pack_bf16(a.x, a.y); u.y = pack_bf16(a.z, a.w);
+      const float4 a = reinterpret_cast<const float4*>(sa)[j];
+      const float4 b = reinterpret_cast<const float4*>(sb)[j];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        if (!(rr ? ok1 : ok0)) continue;
+        const float4 xv = rr ? v1[i] : v0[i];
+        const float r = rr ? r1 : r0;
+        float4 o;
+        o.x = fmaf(xv.x * r, a.x, b.x); o.y = fmaf(xv.y * r, a.y, b.y);
+        o.z = fmaf(xv.z * r, a.z, b.z); o.w = fmaf(xv.w * r, a.w, b.w);
+        TOut* op = out + (row0 + rr) * D + j * 4;
+        if constexpr (sizeof(TOut) == 2) {
+          uint2 u;
+          if constexpr (std::is_same<TOut, __nv_bfloat16>::value) {
+            u.x = pack_bf16(o.x, o.y); u.y = pack_bf16(o.z, o.w);
+          } else {
+            u.x = pack_f16(o.x, o.y); u.y = pack_f16(o.z, o.w);
+          }
+          *reinterpret_cast<uint2*>(op) = u;
         } else {
-          u.x = pack_f16(a.x, a.y); u.y = pack_f16(a.z, a.w);
+          *reinterpret_cast<float4*>(op) = o;
         }
-        *reinterpret_cast<uint2*>(o) = u;
-      } else {
-        *reinterpret_cast<float4*>(o) = a;
       }
     }
   }
@@ -396,11 +419,14 @@ int ma3_rmsnorm_modulate(const float* x, const float* w, const float* mod, int64
               "rmsnorm_modulate: modulation offsets must be multiples of 4");
   MA3_REQUIRE(aligned16(x) && aligned16(out) && (!w || aligned16(w)) && (!mod || aligned16(mod)),
               "rmsnorm_modulate: pointers must be 16-byte aligned");
-  const unsigned grid = nblk(M, 4);
+  const int rps = mod ? rows_per_sample : M;   // without modulation all rows form one "sample"
+  MA3_REQUIRE(!mod || M % rows_per_sample == 0, "rmsnorm_modulate: M must be samples * rows_per_sample");
+  const dim3 grid((unsigned)((rps + kRmsRows - 1) / kRmsRows), (unsigned)(M / rps));
+  const size_t smem = 2 * (size_t)D * sizeof(float);
   const int nv = (D / 4 + 31) / 32;  // float4 per lane
 #define RMS_LAUNCH(TO, KV)                                                                                         \
-  rmsnorm_modulate_kernel<TO, KV><<<grid, 128, 0, ST(stream)>>>(x, w, mod, mod_ld, shift_off, scale_off,           \
-                                                                  rows_per_sample, (TO*)out, M, D, eps)
+  rmsnorm_modulate_kernel<TO, KV><<<grid, 256, smem, ST(stream)>>>(x, w, mod, mod_ld, shift_off, scale_off, rps,   \
+                                                                   (TO*)out, M, D, eps)
 #define RMS_DISPATCH(TO)                 \
   do {                                   \
     if (nv <= 6) RMS_LAUNCH(TO, 6);      \

@@ -2,15 +2,16 @@
 // accumulator) -> fused epilogue.  One kernel serves nn.Linear, Conv1d (any k / dilation, channels-last) and the
 // phases of ConvTranspose1d; see include/ma3_b200.h for the contract and the reference code it replaces.
 //
-// Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one elected
-// lane), warps 2..5 = epilogue (TMEM lane quarter = warp % 4; thread <-> accumulator row).
+// Roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one elected
+// lane), warps 2..9 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter on alternating 32-column chunks).
 #include "host_common.h"
 #include "ptx.cuh"
 
 namespace ma3 {
 
 constexpr int kBM = 128;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quarter, alternating column chunks
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 
 struct GemmKParams {
@@ -51,16 +52,8 @@ struct GemmKParams {
 // (a + 0.5) * inv is far below the 0.5 / b margin for the sizes used here (rows < 4M, b < 64K).
 __device__ __forceinline__ int fast_div(int a, float inv) { return __float2int_rd(((float)a + 0.5f) * inv); }
 
-// residual rows of one GATE_RES chunk, fetched ahead of the accumulator (they do not depend on the MMA)
-__device__ __forceinline__ void gate_res_prefetch(const GemmKParams& p, int m0, int n0, int w, int lane, float4 (&hv)[8]) {
-  const float* out = reinterpret_cast<const float*>(p.out);
-  const int cg = (lane & 7) * 4, col = n0 + cg;
-  const bool colok = cg < w && col < p.N;
-#pragma unroll
-  for (int pass = 0; pass < 8; ++pass) {
-    const int m = m0 + pass * 4 + (lane >> 3);
-    if (colok && m < p.M) hv[pass] = *reinterpret_cast<const float4*>(out + (long long)m * p.out_ld + col);
-  }
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
@@ -137,13 +130,68 @@ __device__ __forceinline__ void store8(void* base, int dtype, long long idx, boo
 // residual / gate / RoPE table and the stores are coalesced.
 constexpr int kStagePitch = 33;
 
+// Per-tile, per-lane row bookkeeping hoisted out of the chunk loop (the epilogue warps are instruction-latency bound:
+// one warp per scheduler, dependent chains).  Meaning per epilogue:
+//   STORE    : 4 rows (m0 + pass*8 + lane/4): off = out offset of the row start, aux = res offset, brow = row bias
+//   GATE_RES : 8 rows (m0 + pass*4 + lane/8): off = out offset of the row start, aux = gate row offset
+//   SWIGLU   : 2 rows (m0 + pass*16 + lane/2): off = out offset of the row start
+//   QKV_ROPE : 4 rows as STORE: off = sample*H*tokens*hdp + t*hdp (q/k row part), aux = t*head_dim (RoPE row offset)
+// off < 0 marks a row outside [0, M).
+struct RowCtx {
+  long long off[8];
+  long long aux[8];
+  float brow[4];
+};
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int m0, int n0, int w, const uint32_t* r,
-                                               float* stg, int lane, const float4 (&hv)[8]) {
+__device__ __forceinline__ void make_row_ctx(const GemmKParams& p, int z, int m0, int lane, RowCtx& rc) {
+  if constexpr (EPI == MA3_EPI_GATE_RES) {
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int m = m0 + pass * 4 + (lane >> 3);
+      rc.off[pass] = m < p.M ? (long long)m * p.out_ld : -1;
+      rc.aux[pass] = m < p.M ? (long long)fast_div(m, p.inv_rows_per_sample) * p.gate_ld : 0;
+    }
+  } else if constexpr (EPI == MA3_EPI_SWIGLU) {
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int m = m0 + pass * 16 + (lane >> 1);
+      rc.off[pass] = m < p.M ? (long long)m * p.out_ld : -1;
+    }
+  } else if constexpr (EPI == MA3_EPI_STORE) {
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int m = m0 + pass * 8 + (lane >> 2);
+      const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
+      rc.off[pass] = m < p.M ? (long long)z * p.out_batch_stride + orow * p.out_ld : -1;
+      rc.aux[pass] = (long long)z * p.res_batch_stride + orow * p.res_ld;
+      rc.brow[pass] = (p.bias && p.bias_per_row && m < p.M) ? p.bias[m] : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int m = m0 + pass * 8 + (lane >> 2);
+      const int sample = fast_div(m, p.inv_tokens), t = m - sample * p.tokens;
+      rc.off[pass] = m < p.M ? ((long long)sample * p.heads * p.tokens + t) * p.head_dim_pad : -1;
+      rc.aux[pass] = (long long)t * p.head_dim;
+    }
+  }
+}
+
+// Epilogue of one 32-row x w-column (w = 16 or 32) accumulator chunk owned by one warp.  tcgen05.ld delivers the chunk
+// with thread <-> row; writing global memory in that mapping costs 32 wavefronts per instruction (each lane touches a
+// different row).  The chunk is therefore transposed through a per-warp shared-memory patch (pitch 33 floats, conflict
+// free both ways) and processed row-wise: a group of lanes covers contiguous columns of one row, so loads of the
+// residual / RoPE table and the stores are coalesced.  All global loads of a chunk are issued before its first store.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int n0, int w, const uint32_t* r,
+                                               float* stg, int lane, const RowCtx& rc) {
   if constexpr (EPI == MA3_EPI_QKV_ROPE) {
     // V^T scatter straight from registers: lanes = consecutive tokens -> contiguous 2-byte stores per column
     const int m = m0 + lane;
-    if (m < p.M) {
+    const int sec0 = (n0 >= p.model_dim) + (n0 >= 2 * p.model_dim);
+    const int sec1 = (n0 + w - 1 >= p.model_dim) + (n0 + w - 1 >= 2 * p.model_dim);
+    if (m < p.M && (sec0 + p.first_section == 2 || sec1 + p.first_section == 2)) {
       const int sample = fast_div(m, p.inv_tokens), t = m - sample * p.tokens;
       for (int g = 0; g < w; g += 8) {
         const int col = n0 + g;
@@ -173,172 +221,152 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int z, int 
   __syncwarp();
 
   if constexpr (EPI == MA3_EPI_GATE_RES) {
-    // 8 lanes x float4 cover 32 columns of one row; 4 rows per pass
+    // 8 lanes x float4 cover 32 columns of one row; 4 rows per pass.
+    // h += gate * acc as vectorised fire-and-forget reductions (REDG.ADD.F32x4): the fp32 residual stream is never
+    // loaded by the epilogue, so no HBM round trip sits on its critical path.  One reduction per element per GEMM
+    // (no split-K) keeps the result deterministic.
     float* out = reinterpret_cast<float*>(p.out);
     const int cg = (lane & 7) * 4;
     const int col = n0 + cg;
-    const bool colok = cg < w && col < p.N;  // N % 4 == 0 enforced on the host
-    // residual rows were prefetched (hv); the gate vectors are tiny and L1/L2 resident
-    float4 gv[8];
+    if (cg < w && col < p.N) {  // N % 4 == 0 enforced on the host
+      float4 gv[8];
 #pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-      const int m = m0 + pass * 4 + (lane >> 3);
-      if (colok && m < p.M)
-        gv[pass] = *reinterpret_cast<const float4*>(p.gate + (long long)fast_div(m, p.inv_rows_per_sample) * p.gate_ld + col);
-    }
+      for (int pass = 0; pass < 8; ++pass)
+        if (rc.off[pass] >= 0) gv[pass] = *reinterpret_cast<const float4*>(p.gate + rc.aux[pass] + col);
+      const float* sp = stg + (lane >> 3) * kStagePitch + cg;
 #pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-      const int rr = pass * 4 + (lane >> 3);
-      const int m = m0 + rr;
-      if (colok && m < p.M) {
-        const float* sp = stg + rr * kStagePitch + cg;
-        float4 h = hv[pass];
-        h.x = fmaf(gv[pass].x, sp[0], h.x);
-        h.y = fmaf(gv[pass].y, sp[1], h.y);
-        h.z = fmaf(gv[pass].z, sp[2], h.z);
-        h.w = fmaf(gv[pass].w, sp[3], h.w);
-        *reinterpret_cast<float4*>(out + (long long)m * p.out_ld + col) = h;
+      for (int pass = 0; pass < 8; ++pass) {
+        if (rc.off[pass] >= 0)
+          red_add_f32x4(out + rc.off[pass] + col, gv[pass].x * sp[0], gv[pass].y * sp[1], gv[pass].z * sp[2],
+                        gv[pass].w * sp[3]);
+        sp += 4 * kStagePitch;
       }
     }
   } else if constexpr (EPI == MA3_EPI_SWIGLU) {
     // B rows interleave w1 (even) and w3 (odd): out[m, n/2] = silu(acc[n]) * acc[n+1]; 2 lanes x 16 columns per row
     const int cg = (lane & 1) * 16;
+    const int col = n0 + cg;
+    if (cg < w && col < p.N) {  // N % 16 == 0 enforced on the host
+      const float* sp = stg + (lane >> 1) * kStagePitch + cg;
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const int rr = pass * 16 + (lane >> 1);
-      const int m = m0 + rr, col = n0 + cg;
-      if (m < p.M && cg < w && col < p.N) {  // N % 16 == 0 enforced on the host
-        const float* sp = stg + rr * kStagePitch + cg;
-        float v[8];
+      for (int pass = 0; pass < 2; ++pass) {
+        if (rc.off[pass] >= 0) {
+          float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = silu_f(sp[2 * e]) * sp[2 * e + 1];
-        store8(p.out, p.out_dtype, (long long)m * p.out_ld + (col >> 1), true, 8, v);
+          for (int e = 0; e < 8; ++e) v[e] = silu_f(sp[2 * e]) * sp[2 * e + 1];
+          store8(p.out, p.out_dtype, rc.off[pass] + (col >> 1), true, 8, v);
+        }
+        sp += 16 * kStagePitch;
       }
     }
-  } else {
+  } else if constexpr (EPI == MA3_EPI_STORE) {
     // 4 lanes x 8 columns cover 32 columns of one row; 8 rows per pass
     const int cg = (lane & 3) * 8;
-    [[maybe_unused]] float rv[4][8];
-    [[maybe_unused]] float ov[4][8];
-    [[maybe_unused]] float bcol[8];
-    [[maybe_unused]] float brow[4];
-    [[maybe_unused]] float4 rope_cs[4][2];
-    if constexpr (EPI == MA3_EPI_QKV_ROPE) {
-      // RoPE table entries of all 4 passes before any store (the table is L2-resident; serialising the round
-      // trips behind possibly-aliasing stores made this epilogue the bottleneck)
+    const int col = n0 + cg;
+    if (cg < w && col < p.N) {
+      const int n = min(8, p.N - col);
+      const bool vec = p.vec_ok != 0;
+      float rv[4][8], ov[4][8], bcol[8];
+      if (p.bias && !p.bias_per_row) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bcol[e] = e < n ? p.bias[col + e] : 0.f;
+      }
+      if (p.res) {
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass)
+          if (rc.off[pass] >= 0) load8(p.res, p.res_dtype, rc.aux[pass] + col, vec, n, rv[pass]);
+      }
+      if (p.accumulate) {
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass)
+          if (rc.off[pass] >= 0) load8(p.out, p.out_dtype, rc.off[pass] + col, vec, n, ov[pass]);
+      }
+      const float* sp = stg + (lane >> 2) * kStagePitch + cg;
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        if (rc.off[pass] >= 0) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = sp[e];
+          if (p.bias) {
+            if (p.bias_per_row) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += rc.brow[pass];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += bcol[e];
+            }
+          }
+          if (p.res) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += rv[pass][e];
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
+          if (p.act == 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.5f * v[e] * (1.f + erff(v[e] * 0.70710678118654752f));
+          } else if (p.act == 3) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = tanhf(v[e]);
+          }
+          if (p.accumulate) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += ov[pass][e];
+          }
+          store8(p.out, p.out_dtype, rc.off[pass] + col, vec, n, v);
+        }
+        sp += 8 * kStagePitch;
+      }
+    }
+  } else {  // MA3_EPI_QKV_ROPE: q / k columns (v was scattered above); 4 lanes x 8 columns per row
+    const int cg = (lane & 3) * 8;
+    const int col = n0 + cg;
+    const int sec = (col >= p.model_dim) + (col >= 2 * p.model_dim);
+    const int which = sec + p.first_section;  // 0 q, 1 k, 2 v
+    if (cg < w && col < p.N && which != 2) {
+      const int within = col - sec * p.model_dim;
+      const int head = fast_div(within, p.inv_head_dim);
+      const int d = within - head * p.head_dim;  // multiple of 8 (head_dim % 8 == 0 enforced on the host)
+      const long long colpart = (long long)head * p.tokens * p.head_dim_pad + d;
+      const float sc = which == 0 ? p.q_scale : 1.0f;
+      void* dst = which == 0 ? p.q_out : p.k_out;
+      float4 cs[4][2];
       if (p.rope) {
 #pragma unroll
         for (int pass = 0; pass < 4; ++pass) {
-          const int m = m0 + pass * 8 + (lane >> 2), col = n0 + cg;
-          if (m >= p.M || cg >= w || col >= p.N) continue;
-          const int sec = (col >= p.model_dim) + (col >= 2 * p.model_dim);
-          if (sec + p.first_section == 2) continue;
-          const int within = col - sec * p.model_dim;
-          const int d = within - fast_div(within, p.inv_head_dim) * p.head_dim;
-          const int t = m - fast_div(m, p.inv_tokens) * p.tokens;
-          const float4* cs = reinterpret_cast<const float4*>(p.rope + ((long long)t * (p.head_dim >> 1) + (d >> 1)) * 2);
-          rope_cs[pass][0] = cs[0];
-          rope_cs[pass][1] = cs[1];
-        }
-      }
-    }
-    if constexpr (EPI == MA3_EPI_STORE) {
-      if (p.bias) {
-        if (p.bias_per_row) {
-#pragma unroll
-          for (int pass = 0; pass < 4; ++pass) {
-            const int m = m0 + pass * 8 + (lane >> 2);
-            brow[pass] = m < p.M ? p.bias[m] : 0.f;
+          if (rc.off[pass] >= 0) {
+            const float4* c4 = reinterpret_cast<const float4*>(p.rope + rc.aux[pass] + d);
+            cs[pass][0] = c4[0];
+            cs[pass][1] = c4[1];
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) bcol[e] = (cg < w && n0 + cg + e < p.N) ? p.bias[n0 + cg + e] : 0.f;
         }
       }
-      // residual / accumulate operands of all 4 passes are fetched before any store (independent L2 round trips)
-      if (p.res || p.accumulate) {
+      const float* sp = stg + (lane >> 2) * kStagePitch + cg;
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-          const int m = m0 + pass * 8 + (lane >> 2), col = n0 + cg;
-          if (m >= p.M || cg >= w || col >= p.N) continue;
-          const int n = min(8, p.N - col);
-          const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
-          if (p.res)
-            load8(p.res, p.res_dtype, (long long)z * p.res_batch_stride + orow * p.res_ld + col, p.vec_ok != 0, n, rv[pass]);
-          if (p.accumulate)
-            load8(p.out, p.out_dtype, (long long)z * p.out_batch_stride + orow * p.out_ld + col, p.vec_ok != 0, n, ov[pass]);
-        }
-      }
-    }
+      for (int pass = 0; pass < 4; ++pass) {
+        if (rc.off[pass] >= 0) {
+          float v[8];
+          if (p.rope) {
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-      const int rr = pass * 8 + (lane >> 2);
-      const int m = m0 + rr, col = n0 + cg;
-      if (m >= p.M || cg >= w || col >= p.N) continue;
-      const float* sp = stg + rr * kStagePitch + cg;
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = sp[e];
-      if constexpr (EPI == MA3_EPI_STORE) {
-        const int n = min(8, p.N - col);
-        const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
-        const long long obase = (long long)z * p.out_batch_stride + orow * p.out_ld;
-        const bool vec = p.vec_ok != 0;
-        if (p.bias) {
-          if (p.bias_per_row) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += brow[pass];
+            for (int e = 0; e < 2; ++e) {
+              const float4 f = cs[pass][e];  // (cos, sin) of two consecutive pairs
+              const float x0 = sp[4 * e], x1 = sp[4 * e + 1], x2 = sp[4 * e + 2], x3 = sp[4 * e + 3];
+              v[4 * e] = (x0 * f.x - x1 * f.y) * sc;
+              v[4 * e + 1] = (x0 * f.y + x1 * f.x) * sc;
+              v[4 * e + 2] = (x2 * f.z - x3 * f.w) * sc;
+              v[4 * e + 3] = (x2 * f.w + x3 * f.z) * sc;
+            }
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += bcol[e];
+            for (int e = 0; e < 8; ++e) v[e] = sp[e] * sc;
           }
+          store8(dst, p.op_dtype, rc.off[pass] + colpart, true, 8, v);
         }
-        if (p.res) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] += rv[pass][e];
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
-        if (p.act == 1) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
-        } else if (p.act == 2) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.5f * v[e] * (1.f + erff(v[e] * 0.70710678118654752f));
-        } else if (p.act == 3) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = tanhf(v[e]);
-        }
-        if (p.accumulate) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] += ov[pass][e];
-        }
-        store8(p.out, p.out_dtype, obase + col, vec, n, v);
-      } else {  // MA3_EPI_QKV_ROPE: q / k columns (v was scattered above)
-        const int sec = (col >= p.model_dim) + (col >= 2 * p.model_dim);
-        const int which = sec + p.first_section;  // 0 q, 1 k, 2 v
-        if (which == 2) continue;
-        const int within = col - sec * p.model_dim;
-        const int head = fast_div(within, p.inv_head_dim);
-        const int d = within - head * p.head_dim;  // multiple of 8 (head_dim % 8 == 0 enforced on the host)
-        const int sample = fast_div(m, p.inv_tokens), t = m - sample * p.tokens;
-        const float sc = which == 0 ? p.q_scale : 1.0f;
-        if (p.rope) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float4 f = rope_cs[pass][e];  // (cos, sin) of two consecutive pairs
-            const float x0 = v[4 * e], x1 = v[4 * e + 1], x2 = v[4 * e + 2], x3 = v[4 * e + 3];
-            v[4 * e] = (x0 * f.x - x1 * f.y) * sc;
-            v[4 * e + 1] = (x0 * f.y + x1 * f.x) * sc;
-            v[4 * e + 2] = (x2 * f.z - x3 * f.w) * sc;
-            v[4 * e + 3] = (x2 * f.w + x3 * f.z) * sc;
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] *= sc;
-        }
-        void* dst = which == 0 ? p.q_out : p.k_out;
-        store8(dst, p.op_dtype, (((long long)sample * p.heads + head) * p.tokens + t) * p.head_dim_pad + d, true, 8, v);
+        sp += 8 * kStagePitch;
       }
     }
   }
@@ -374,7 +402,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], 4);
+        mbar_init(&tempty[i], kEpiWarps);
       }
       fence_barrier_init();
     }
@@ -440,7 +468,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       }
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int ew = warp - 2;                // epilogue warp index 0..7
+    const int half = ew >> 2;               // which alternating set of 32-column chunks it owns
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int n_t = tile % p.tiles_n;
@@ -450,13 +480,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       const int m0 = m_t * kBM + q * 32;
-      float* stg = staging + q * (32 * kStagePitch);
-      float4 hv[8], hv_next[8];
-      if constexpr (EPI == MA3_EPI_GATE_RES) gate_res_prefetch(p, m0, n_t * p.BN, min(32, p.BN), lane, hv);
+      float* stg = staging + ew * (32 * kStagePitch);
+      RowCtx rc;
+      make_row_ctx<EPI>(p, z, m0, lane, rc);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.tmem_stage_cols;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < p.BN; c0 += 32 * (kEpiWarps / 4)) {
         uint32_t r[32];
         const int w = min(32, p.BN - c0);
         if (w == 32) {
@@ -467,15 +497,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
 #pragma unroll
           for (int e = 0; e < 16; ++e) r[e] = r16[e];
         }
-        if constexpr (EPI == MA3_EPI_GATE_RES) {
-          if (c0 + 32 < p.BN) gate_res_prefetch(p, m0, n_t * p.BN + c0 + 32, min(32, p.BN - c0 - 32), lane, hv_next);
-        }
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, z, m0, n_t * p.BN + c0, w, r, stg, lane, hv);
-        if constexpr (EPI == MA3_EPI_GATE_RES) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) hv[i] = hv_next[i];
-        }
+        epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc);
       }
       tc_fence_before();
       __syncwarp();
@@ -543,7 +566,7 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   }
   MA3_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm: tile_n=%d must be a multiple of 16 in [16,256]", BN);
   const size_t stage_bytes = (size_t)(kBM + BN) * BK * 2;
-  const size_t kTail = 256 + 4 * 32 * kStagePitch * sizeof(float);  // barriers + epilogue staging
+  const size_t kTail = 256 + kEpiWarps * 32 * kStagePitch * sizeof(float);  // barriers + epilogue staging
   const size_t budget = 232448 - 1024 - kTail;
   int stages = (int)(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;

@@ -1,17 +1,16 @@
 #!/bin/bash
 # Build libma3b200.so for sm_100a (in-tree; the .so travels to the GPU box with the snapshot).
-set -e
-cd "$(dirname "$0")/../make-an-audio-3_b200/csrc"
+cd "$(dirname "$0")/../make-an-audio-3_b200/csrc" || exit 1
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include"
 mkdir -p build
-pids=()
+rm -f build/*.fail
 for f in host_common gemm elementwise act1d attention; do
   if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ ptx.cuh -nt build/$f.o ] || [ host_common.h -nt build/$f.o ] || [ ../../include/ma3_b200.h -nt build/$f.o ]; then
-    $NVCC $FLAGS -c -o build/$f.o $f.cu &
-    pids+=($!)
+    ( $NVCC $FLAGS -c -o build/$f.o.tmp $f.cu && mv build/$f.o.tmp build/$f.o || { rm -f build/$f.o build/$f.o.tmp; touch build/$f.fail; } ) &
   fi
 done
-for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libma3b200.so build/*.o
+wait
+if ls build/*.fail >/dev/null 2>&1; then echo "BUILD FAILED: $(ls build/*.fail)"; rm -f libma3b200.so; exit 1; fi
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libma3b200.so build/host_common.o build/gemm.o build/elementwise.o build/act1d.o build/attention.o || exit 1
 echo "built $(pwd)/libma3b200.so"
