@@ -104,11 +104,15 @@ typedef struct ma3_gemm {
   int32_t model_dim, head_dim, head_dim_pad, tokens, tokens_pad;
   float q_scale;
   int32_t first_section;  /* 0: columns are q|k|v (N = 3*model_dim); 1: k|v only (cross K/V, N = 2*model_dim) */
-  /* tiling override: 0 = library heuristic */
+  /* tiling overrides: 0 = library heuristic */
   int32_t tile_n;
+  int32_t cta_group;      /* 1: one CTA per 128-row tile; 2: CTA pair (tcgen05 cta_group::2) per 256-row tile */
 } ma3_gemm_t;
 
 int ma3_gemm(const ma3_gemm_t* g, void* stream);
+/* diagnostics only: device buffer (>= 256 int64) that CTA 0 of later ma3_gemm launches fills with clock64() stamps of
+ * its pipeline events; NULL switches tracing off (tools/probe_trace.py). */
+int ma3_debug_set_gemm_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused flash attention of one Next-DiT block: self-attention over the T latent tokens plus tanh-gated

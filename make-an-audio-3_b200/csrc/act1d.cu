@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(kActThreads) act1d_kernel(const TIn* __restric
                                                             int tiles_c, int logscale) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   TIn* tile = reinterpret_cast<TIn*>(smem_raw);
+  pdl_launch_dependents();
+  pdl_wait();
   const int CP = CT >> 1;                 // channel pairs per tile
   const int groups = kActThreads / CP;    // time groups per block
   const int TB = groups * kTT;
@@ -221,8 +223,9 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
   dim3 grid((unsigned)(tiles_c * tiles_t), (unsigned)B);
   const size_t smem = (size_t)(TB + 10) * CT * dtype_bytes(in_dtype);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t le = cudaSuccess;
 #define ACT_CASE(TI, TO) \
-  act1d_kernel<TI, TO><<<grid, kActThreads, smem, st>>>((const TI*)x, (TO*)out, alpha, beta, T, C, CT, tiles_c, logscale)
+  le = launch_pdl(act1d_kernel<TI, TO>, grid, dim3(kActThreads), smem, st, 1, (const TI*)x, (TO*)out, alpha, beta, T, C, CT, tiles_c, logscale)
   if (in_dtype == MA3_F16 && out_dtype == MA3_F16) ACT_CASE(__half, __half);
   else if (in_dtype == MA3_F32 && out_dtype == MA3_F16) ACT_CASE(float, __half);
   else if (in_dtype == MA3_BF16 && out_dtype == MA3_BF16) ACT_CASE(__nv_bfloat16, __nv_bfloat16);
@@ -230,6 +233,7 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
   else if (in_dtype == MA3_F32 && out_dtype == MA3_F32) ACT_CASE(float, float);
   else MA3_FAIL(MA3_EINVAL, "act1d: unsupported dtype pair %d -> %d", in_dtype, out_dtype);
 #undef ACT_CASE
+  if (le != cudaSuccess) MA3_FAIL((int)le, "act1d launch: %s", cudaGetErrorString(le));
   MA3_LAUNCH_CHECK("act1d");
   return 0;
 }

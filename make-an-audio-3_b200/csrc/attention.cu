@@ -98,10 +98,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
     __syncwarp();
     tmem_alloc(tmem_slot, kTmemCols);
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * BKV;
 
   if (warp == 4) {
@@ -298,7 +300,8 @@ static int launch_attn(const AttnParams& p, int NS, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((unsigned)((p.T + 127) / 128), (unsigned)p.H, (unsigned)NS);
-  attn_kernel<HDP, HD, BKV><<<grid, kAttnThreads, smem, st>>>(p);
+  cudaError_t le = launch_pdl(attn_kernel<HDP, HD, BKV>, grid, dim3(kAttnThreads), smem, st, 1, p);
+  if (le != cudaSuccess) MA3_FAIL((int)le, "attention launch: %s", cudaGetErrorString(le));
   MA3_LAUNCH_CHECK("attention");
   return 0;
 }

@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(const float* __re
                                                                int shift_off, int scale_off, int rows_per_sample,
                                                                TOut* __restrict__ out, int M, int D, float eps) {
   extern __shared__ __align__(16) float ab[];  // a[D] | b[D]
+  pdl_launch_dependents();
+  pdl_wait();
   float* sa = ab;
   float* sb = ab + D;
   const int sample = blockIdx.y;
@@ -181,6 +183,8 @@ __global__ void __launch_bounds__(256) final_layer_kernel(const float* __restric
                                                           float dt, float guidance) {
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_launch_dependents();
+  pdl_wait();
   if constexpr (!kCfg) {
     if (wid >= N * T) return;
     const int n = wid / T, t = wid - n * T;
@@ -228,6 +232,8 @@ __global__ void cfg_euler_kernel(const float* __restrict__ v, const float* __res
 __global__ void proj_in_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
                                float* __restrict__ h, int N, int xB, int C, int T, int D) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (i >= (long long)N * T * D) return;
   const int d = (int)(i % D);
   const long long row = i / D;
@@ -316,6 +322,8 @@ __global__ void __launch_bounds__(512) groupnorm_swish_kernel(const TIn* __restr
                                                               const float* __restrict__ b, TOut* __restrict__ out,
                                                               int T, int C, int groups, float eps, int swish) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int cg = C / groups;
   const int bidx = blockIdx.x / groups, g = blockIdx.x - bidx * groups;
   const TIn* xb = x + (long long)bidx * T * C + g * cg;
@@ -425,8 +433,8 @@ int ma3_rmsnorm_modulate(const float* x, const float* w, const float* mod, int64
   const size_t smem = 2 * (size_t)D * sizeof(float);
   const int nv = (D / 4 + 31) / 32;  // float4 per lane
 #define RMS_LAUNCH(TO, KV)                                                                                         \
-  rmsnorm_modulate_kernel<TO, KV><<<grid, 256, smem, ST(stream)>>>(x, w, mod, mod_ld, shift_off, scale_off, rps,   \
-                                                                   (TO*)out, M, D, eps)
+  launch_pdl(rmsnorm_modulate_kernel<TO, KV>, grid, dim3(256), smem, ST(stream), 1, x, w, mod, (long long)mod_ld,  \
+             shift_off, scale_off, rps, (TO*)out, M, D, eps)
 #define RMS_DISPATCH(TO)                 \
   do {                                   \
     if (nv <= 6) RMS_LAUNCH(TO, 6);      \
@@ -447,8 +455,9 @@ int ma3_final_layer(const float* h, const float* mod, int64_t mod_ld, int shift_
                     const float* bias, int N, int T, int D, int Cout, float eps, float* v_out, void* stream) {
   MA3_REQUIRE(h && mod && W && bias && v_out, "final_layer: null pointer");
   MA3_REQUIRE(Cout <= kMaxCout && N > 0 && T > 0 && D <= 2048, "final_layer: Cout=%d must be <= 32, D <= 2048", Cout);
-  final_layer_kernel<false><<<nblk((long long)N * T, 8), 256, 0, ST(stream)>>>(
-      h, mod, mod_ld, shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, nullptr, nullptr, 0.f, 0.f);
+  launch_pdl(final_layer_kernel<false>, dim3(nblk((long long)N * T, 8)), dim3(256), 0, ST(stream), 1, h, mod,
+             (long long)mod_ld, shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, (const float*)nullptr,
+             (float*)nullptr, 0.f, 0.f);
   MA3_LAUNCH_CHECK("final_layer");
   return 0;
 }
@@ -459,8 +468,8 @@ int ma3_final_layer_cfg_euler(const float* h, const float* mod, int64_t mod_ld, 
                               void* stream) {
   MA3_REQUIRE(h && mod && W && bias && x_in && x_out, "final_layer_cfg_euler: null pointer");
   MA3_REQUIRE(Cout <= kMaxCout && N > 0 && N % 2 == 0 && T > 0 && D <= 2048, "final_layer_cfg_euler: N must be even, Cout <= 32, D <= 2048");
-  final_layer_kernel<true><<<nblk((long long)(N / 2) * T, 8), 256, 0, ST(stream)>>>(
-      h, mod, mod_ld, shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, x_in, x_out, dt, guidance);
+  launch_pdl(final_layer_kernel<true>, dim3(nblk((long long)(N / 2) * T, 8)), dim3(256), 0, ST(stream), 1, h, mod,
+             (long long)mod_ld, shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, x_in, x_out, dt, guidance);
   MA3_LAUNCH_CHECK("final_layer_cfg_euler");
   return 0;
 }
@@ -476,7 +485,8 @@ int ma3_cfg_euler_update(const float* v, const float* x, float* out, int64_t ele
 int ma3_proj_in(const float* x, const float* W, const float* b, float* h, int N, int x_batch, int C, int T, int D,
                 void* stream) {
   MA3_REQUIRE(x && W && b && h && N > 0 && x_batch > 0, "proj_in: null pointer or empty");
-  proj_in_kernel<<<nblk((long long)N * T * D, 256), 256, 0, ST(stream)>>>(x, W, b, h, N, x_batch, C, T, D);
+  launch_pdl(proj_in_kernel, dim3(nblk((long long)N * T * D, 256)), dim3(256), 0, ST(stream), 1, x, W, b, h, N, x_batch, C,
+             T, D);
   MA3_LAUNCH_CHECK("proj_in");
   return 0;
 }
@@ -528,7 +538,8 @@ int ma3_groupnorm_swish(const void* x, int in_dtype, const float* w, const float
   MA3_REQUIRE(x && w && b && out && B > 0 && T > 0 && C % groups == 0, "groupnorm_swish: bad arguments");
   const unsigned grid = (unsigned)(B * groups);
 #define GN_CASE(TI, TO) \
-  groupnorm_swish_kernel<TI, TO><<<grid, 512, 0, ST(stream)>>>((const TI*)x, w, b, (TO*)out, T, C, groups, eps, swish)
+  launch_pdl(groupnorm_swish_kernel<TI, TO>, dim3(grid), dim3(512), 0, ST(stream), 1, (const TI*)x, w, b, (TO*)out, T, C, \
+             groups, eps, swish)
   if (in_dtype == MA3_BF16 && out_dtype == MA3_BF16) GN_CASE(__nv_bfloat16, __nv_bfloat16);
   else if (in_dtype == MA3_F32 && out_dtype == MA3_BF16) GN_CASE(float, __nv_bfloat16);
   else if (in_dtype == MA3_F16 && out_dtype == MA3_F16) GN_CASE(__half, __half);

@@ -46,7 +46,12 @@ struct GemmKParams {
   int first_section;
   int op_dtype;
   float inv_rows_per_sample, inv_tokens, inv_head_dim;  // exact-division helpers (see fast_div)
+  long long* trace;  // diagnostics: when non-null, CTA 0 records clock64() at pipeline events (tools/probe_trace.py)
 };
+
+__device__ __forceinline__ void trace_evt(const GemmKParams& p, int tile_local, int slot) {
+  if (p.trace && blockIdx.x == 0 && tile_local < 16) p.trace[tile_local * 16 + slot] = clock64();
+}
 
 // floor(a / b) for 0 <= a < 2^22 via a float reciprocal (inv = 1/b): exact because the rounding error of
 // (a + 0.5) * inv is far below the 0.5 / b margin for the sizes used here (rows < 4M, b < 64K).
@@ -128,7 +133,7 @@ __device__ __forceinline__ void store8(void* base, int dtype, long long idx, boo
 // different row).  The chunk is therefore transposed through a per-warp shared-memory patch (pitch 33 floats, conflict
 // free both ways) and processed row-wise: a group of lanes covers contiguous columns of one row, so loads of the
 // residual / gate / RoPE table and the stores are coalesced.
-constexpr int kStagePitch = 33;
+constexpr int kStagePitch = 36;  // floats; 16-byte aligned rows, conflict-free for 128-bit shared accesses both ways
 
 // Per-tile, per-lane row bookkeeping hoisted out of the chunk loop (the epilogue warps are instruction-latency bound:
 // one warp per scheduler, dependent chains).  Meaning per epilogue:
@@ -214,10 +219,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
       }
     }
   }
-  // registers (thread = row) -> staging patch
+  // registers (thread = row) -> staging patch, 128-bit stores
 #pragma unroll
-  for (int e = 0; e < 32; ++e)
-    if (e < w) stg[lane * kStagePitch + e] = __uint_as_float(r[e]);
+  for (int e = 0; e < 32; e += 4)
+    if (e < w)
+      *reinterpret_cast<uint4*>(stg + lane * kStagePitch + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
   __syncwarp();
 
   if constexpr (EPI == MA3_EPI_GATE_RES) {
@@ -236,9 +242,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
       const float* sp = stg + (lane >> 3) * kStagePitch + cg;
 #pragma unroll
       for (int pass = 0; pass < 8; ++pass) {
-        if (rc.off[pass] >= 0)
-          red_add_f32x4(out + rc.off[pass] + col, gv[pass].x * sp[0], gv[pass].y * sp[1], gv[pass].z * sp[2],
-                        gv[pass].w * sp[3]);
+        if (rc.off[pass] >= 0) {
+          const float4 a = *reinterpret_cast<const float4*>(sp);
+          red_add_f32x4(out + rc.off[pass] + col, gv[pass].x * a.x, gv[pass].y * a.y, gv[pass].z * a.z, gv[pass].w * a.w);
+        }
         sp += 4 * kStagePitch;
       }
     }
@@ -253,7 +260,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
         if (rc.off[pass] >= 0) {
           float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = silu_f(sp[2 * e]) * sp[2 * e + 1];
+          for (int e = 0; e < 4; ++e) {
+            const float4 a = *reinterpret_cast<const float4*>(sp + 4 * e);
+            v[2 * e] = silu_f(a.x) * a.y;
+            v[2 * e + 1] = silu_f(a.z) * a.w;
+          }
           store8(p.out, p.out_dtype, rc.off[pass] + (col >> 1), true, 8, v);
         }
         sp += 16 * kStagePitch;
@@ -286,8 +297,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
       for (int pass = 0; pass < 4; ++pass) {
         if (rc.off[pass] >= 0) {
           float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = sp[e];
+          {
+            const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+          }
           if (p.bias) {
             if (p.bias_per_row) {
 #pragma unroll
@@ -301,8 +314,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] += rv[pass][e];
           }
+          if (p.alpha != 1.f) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
+            for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
+          }
           if (p.act == 1) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
@@ -354,15 +369,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const float4 f = cs[pass][e];  // (cos, sin) of two consecutive pairs
-              const float x0 = sp[4 * e], x1 = sp[4 * e + 1], x2 = sp[4 * e + 2], x3 = sp[4 * e + 3];
+              const float4 xv = *reinterpret_cast<const float4*>(sp + 4 * e);
+              const float x0 = xv.x, x1 = xv.y, x2 = xv.z, x3 = xv.w;
               v[4 * e] = (x0 * f.x - x1 * f.y) * sc;
               v[4 * e + 1] = (x0 * f.y + x1 * f.x) * sc;
               v[4 * e + 2] = (x2 * f.z - x3 * f.w) * sc;
               v[4 * e + 3] = (x2 * f.w + x3 * f.z) * sc;
             }
           } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = sp[e] * sc;
+            const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+            v[0] = a.x * sc; v[1] = a.y * sc; v[2] = a.z * sc; v[3] = a.w * sc;
+            v[4] = b.x * sc; v[5] = b.y * sc; v[6] = b.z * sc; v[7] = b.w * sc;
           }
           store8(dst, p.op_dtype, rc.off[pass] + colpart, true, 8, v);
         }
@@ -374,21 +391,27 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int EPI>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile: each
+// CTA stages its own 128 rows of A and HALF of the B tile, the leader issues one M=256 MMA that reads both CTAs' shared
+// memory, and each CTA drains its own 128 accumulator rows from its own TMEM.  Halving the B bytes every SM has to pull
+// through L2 is what lifts the L2-feed bound of the large GEMMs.
+template <int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t a_bytes = kBM * p.BK * 2, b_bytes = p.BN * p.BK * 2;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t a_bytes = kBM * p.BK * 2, b_bytes = (p.BN / CG) * p.BK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;   // per CTA
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* staging = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);  // 4 warps x 32 x 33 floats
+  float* staging = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);  // kEpiWarps x 32 x 33 floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA);
@@ -402,54 +425,68 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], kEpiWarps);
+        mbar_init(&tempty[i], kEpiWarps * CG);   // CG = 2: the leader's copy collects both CTAs' epilogue warps
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, p.tmem_cols);
+    if constexpr (CG == 2) tmem_alloc2(tmem_slot, p.tmem_cols);
+    else tmem_alloc(tmem_slot, p.tmem_cols);
   }
+  pdl_launch_dependents();
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
 
+  // work items: CG = 1 -> 128-row tiles over all CTAs; CG = 2 -> 256-row tiles over CTA pairs
   const int total_tiles = p.tiles_m * p.tiles_n * p.batch;
+  const int worker = blockIdx.x / CG, n_workers = gridDim.x / CG;
   const int kchunks = p.K / p.BK;
   const int iters = p.taps * kchunks;
 
   if (warp == 0) {
     if (elect_one()) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
         const int n_t = tile % p.tiles_n;
         const int rest = tile / p.tiles_n;
         const int m_t = rest % p.tiles_m;
         const int z = rest / p.tiles_m;
         for (int tap = 0; tap < p.taps; ++tap) {
-          const int arow = m_t * kBM + p.a_shift[tap];
-          const int brow = n_t * p.BN + p.b_row[tap];
+          const int arow = (m_t * CG + (int)rank) * kBM + p.a_shift[tap];
+          const int brow = n_t * p.BN + (int)rank * (p.BN / CG) + p.b_row[tap];
           for (int kc = 0; kc < kchunks; ++kc, ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1;
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full[s], stage_bytes);
             uint8_t* dst = tiles + (size_t)s * stage_bytes;
-            tma_load_3d(dst, &p.tmA, &full[s], kc * p.BK, arow, p.a_batched ? z : 0);
-            tma_load_3d(dst + a_bytes, &p.tmB, &full[s], kc * p.BK, brow, p.b_batched ? z : 0);
+            if constexpr (CG == 2) {
+              if (leader) mbar_arrive_expect_tx(&full[s], 2 * stage_bytes);   // bytes of both CTAs land on the leader
+              tma_load_3d_2cta(dst, &p.tmA, &full[s], kc * p.BK, arow, p.a_batched ? z : 0);
+              tma_load_3d_2cta(dst + a_bytes, &p.tmB, &full[s], kc * p.BK, brow, p.b_batched ? z : 0);
+            } else {
+              mbar_arrive_expect_tx(&full[s], stage_bytes);
+              tma_load_3d(dst, &p.tmA, &full[s], kc * p.BK, arow, p.a_batched ? z : 0);
+              tma_load_3d(dst + a_bytes, &p.tmB, &full[s], kc * p.BK, brow, p.b_batched ? z : 0);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
+    if (leader && elect_one()) {
       int it = 0, lt = 0;
       const int sw = p.BK * 2;
       const int ksteps = p.BK / 16;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers, ++lt) {
         const int as = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
+        trace_evt(p, lt, 0);
         mbar_wait(&tempty[as], aph ^ 1);
+        trace_evt(p, lt, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * p.tmem_stage_cols;
         for (int i = 0; i < iters; ++i, ++it) {
@@ -460,11 +497,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
           const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
           const uint64_t da = umma_desc_kmajor(a_addr, sw);
           const uint64_t db = umma_desc_kmajor(a_addr + a_bytes, sw);
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (i | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[s]);
+          for (int k = 0; k < ksteps; ++k) {
+            if constexpr (CG == 2)
+              umma_f16_2cta(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (i | k) != 0 ? 1u : 0u);
+            else
+              umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (CG == 2) umma_commit_2cta(&empty[s]);   // frees the stage in both CTAs
+          else umma_commit(&empty[s]);
         }
-        umma_commit(&tfull[as]);
+        if constexpr (CG == 2) umma_commit_2cta(&tfull[as]);
+        else umma_commit(&tfull[as]);
+        trace_evt(p, lt, 2);
       }
     }
   } else {
@@ -472,23 +516,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
     const int ew = warp - 2;                // epilogue warp index 0..7
     const int half = ew >> 2;               // which alternating set of 32-column chunks it owns
     int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = worker; tile < total_tiles; tile += n_workers, ++lt) {
       const int n_t = tile % p.tiles_n;
       const int rest = tile / p.tiles_n;
       const int m_t = rest % p.tiles_m;
       const int z = rest / p.tiles_m;
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
-      const int m0 = m_t * kBM + q * 32;
+      const int m0 = (m_t * CG + (int)rank) * kBM + q * 32;
       float* stg = staging + ew * (32 * kStagePitch);
       RowCtx rc;
       make_row_ctx<EPI>(p, z, m0, lane, rc);
+      if (ew == 0 && lane == 0) trace_evt(p, lt, 4);
       mbar_wait(&tfull[as], aph);
+      if (ew == 0 && lane == 0) trace_evt(p, lt, 5);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.tmem_stage_cols;
       for (int c0 = half * 32; c0 < p.BN; c0 += 32 * (kEpiWarps / 4)) {
         uint32_t r[32];
         const int w = min(32, p.BN - c0);
+        const bool tr0 = ew == 0 && lane == 0 && c0 == 0;
+        if (tr0) trace_evt(p, lt, 8);
         if (w == 32) {
           tmem_ld32(taddr + c0, r);
         } else {
@@ -498,21 +546,31 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
           for (int e = 0; e < 16; ++e) r[e] = r16[e];
         }
         tmem_ld_wait();
+        if (tr0) trace_evt(p, lt, 9);
         epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc);
+        if (tr0) trace_evt(p, lt, 10);
       }
+      if (ew == 0 && lane == 0) trace_evt(p, lt, 6);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_leader(&tempty[as]);
+        else mbar_arrive(&tempty[as]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if constexpr (CG == 2) tmem_dealloc2(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
+
+static long long* g_trace = nullptr;
 
 static uint32_t pow2_cols(int n) {
   uint32_t c = 32;
@@ -520,17 +578,23 @@ static uint32_t pow2_cols(int n) {
   return c;
 }
 
-template <int EPI>
-static int launch(const GemmKParams& kp, size_t smem, int grid, cudaStream_t st) {
+template <int EPI, int CG>
+static int launch_cg(const GemmKParams& kp, size_t smem, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(tap_gemm): %s", cudaGetErrorString(e));
     configured = true;
   }
-  tap_gemm_kernel<EPI><<<grid, kGemmThreads, smem, st>>>(kp);
+  cudaError_t e = launch_pdl(tap_gemm_kernel<EPI, CG>, dim3((unsigned)grid), dim3(kGemmThreads), smem, st, CG, kp);
+  if (e != cudaSuccess) MA3_FAIL((int)e, "tap_gemm launch: %s", cudaGetErrorString(e));
   MA3_LAUNCH_CHECK("tap_gemm");
   return 0;
+}
+
+template <int EPI>
+static int launch(const GemmKParams& kp, size_t smem, int grid, int cta_group, cudaStream_t st) {
+  return cta_group == 2 ? launch_cg<EPI, 2>(kp, smem, grid, st) : launch_cg<EPI, 1>(kp, smem, grid, st);
 }
 
 }  // namespace ma3
@@ -565,7 +629,12 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
     }
   }
   MA3_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm: tile_n=%d must be a multiple of 16 in [16,256]", BN);
-  const size_t stage_bytes = (size_t)(kBM + BN) * BK * 2;
+  // CTA pairs (cta_group::2, 256-row tiles) for the large GEMMs: each SM pulls only half of the B tile through L2.
+  int CG = g->cta_group;
+  MA3_REQUIRE(CG >= 0 && CG <= 2, "gemm: cta_group must be 0 (auto), 1 or 2");
+  if (CG == 0) CG = (g->M >= 1024 && BN >= 128 && BN % 32 == 0) ? 2 : 1;
+  if (CG == 2) MA3_REQUIRE(BN % 32 == 0, "gemm: cta_group 2 needs tile_n %% 32 == 0 (got %d)", BN);
+  const size_t stage_bytes = (size_t)(kBM + BN / CG) * BK * 2;   // per CTA
   const size_t kTail = 256 + kEpiWarps * 32 * kStagePitch * sizeof(float);  // barriers + epilogue staging
   const size_t budget = 232448 - 1024 - kTail;
   int stages = (int)(budget / stage_bytes);
@@ -579,8 +648,8 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   for (int i = 0; i < g->taps; ++i) { kp.a_shift[i] = g->a_shift[i]; kp.b_row[i] = g->b_row[i]; }
   kp.a_batched = g->a_batch_stride != 0; kp.b_batched = g->b_batch_stride != 0;
   kp.BN = BN; kp.BK = BK; kp.stages = stages;
-  kp.tiles_m = (g->M + kBM - 1) / kBM; kp.tiles_n = (g->N + BN - 1) / BN; kp.batch = g->batch;
-  kp.idesc = umma_idesc(kBM, BN, g->dtype == MA3_BF16 ? 1 : 0);
+  kp.tiles_m = (g->M + kBM * CG - 1) / (kBM * CG); kp.tiles_n = (g->N + BN - 1) / BN; kp.batch = g->batch;
+  kp.idesc = umma_idesc(kBM * CG, BN, g->dtype == MA3_BF16 ? 1 : 0);
   kp.tmem_stage_cols = pow2_cols(BN);
   kp.tmem_cols = 2 * kp.tmem_stage_cols;
   kp.op_dtype = g->dtype;
@@ -595,7 +664,7 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   {
     uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->b_rows, (uint64_t)(kp.b_batched ? g->batch : 1)};
     uint64_t str[2] = {(uint64_t)g->b_ld * 2, (uint64_t)(kp.b_batched ? g->b_batch_stride : g->b_rows * g->b_ld) * 2};
-    uint32_t box[3] = {(uint32_t)BK, (uint32_t)BN, 1};
+    uint32_t box[3] = {(uint32_t)BK, (uint32_t)(BN / CG), 1};
     int rc = encode_tmap(&kp.tmB, g->b, 2, 3, dims, str, box, BK * 2);
     if (rc) return rc;
   }
@@ -613,9 +682,11 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   kp.inv_rows_per_sample = g->rows_per_sample > 0 ? 1.0f / (float)g->rows_per_sample : 0.f;
   kp.inv_tokens = g->tokens > 0 ? 1.0f / (float)g->tokens : 0.f;
   kp.inv_head_dim = g->head_dim > 0 ? 1.0f / (float)g->head_dim : 0.f;
+  kp.trace = g_trace;
 
   const int total_tiles = kp.tiles_m * kp.tiles_n * kp.batch;
-  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  const int workers = num_sms() / CG;   // CTAs (CG = 1) or CTA pairs (CG = 2)
+  const int grid = (total_tiles < workers ? total_tiles : workers) * CG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   switch (g->epi) {
@@ -637,19 +708,19 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
       }
       kp.vec_ok = vec ? 1 : 0;
       if (kp.alpha == 0.f) kp.alpha = 1.f;
-      return launch<MA3_EPI_STORE>(kp, smem, grid, st);
+      return launch<MA3_EPI_STORE>(kp, smem, grid, CG, st);
     }
     case MA3_EPI_GATE_RES:
       MA3_REQUIRE(g->out && g->gate && g->rows_per_sample > 0, "gemm/gate_res: out, gate, rows_per_sample required");
       MA3_REQUIRE(g->batch == 1, "gemm/gate_res: batch must be 1 (flatten samples into M)");
       MA3_REQUIRE(g->N % 4 == 0 && g->out_ld % 4 == 0 && g->gate_ld % 4 == 0 && aligned16(g->out) && aligned16(g->gate),
                   "gemm/gate_res: N, out_ld, gate_ld must be multiples of 4 and pointers 16-byte aligned");
-      return launch<MA3_EPI_GATE_RES>(kp, smem, grid, st);
+      return launch<MA3_EPI_GATE_RES>(kp, smem, grid, CG, st);
     case MA3_EPI_SWIGLU:
       MA3_REQUIRE(g->out && g->batch == 1, "gemm/swiglu: out required, batch must be 1");
       MA3_REQUIRE(g->N % 16 == 0 && g->out_ld % 8 == 0 && aligned16(g->out) && g->out_dtype != MA3_F32,
                   "gemm/swiglu: N %% 16, out_ld %% 8, 16-bit out required");
-      return launch<MA3_EPI_SWIGLU>(kp, smem, grid, st);
+      return launch<MA3_EPI_SWIGLU>(kp, smem, grid, CG, st);
     case MA3_EPI_QKV_ROPE:
       MA3_REQUIRE(g->q_out && g->k_out && g->vt_out, "gemm/qkv_rope: q_out, k_out, vt_out required");
       MA3_REQUIRE(g->first_section == 0 || g->first_section == 1, "gemm/qkv_rope: first_section must be 0 or 1");
@@ -661,8 +732,15 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
       MA3_REQUIRE(g->tokens > 0 && g->M % g->tokens == 0 && g->tokens_pad >= g->tokens,
                   "gemm/qkv_rope: M must be samples*tokens");
       MA3_REQUIRE(aligned16(g->q_out) && aligned16(g->k_out), "gemm/qkv_rope: outputs must be 16-byte aligned");
-      return launch<MA3_EPI_QKV_ROPE>(kp, smem, grid, st);
+      return launch<MA3_EPI_QKV_ROPE>(kp, smem, grid, CG, st);
     default:
       MA3_FAIL(MA3_EINVAL, "gemm: unknown epilogue %d", g->epi);
   }
+}
+
+/* diagnostics: device buffer of >= 256 int64 that CTA 0 of subsequent ma3_gemm launches fills with clock64()
+ * timestamps (per tile: MMA thread slots 0-2, epilogue warp slots 4-6); pass NULL to switch tracing off. */
+extern "C" int ma3_debug_set_gemm_trace(void* buf) {
+  ma3::g_trace = reinterpret_cast<long long*>(buf);
+  return 0;
 }

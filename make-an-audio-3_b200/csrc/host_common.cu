@@ -4,11 +4,21 @@
 
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace ma3 {
 
 std::atomic<int64_t> g_launches{0};
 thread_local char g_err[512] = {0};
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MA3_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;   // measured neutral on B200 (graph replay already hides the gaps): opt-in
+  }
+  return v != 0;
+}
 
 int num_sms() {
   static int n = 0;

@@ -65,7 +65,7 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
          out_row_mul=1, out_row_off=0, bias=None, bias_per_row=False, res=None, res_ld=None, res_batch_stride=0,
          alpha=1.0, accumulate=False, gate=None, rows_per_sample=0, q_out=None, k_out=None, vt_out=None, rope=None,
          model_dim=0, head_dim=0, head_dim_pad=0, tokens=0, tokens_pad=0, q_scale=1.0, first_section=0, act=0,
-         tile_n=0):
+         tile_n=0, cta_group=0):
     """acc[z,m,n] = sum_taps sum_k A[z, m + a_shift, k] * B[z, n + b_row, k]; see include/ma3_b200.h."""
     lib = L.require_device()
     assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float16)
@@ -116,6 +116,7 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
     d.first_section = first_section
     d.act = act
     d.tile_n = tile_n
+    d.cta_group = cta_group
     with _Span("tap_gemm/" + _EPI_NAMES[epi], 2.0 * M * N * K * len(taps) * batch):
         L.check(lib.ma3_gemm(C.byref(d), L.stream_ptr()), "ma3_gemm")
     return out

@@ -37,6 +37,20 @@ def test_gemm_plain(ops, M, N, K, dt):
     assert rel(out, a.float() @ b.float().t()) < 1e-4  # fp32 accumulate of identical 16-bit operands
 
 
+@pytest.mark.parametrize("M,N,K,tn", [(256, 128, 64, 128), (1000, 1152, 1152, 0), (4992, 3456, 1152, 0), (300, 256, 128, 256),
+                                      (2496, 768, 768, 0)])
+def test_gemm_cta_pair(ops, M, N, K, tn):
+    """cta_group::2 (256-row tiles over CTA pairs) against the same fp32 reference, incl. a ragged last pair."""
+    a = torch.randn(M, K, generator=g(1)).bfloat16().cuda()
+    b = (torch.randn(N, K, generator=g(2)) / K ** 0.5).bfloat16().cuda()
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, M=M, N=N, K=K, out=out, tile_n=tn, cta_group=2)
+    assert rel(out, a.float() @ b.float().t()) < 1e-4
+    o1 = torch.empty_like(out)
+    ops.gemm(a, b, M=M, N=N, K=K, out=o1, tile_n=tn, cta_group=1)
+    assert torch.equal(out, o1)   # same accumulation order per output element
+
+
 def test_gemm_epilogue_store_variants(ops):
     from ma3_b200 import lib as L
     M, N, K = 500, 384, 384

@@ -30,7 +30,7 @@ def bench(name, fn, flops=0, bytes_=0, n=10):
     torch.cuda.synchronize()
     tot = 0.0
     for _ in range(n):
-        flush.zero_()   # evict L2
+        flush.sum()   # evict L2 with clean lines
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
@@ -46,6 +46,12 @@ bench("attention self+cross", lambda: ops.attention(q, k, vt, ky, vyt, gate, att
 bench("wo gemm + gate_res", lambda: ops.gemm(att, wo, M=M, N=D, K=D, epi=L.EPI_GATE_RES, out=h, gate=mod[:, 2 * D:3 * D], rows_per_sample=T), flops=2.0 * M * D * D)
 bench("w13 gemm + swiglu", lambda: ops.gemm(u, w13, M=M, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=mid, out_ld=F), flops=2.0 * M * 2 * F * D)
 bench("w2 gemm + gate_res", lambda: ops.gemm(mid, w2, M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=h, gate=mod[:, 5 * D:6 * D], rows_per_sample=T), flops=2.0 * M * D * F)
+for cg in (1, 2):
+    bench(f"qkv cta_group={cg}", lambda: ops.gemm(u, wqkv, M=M, N=3 * D, K=D, epi=L.EPI_QKV_ROPE, q_out=q, k_out=k, vt_out=vt, rope=rope, model_dim=D, head_dim=hd, head_dim_pad=hdp, tokens=T, tokens_pad=Tp, q_scale=qs, cta_group=cg), flops=2.0 * M * 3 * D * D)
+    bench(f"wo cta_group={cg}", lambda: ops.gemm(att, wo, M=M, N=D, K=D, epi=L.EPI_GATE_RES, out=h, gate=mod[:, 2 * D:3 * D], rows_per_sample=T, cta_group=cg), flops=2.0 * M * D * D)
+    bench(f"w13 cta_group={cg}", lambda: ops.gemm(u, w13, M=M, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=mid, out_ld=F, cta_group=cg), flops=2.0 * M * 2 * F * D)
+    bench(f"w2 cta_group={cg}", lambda: ops.gemm(mid, w2, M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=h, gate=mod[:, 5 * D:6 * D], rows_per_sample=T, cta_group=cg), flops=2.0 * M * D * F)
+sys.exit(0)
 for tn in (128, 192, 256):
     bench(f"w13 swiglu tile_n={tn}", lambda: ops.gemm(u, w13, M=M, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=mid, out_ld=F, tile_n=tn), flops=2.0 * M * 2 * F * D)
     bench(f"qkv rope tile_n={tn}", lambda: ops.gemm(u, wqkv, M=M, N=3 * D, K=D, epi=L.EPI_QKV_ROPE, q_out=q, k_out=k, vt_out=vt, rope=rope, model_dim=D, head_dim=hd, head_dim_pad=hdp, tokens=T, tokens_pad=Tp, q_scale=qs, tile_n=tn), flops=2.0 * M * 3 * D * D)
