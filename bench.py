@@ -243,6 +243,26 @@ def main():
     h2d = cond_h.numel() * 4 + unc_h.numel() * 4 + x0_h.numel() * 4
     d2h = B * samples * 4
 
+    # per-stage device time (sampler graph / VAE decode / vocoder), same inputs, CUDA events
+    stage_ms = None
+    if rank == 0:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc = [0.0, 0.0, 0.0]
+        reps = 3
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            ev[0].record()
+            z, _ = pipe.sample_cfg(cond, GUIDANCE, unc, B, timesteps=N_POINTS, x_latent=x0)
+            ev[1].record()
+            mel = pipe.decode_first_stage(z)
+            ev[2].record()
+            pipe.vocoder.vocode_tensor(mel)
+            ev[3].record()
+            torch.cuda.synchronize()
+            for i in range(3):
+                acc[i] += ev[i].elapsed_time(ev[i + 1]) / reps
+        stage_ms = {"sample_cfg_24_steps": round(acc[0], 3), "vae_decode": round(acc[1], 3), "bigvgan": round(acc[2], 3)}
+
     # live roofline of the dominant kernel: one eager (no graph) pass over the same workload with CUDA events around
     # every launch on the launching stream
     roofline, breakdown = None, None
@@ -309,7 +329,8 @@ def main():
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "kernel_breakdown": breakdown}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stage_ms,
+                "kernel_breakdown": breakdown}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

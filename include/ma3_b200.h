@@ -150,8 +150,9 @@ int ma3_final_layer_cfg_euler(const float* h, const float* mod, int64_t mod_ld, 
 int ma3_cfg_euler_update(const float* v, const float* x, float* out, int64_t elems, float dt, float guidance, int cfg,
                          void* stream);
 
-/* h[n*T + t, :] = W x[n % x_batch, :, t] + b   (proj_in on the 'b c t -> b t c' view, flag_large_dit.py:186-187). */
-int ma3_proj_in(const float* x, const float* W, const float* b, float* h, int N, int x_batch, int C, int T, int D,
+/* h[n*T + t, :] = x[n % x_batch, :, t] Wt + b   (proj_in on the 'b c t -> b t c' view, flag_large_dit.py:186-187);
+ * Wt is the TRANSPOSED nn.Linear weight, [C, D] row-major. */
+int ma3_proj_in(const float* x, const float* Wt, const float* b, float* h, int N, int x_batch, int C, int T, int D,
                 void* stream);
 
 /* Sinusoidal timestep embedding [cos | sin] (flag_large_dit_moe.py:110-127); t int64 [M] -> out [M, dim]. */

@@ -21,7 +21,12 @@ struct AttnParams {
   void* out;
   const float* gate;
   int dtype;
+  long long* trace;  // diagnostics (CTA 0 records clock64 at pipeline events when non-null)
 };
+
+__device__ __forceinline__ void attn_trace(const AttnParams& p, int it, int slot) {
+  if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 16) p.trace[it * 16 + slot] = clock64();
+}
 
 template <int N>
 __device__ __forceinline__ void tmem_ld_n(uint32_t addr, uint32_t* r);
@@ -44,6 +49,82 @@ __device__ __forceinline__ void accumulate_o(uint32_t taddr, float (&acc)[HD], f
     for (int e = 0; e < W; ++e) acc[OFF + e] = fmaf(acc[OFF + e], alpha, __uint_as_float(r[e]));
     accumulate_o<HD, OFF + W>(taddr, acc, alpha);
   }
+}
+
+// Pass 1 of a KV tile: row maximum over BKV logits (thread <-> query row).  kMask only on the ragged last tile of a
+// segment: the unmasked variant is one FMNMX per element.  TMEM loads are software-pipelined (the next 16 columns are
+// in flight while the current 16 are reduced) and the reduction uses four independent chains.
+template <bool kMask>
+__device__ __forceinline__ void max16(const uint32_t (&r)[16], int c0, int valid, float (&mx)[4]) {
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    if (kMask) {
+      if (c0 + e < valid) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[e]));
+    } else {
+      mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[e]));
+    }
+  }
+}
+
+template <int BKV, bool kMask>
+__device__ __forceinline__ float row_max_pass(uint32_t tS, float m, int valid) {
+  float mx[4] = {m, m, m, m};
+  uint32_t ra[16], rb[16];
+  tmem_ld16(tS, ra);
+#pragma unroll
+  for (int c0 = 0; c0 < BKV; c0 += 32) {
+    tmem_ld_wait();
+    tmem_ld16(tS + c0 + 16, rb);
+    max16<kMask>(ra, c0, valid, mx);
+    tmem_ld_wait();
+    if (c0 + 32 < BKV) tmem_ld16(tS + c0 + 32, ra);
+    max16<kMask>(rb, c0 + 16, valid, mx);
+  }
+  return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+}
+
+// Pass 2: p = exp2(s - max), row sum, P written as 16-bit into the 128B-swizzled K-major smem tile.
+template <bool kMask, bool kBf16>
+__device__ __forceinline__ void exp16(const uint32_t (&r)[16], int c0, int valid, float mx, float (&sum)[2], uint8_t* sP,
+                                      int row) {
+  uint32_t pk[8];
+#pragma unroll
+  for (int e = 0; e < 16; e += 2) {
+    float p0 = ex2_approx(__uint_as_float(r[e]) - mx);
+    float p1 = ex2_approx(__uint_as_float(r[e + 1]) - mx);
+    if (kMask) {
+      p0 = (c0 + e < valid) ? p0 : 0.f;
+      p1 = (c0 + e + 1 < valid) ? p1 : 0.f;
+    }
+    sum[0] += p0;
+    sum[1] += p1;
+    pk[e >> 1] = kBf16 ? pack_bf16(p0, p1) : pack_f16(p0, p1);
+  }
+  // 16 keys = 32 B = two 16-byte units of this row inside the 64-key chunk (128 B per row)
+  uint8_t* chunk = sP + (c0 >> 6) * (128 * 128) + row * 128;
+  const int u0 = (c0 & 63) >> 3;  // first 16-byte unit
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int pos = (u0 + u) ^ (row & 7);
+    *reinterpret_cast<uint4*>(chunk + pos * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+  }
+}
+
+template <int BKV, bool kMask, bool kBf16>
+__device__ __forceinline__ float exp_store_pass(uint32_t tS, float mx, int valid, uint8_t* sP, int row) {
+  float sum[2] = {0.f, 0.f};
+  uint32_t ra[16], rb[16];
+  tmem_ld16(tS, ra);
+#pragma unroll
+  for (int c0 = 0; c0 < BKV; c0 += 32) {
+    tmem_ld_wait();
+    tmem_ld16(tS + c0 + 16, rb);
+    exp16<kMask, kBf16>(ra, c0, valid, mx, sum, sP, row);
+    tmem_ld_wait();
+    if (c0 + 32 < BKV) tmem_ld16(tS + c0 + 32, ra);
+    exp16<kMask, kBf16>(rb, c0 + 16, valid, mx, sum, sP, row);
+  }
+  return sum[0] + sum[1];
 }
 
 template <int HDP, int HD, int BKV>
@@ -161,7 +242,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
           mbar_wait(&k_empty[st], (i >> 1) & 1);
           load_k(i + 2);
         }
+        attn_trace(p, i, 8);
         mbar_wait(p_full, i & 1);     // P(i) in smem, S buffer st drained, O tile of PV(i-1) consumed
+        attn_trace(p, i, 9);
         mbar_wait(&v_full[st], (i >> 1) & 1);
         tc_fence_after();
         const uint32_t pa = smem_u32(sP), va = smem_u32(sKV + st * kStageBytes + kKBytes);
@@ -173,6 +256,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
         }
         umma_commit(o_full);
         umma_commit(&v_empty[st]);
+        attn_trace(p, i, 10);
         if (i + 2 < n_tiles) {
           issue_s(i + 2);
           mbar_wait(&v_empty[st], (i >> 1) & 1);
@@ -198,57 +282,39 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
       for (int e = 0; e < HD; ++e) acc[e] = 0.f;
       float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
       for (int j = 0; j < ntl; ++j, ++it) {
+        const bool tr = warp == 0 && lane == 0;
+        if (tr) attn_trace(p, it, 0);
         mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+        if (tr) attn_trace(p, it, 1);
         tc_fence_after();
         const uint32_t tS = tmem_S + (it & 1) * BKV + lane_base;
-        const int kv0 = j * BKV;
-        float mx = m;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BKV; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(tS + c0, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float v = (kv0 + c0 + e < kvlen) ? __uint_as_float(r[e]) : -INFINITY;
-            mx = fmaxf(mx, v);
-          }
-        }
+        const int valid = kvlen - j * BKV;        // >= BKV on every tile but the ragged last one of a segment
+        const bool full = valid >= BKV;
+        const float mx = full ? row_max_pass<BKV, false>(tS, m, valid) : row_max_pass<BKV, true>(tS, m, valid);
         const float alpha = ex2_approx(m - mx);
+        if (tr) attn_trace(p, it, 2);
         if (j > 0) {
           mbar_wait(o_full, (it - 1) & 1);
+          if (tr) attn_trace(p, it, 3);
           tc_fence_after();
           accumulate_o<HD>(tmem_O + lane_base, acc, alpha_prev);
         }
-        float rowsum = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BKV; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(tS + c0, r);
-          tmem_ld_wait();
-          uint32_t pk[8];
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            const float p0 = (kv0 + c0 + e < kvlen) ? ex2_approx(__uint_as_float(r[e]) - mx) : 0.f;
-            const float p1 = (kv0 + c0 + e + 1 < kvlen) ? ex2_approx(__uint_as_float(r[e + 1]) - mx) : 0.f;
-            rowsum += p0 + p1;
-            pk[e >> 1] = (p.dtype == MA3_BF16) ? pack_bf16(p0, p1) : pack_f16(p0, p1);
-          }
-          // 16 keys = 32 B = two 16-byte units of this row inside the 64-key chunk (128 B per row)
-          uint8_t* chunk = sP + (c0 >> 6) * (128 * 128) + row * 128;
-          const int u0 = (c0 & 63) >> 3;  // first 16-byte unit
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int pos = (u0 + u) ^ (row & 7);
-            *reinterpret_cast<uint4*>(chunk + pos * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-          }
-        }
+        if (tr) attn_trace(p, it, 4);
+        float rowsum;
+        if (p.dtype == MA3_BF16)
+          rowsum = full ? exp_store_pass<BKV, false, true>(tS, mx, valid, sP, row)
+                        : exp_store_pass<BKV, true, true>(tS, mx, valid, sP, row);
+        else
+          rowsum = full ? exp_store_pass<BKV, false, false>(tS, mx, valid, sP, row)
+                        : exp_store_pass<BKV, true, false>(tS, mx, valid, sP, row);
         l = l * alpha + rowsum;
         m = mx;
         alpha_prev = alpha;
+        if (tr) attn_trace(p, it, 5);
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(p_full);
+        if (tr) attn_trace(p, it, 6);
       }
       mbar_wait(o_full, (it - 1) & 1);
       tc_fence_after();
@@ -324,6 +390,7 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.T = T; p.L = L; p.H = H; p.D = H * hd; p.out = out; p.gate = gate; p.dtype = dtype;
+  p.trace = g_trace;
   const int BKV = 64;
   const uint64_t nbh = (uint64_t)NS * H;
   int rc;

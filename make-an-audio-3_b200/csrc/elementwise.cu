@@ -134,11 +134,12 @@ __global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(const float* __re
 // the Euler update x <- x + dt v applied (cfm1_audio.py:154-161 + torchdyn Euler), so no velocity round trip.
 constexpr int kMaxCout = 32;
 
+// One warp normalises a row (kept in registers) and takes its Cout dot products against W staged in shared memory.
 __device__ __forceinline__ void final_row(const float* __restrict__ hrow, const float* __restrict__ sc,
-                                          const float* __restrict__ sh, const float* __restrict__ W,
+                                          const float* __restrict__ sh, const float* __restrict__ sW,
                                           const float* __restrict__ bias, int D, int Cout, float eps, int lane,
                                           float& result) {
-  // returns in `result` the output channel `lane` (valid for lane < Cout); the normalised row lives in registers
+  // returns in `result` the output channel `lane` (valid for lane < Cout)
   constexpr int kMaxPerLane = 64;  // D <= 2048
   float xn[kMaxPerLane];
   float s = 0.f, s2 = 0.f;
@@ -160,12 +161,12 @@ __device__ __forceinline__ void final_row(const float* __restrict__ hrow, const 
   }
   float mine = 0.f;
   for (int c = 0; c < Cout; ++c) {
-    const float* wr = W + (long long)c * D;
+    const float* wr = sW + (long long)c * D;
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxPerLane; ++i) {
       const int j = i * 32 + lane;
-      if (j < D) acc += xn[i] * wr[j];
+      if (j < D) acc = fmaf(xn[i], wr[j], acc);
     }
     acc = warp_sum(acc);
     if (lane == c) mine = acc + bias[c];
@@ -181,32 +182,37 @@ __global__ void __launch_bounds__(256) final_layer_kernel(const float* __restric
                                                           float* __restrict__ v_out,  // [N or B, Cout, T] (nullable if kCfg)
                                                           const float* __restrict__ x_in, float* __restrict__ x_out,
                                                           float dt, float guidance) {
-  const int lane = threadIdx.x & 31;
-  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) float sW[];  // [Cout, D]: read once per block instead of once per row
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   pdl_launch_dependents();
   pdl_wait();
+  for (int i = threadIdx.x; i < (Cout * D) >> 2; i += blockDim.x)
+    reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(W)[i];
+  __syncthreads();
   if constexpr (!kCfg) {
-    if (wid >= N * T) return;
-    const int n = wid / T, t = wid - n * T;
-    float r;
-    final_row(h + (long long)wid * D, mod + (long long)n * mod_ld + scale_off, mod + (long long)n * mod_ld + shift_off,
-              W, bias, D, Cout, eps, lane, r);
-    if (lane < Cout) v_out[((long long)n * Cout + lane) * T + t] = r;
+    for (int wid = blockIdx.x * nwarp + warp; wid < N * T; wid += gridDim.x * nwarp) {
+      const int n = wid / T, t = wid - n * T;
+      float r;
+      final_row(h + (long long)wid * D, mod + (long long)n * mod_ld + scale_off, mod + (long long)n * mod_ld + shift_off,
+                sW, bias, D, Cout, eps, lane, r);
+      if (lane < Cout) v_out[((long long)n * Cout + lane) * T + t] = r;
+    }
   } else {
     const int B = N >> 1;
-    if (wid >= B * T) return;
-    const int b = wid / T, t = wid - b * T;
-    float ru, rc;
-    final_row(h + (long long)wid * D, mod + (long long)b * mod_ld + scale_off, mod + (long long)b * mod_ld + shift_off,
-              W, bias, D, Cout, eps, lane, ru);
-    const int nc = b + B;
-    final_row(h + ((long long)nc * T + t) * D, mod + (long long)nc * mod_ld + scale_off,
-              mod + (long long)nc * mod_ld + shift_off, W, bias, D, Cout, eps, lane, rc);
-    if (lane < Cout) {
-      const float vg = ru + guidance * (rc - ru);
-      const long long idx = ((long long)b * Cout + lane) * T + t;
-      if (v_out) v_out[idx] = vg;
-      if (x_out) x_out[idx] = x_in[idx] + dt * vg;
+    for (int wid = blockIdx.x * nwarp + warp; wid < B * T; wid += gridDim.x * nwarp) {
+      const int b = wid / T, t = wid - b * T;
+      float ru, rc;
+      final_row(h + (long long)wid * D, mod + (long long)b * mod_ld + scale_off, mod + (long long)b * mod_ld + shift_off,
+                sW, bias, D, Cout, eps, lane, ru);
+      const int nc = b + B;
+      final_row(h + ((long long)nc * T + t) * D, mod + (long long)nc * mod_ld + scale_off,
+                mod + (long long)nc * mod_ld + shift_off, sW, bias, D, Cout, eps, lane, rc);
+      if (lane < Cout) {
+        const float vg = ru + guidance * (rc - ru);
+        const long long idx = ((long long)b * Cout + lane) * T + t;
+        if (v_out) v_out[idx] = vg;
+        if (x_out) x_out[idx] = x_in[idx] + dt * vg;
+      }
     }
   }
 }
@@ -227,23 +233,29 @@ __global__ void cfg_euler_kernel(const float* __restrict__ v, const float* __res
 }
 
 // ---------------------------------------------------------------------------------------- proj_in
-// h[n*T + t, d] = sum_c x[n, c, t] * W[d, c] + b[d]      (flag_large_dit.py:186-187); x row n % x_batch (CFG halves
+// h[n*T + t, d] = sum_c x[n, c, t] * Wt[c, d] + b[d]     (flag_large_dit.py:186-187); x row n % x_batch (CFG halves
 // share x).
-__global__ void proj_in_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
-                               float* __restrict__ h, int N, int xB, int C, int T, int D) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(512) proj_in_kernel(const float* __restrict__ x, const float* __restrict__ Wt,
+                                                      const float* __restrict__ b, float* __restrict__ h, int N, int xB,
+                                                      int C, int T, int D) {
+  // one block per output row; Wt is the transposed weight [C, D] so every thread streams contiguous float4
+  __shared__ float sx[64];
   pdl_launch_dependents();
   pdl_wait();
-  if (i >= (long long)N * T * D) return;
-  const int d = (int)(i % D);
-  const long long row = i / D;
-  const int t = (int)(row % T);
-  const int n = (int)(row / T) % xB;
-  const float* xr = x + (long long)n * C * T + t;
-  const float* wr = W + (long long)d * C;
-  float acc = b[d];
-  for (int c = 0; c < C; ++c) acc += xr[(long long)c * T] * wr[c];
-  h[i] = acc;
+  const int row = blockIdx.x;
+  const int t = row % T, n = (row / T) % xB;
+  if (threadIdx.x < C) sx[threadIdx.x] = x[((long long)n * C + threadIdx.x) * T + t];
+  __syncthreads();
+  const int nvec = D >> 2;
+  for (int j = threadIdx.x; j < nvec; j += blockDim.x) {
+    float4 acc = reinterpret_cast<const float4*>(b)[j];
+    for (int c = 0; c < C; ++c) {
+      const float4 w = reinterpret_cast<const float4*>(Wt + (long long)c * D)[j];
+      const float xv = sx[c];
+      acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y); acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
+    }
+    reinterpret_cast<float4*>(h + (long long)row * D)[j] = acc;
+  }
 }
 
 // ---------------------------------------------------------------------------------------- timestep embedding
@@ -455,7 +467,18 @@ int ma3_final_layer(const float* h, const float* mod, int64_t mod_ld, int shift_
                     const float* bias, int N, int T, int D, int Cout, float eps, float* v_out, void* stream) {
   MA3_REQUIRE(h && mod && W && bias && v_out, "final_layer: null pointer");
   MA3_REQUIRE(Cout <= kMaxCout && N > 0 && T > 0 && D <= 2048, "final_layer: Cout=%d must be <= 32, D <= 2048", Cout);
-  launch_pdl(final_layer_kernel<false>, dim3(nblk((long long)N * T, 8)), dim3(256), 0, ST(stream), 1, h, mod,
+  MA3_REQUIRE((Cout * D) % 4 == 0 && aligned16(W), "final_layer: W must be 16-byte aligned");
+  const size_t smem = (size_t)Cout * D * sizeof(float);
+  {
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(final_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      configured = true;
+    }
+  }
+  MA3_REQUIRE(smem <= 200 * 1024, "final_layer: Cout * D too large for shared memory");
+  const unsigned fgrid = (unsigned)min((long long)num_sms(), ((long long)N * T + 7) / 8);
+  launch_pdl(final_layer_kernel<false>, dim3(fgrid), dim3(256), smem, ST(stream), 1, h, mod,
              (long long)mod_ld, shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, (const float*)nullptr,
              (float*)nullptr, 0.f, 0.f);
   MA3_LAUNCH_CHECK("final_layer");
@@ -468,7 +491,18 @@ int ma3_final_layer_cfg_euler(const float* h, const float* mod, int64_t mod_ld, 
                               void* stream) {
   MA3_REQUIRE(h && mod && W && bias && x_in && x_out, "final_layer_cfg_euler: null pointer");
   MA3_REQUIRE(Cout <= kMaxCout && N > 0 && N % 2 == 0 && T > 0 && D <= 2048, "final_layer_cfg_euler: N must be even, Cout <= 32, D <= 2048");
-  launch_pdl(final_layer_kernel<true>, dim3(nblk((long long)(N / 2) * T, 8)), dim3(256), 0, ST(stream), 1, h, mod,
+  MA3_REQUIRE((Cout * D) % 4 == 0 && aligned16(W), "final_layer_cfg_euler: W must be 16-byte aligned");
+  const size_t smem = (size_t)Cout * D * sizeof(float);
+  {
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(final_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      configured = true;
+    }
+  }
+  MA3_REQUIRE(smem <= 200 * 1024, "final_layer_cfg_euler: Cout * D too large for shared memory");
+  const unsigned fgrid = (unsigned)min((long long)num_sms(), ((long long)(N / 2) * T + 7) / 8);
+  launch_pdl(final_layer_kernel<true>, dim3(fgrid), dim3(256), smem, ST(stream), 1, h, mod,
              (long long)mod_ld, shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, x_in, x_out, dt, guidance);
   MA3_LAUNCH_CHECK("final_layer_cfg_euler");
   return 0;
@@ -485,8 +519,11 @@ int ma3_cfg_euler_update(const float* v, const float* x, float* out, int64_t ele
 int ma3_proj_in(const float* x, const float* W, const float* b, float* h, int N, int x_batch, int C, int T, int D,
                 void* stream) {
   MA3_REQUIRE(x && W && b && h && N > 0 && x_batch > 0, "proj_in: null pointer or empty");
-  launch_pdl(proj_in_kernel, dim3(nblk((long long)N * T * D, 256)), dim3(256), 0, ST(stream), 1, x, W, b, h, N, x_batch, C,
-             T, D);
+  MA3_REQUIRE(C <= 64 && D % 4 == 0 && aligned16(W) && aligned16(b) && aligned16(h), "proj_in: C <= 64, D %% 4 == 0, aligned");
+  int threads = ((D / 4 + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  if (threads < 64) threads = 64;
+  launch_pdl(proj_in_kernel, dim3((unsigned)(N * T)), dim3(threads), 0, ST(stream), 1, x, W, b, h, N, x_batch, C, T, D);
   MA3_LAUNCH_CHECK("proj_in");
   return 0;
 }

@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
+  if (threadIdx.x == 0) trace_evt(p, 15, 0);   // kernel entry
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA);
@@ -440,6 +441,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (threadIdx.x == 0) trace_evt(p, 15, 1);   // setup done
 
   // work items: CG = 1 -> 128-row tiles over all CTAs; CG = 2 -> 256-row tiles over CTA pairs
   const int total_tiles = p.tiles_m * p.tiles_n * p.batch;
@@ -563,14 +565,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all();
   else __syncthreads();
+  if (threadIdx.x == 0) trace_evt(p, 15, 2);   // all roles done
   if (warp == 1) {
     __syncwarp();
     if constexpr (CG == 2) tmem_dealloc2(tmem_base, p.tmem_cols);
     else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
-
-static long long* g_trace = nullptr;
 
 static uint32_t pow2_cols(int n) {
   uint32_t c = 32;

@@ -10,6 +10,7 @@ namespace ma3 {
 
 std::atomic<int64_t> g_launches{0};
 thread_local char g_err[512] = {0};
+long long* g_trace = nullptr;
 
 bool pdl_enabled() {
   static int v = -1;

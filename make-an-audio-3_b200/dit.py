@@ -194,7 +194,7 @@ class TxtFlagLargeDiT(nn.Module):
         b16 = lambda t: t.detach().to(device=dev, dtype=bf).contiguous()
         il = lambda w1, w3: torch.stack([w1.detach(), w3.detach()], 1).reshape(2 * w1.shape[0], w1.shape[1])
         p = {}
-        p["proj_w"], p["proj_b"] = f32(self.proj_in.weight), f32(self.proj_in.bias)
+        p["proj_w"], p["proj_b"] = f32(self.proj_in.weight.detach().t()), f32(self.proj_in.bias)  # [C, D]
         m = self.t_embedder.mlp
         p["t_w1"], p["t_b1"] = b16(getattr(m, "0").weight), f32(getattr(m, "0").bias)
         p["t_w2"], p["t_b2"] = b16(getattr(m, "2").weight), f32(getattr(m, "2").bias)

@@ -162,9 +162,10 @@ def cfg_euler_update(v, x, out, dt, guidance, cfg=True):
     return out
 
 
-def proj_in(x, W, b, h, N):
+def proj_in(x, Wt, b, h, N):
+    """h = x^T Wt + b with Wt the transposed nn.Linear weight [C, D]."""
     xB, Cc, T = x.shape
-    _call("ma3_proj_in", L.ptr(x), L.ptr(W), L.ptr(b), L.ptr(h), N, xB, Cc, T, W.shape[0])
+    _call("ma3_proj_in", L.ptr(x), L.ptr(Wt), L.ptr(b), L.ptr(h), N, xB, Cc, T, Wt.shape[1])
     return h
 
 

@@ -208,7 +208,7 @@ def test_proj_in_timestep_pool(ops):
     W = torch.randn(D, Cc, generator=g(39))
     b = torch.randn(D, generator=g(40))
     h = torch.empty(N * T, D, device="cuda")
-    ops.proj_in(x.cuda(), W.cuda(), b.cuda(), h, N)
+    ops.proj_in(x.cuda(), W.t().contiguous().cuda(), b.cuda(), h, N)
     ref = (x.transpose(1, 2) @ W.t() + b).repeat(2, 1, 1).view(N * T, D)
     assert rel(h, ref) < 1e-5
     t = torch.tensor([0, 41, 500, 958, 999])

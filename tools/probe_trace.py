@@ -7,7 +7,7 @@ lib = L.require_device()
 lib.ma3_debug_set_gemm_trace.argtypes = [ctypes.c_void_p]
 dev = "cuda"; bf = torch.bfloat16
 M, N = 4992, 6144
-for K, tn in ((64, 256), (1152, 256)):
+for K, tn, N in ((1152, 192, 3456), (1152, 256, 6144), (1152, 192, 1152), (3072, 192, 1152)):
     a = torch.randn(M, K, device=dev).to(bf); b = (torch.randn(N, K, device=dev) / K ** .5).to(bf)
     out = torch.empty(M, N, device=dev, dtype=bf)
     ops.gemm(a, b, M=M, N=N, K=K, out=out, tile_n=tn, cta_group=1); torch.cuda.synchronize()
@@ -17,6 +17,10 @@ for K, tn in ((64, 256), (1152, 256)):
     lib.ma3_debug_set_gemm_trace(ctypes.c_void_p(0))
     t = tr.cpu().view(16, 16)
     base = int(t[0, 0])
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record(); ops.gemm(a, b, M=M, N=N, K=K, out=out, tile_n=tn, cta_group=1); e1.record(); torch.cuda.synchronize()
+    ent, setup, done = int(t[15, 0]) - base, int(t[15, 1]) - base, int(t[15, 2]) - base
+    print(f"N={N} K={K}: event time {e0.elapsed_time(e1)*1e3:.1f} us; CTA0 entry {ent} setup_done {setup} all_done {done} clocks ({(done-ent)/1.9e3:.1f} us @1.9GHz)")
     print(f"K={K} tile_n={tn}: clocks relative to first event; per tile: mma[wait_tempty, start, issued] epi[ready, tfull, done]")
     for i in range(8):
         r = [int(v) - base if int(v) else -1 for v in t[i, :11]]
