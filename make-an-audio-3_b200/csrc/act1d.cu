@@ -21,19 +21,38 @@ namespace ma3 {
 __constant__ float c_fdn[12];  // f
 __constant__ float c_fup[12];  // 2 f
 
-constexpr int kTT = 16;
+#ifndef MA3_ACT_TT
+#define MA3_ACT_TT 16
+#endif
+#ifndef MA3_ACT_MINBLOCKS
+#define MA3_ACT_MINBLOCKS 1
+#endif
+constexpr int kTT = MA3_ACT_TT;       // outputs per thread (window of kTT + 10 inputs lives in registers)
 constexpr int kActThreads = 256;
 
+// Shared-memory loads of a channel pair.  `asm volatile` on purpose: it pins the 26-entry input window in registers;
+// left to itself ptxas prefers to re-load (and re-convert) every tap operand from shared memory, which made the kernel
+// instruction-bound at ~59 instructions per element.
 template <typename T> struct Ld2;
 template <> struct Ld2<float> {
-  static __device__ __forceinline__ float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+  static __device__ __forceinline__ float2 ld(const float* p) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem_u32(p)));
+    return v;
+  }
 };
 template <> struct Ld2<__half> {
-  static __device__ __forceinline__ float2 ld(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+  static __device__ __forceinline__ float2 ld(const __half* p) {
+    uint32_t u;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(smem_u32(p)));
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  }
 };
 template <> struct Ld2<__nv_bfloat16> {
   static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) {
-    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+    uint32_t u;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(smem_u32(p)));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
   }
 };
 template <typename T> struct St2;
@@ -54,135 +73,190 @@ __device__ __forceinline__ float snake1(float u, float a, float inv_b) {
   return fmaf(inv_b * sn, sn, u);
 }
 
-// activated 2x-rate sample with local index n (m = 2*t0 - 5 + n) from the thread's window xw[0 .. kTT+9]
+// two channels at once: s = u + inv_b * sin^2(a u), packed fp32x2 arithmetic around the two MUFU.SIN
+__device__ __forceinline__ float2 snake2(float2 u, float2 a, float2 ib) {
+  const float2 arg = fmul2(u, a);
+  const float2 sn = make_float2(__sinf(arg.x), __sinf(arg.y));
+  return ffma2(fmul2(ib, sn), sn, u);
+}
+
+// activated 2x-rate sample with local index n (m = 2*t0 - 5 + n) from the thread's window xw[0 .. kTT+9];
+// 6-tap polyphase branch as packed FFMA2 (one instruction per tap for both channels)
 template <int n>
 __device__ __forceinline__ float2 s_local(const float2 (&xw)[kTT + 10], float2 a, float2 ib) {
   float2 u = make_float2(0.f, 0.f);
   if constexpr (n & 1) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      u.x = fmaf(c_fup[11 - 2 * k], xw[(n - 1) / 2 + k].x, u.x);
-      u.y = fmaf(c_fup[11 - 2 * k], xw[(n - 1) / 2 + k].y, u.y);
-    }
+    for (int k = 0; k < 6; ++k) u = ffma2(make_float2(c_fup[11 - 2 * k], c_fup[11 - 2 * k]), xw[(n - 1) / 2 + k], u);
   } else {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      u.x = fmaf(c_fup[10 - 2 * k], xw[n / 2 + k].x, u.x);
-      u.y = fmaf(c_fup[10 - 2 * k], xw[n / 2 + k].y, u.y);
-    }
+    for (int k = 0; k < 6; ++k) u = ffma2(make_float2(c_fup[10 - 2 * k], c_fup[10 - 2 * k]), xw[n / 2 + k], u);
   }
-  return make_float2(snake1(u.x, a.x, ib.x), snake1(u.y, a.y, ib.y));
+  return snake2(u, a, ib);
 }
 
-template <int i, typename TOut>
+// Sequence edges: the reference replicate-pads the ACTIVATED 2x-rate signal, i.e. local indices below n_lo / above
+// n_hi take the value at n_lo / n_hi.  kEdge threads (first / last time group of a sequence) run the same unrolled
+// code with two selects per sample instead of a slow generic path (which used to form the kernel's tail).
+struct EdgeCtx {
+  int n_lo, n_hi;
+  float2 s_lo, s_hi;
+};
+
+template <int n, bool kEdge>
+__device__ __forceinline__ float2 s_val(const float2 (&xw)[kTT + 10], float2 a, float2 ib, const EdgeCtx& ec) {
+  float2 v = s_local<n>(xw, a, ib);
+  if constexpr (kEdge) {
+    if (n < ec.n_lo) v = ec.s_lo;
+    else if (n > ec.n_hi) v = ec.s_hi;
+  }
+  return v;
+}
+
+template <int i, bool kEdge, typename TOut>
 __device__ __forceinline__ void slide(const float2 (&xw)[kTT + 10], float2 (&S)[12], float2 a, float2 ib, TOut* orow,
-                                      long long ostride, int valid) {
+                                      long long ostride, int valid, const EdgeCtx& ec) {
   if constexpr (i < kTT) {
-    float2 acc = make_float2(0.f, 0.f);
+    // the low-pass is symmetric (f[j] = f[11-j]): two independent 6-term FFMA2 chains
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 12; ++j) {
-      acc.x = fmaf(c_fdn[j], S[j].x, acc.x);
-      acc.y = fmaf(c_fdn[j], S[j].y, acc.y);
+    for (int j = 0; j < 6; ++j) {
+      acc0 = ffma2(make_float2(c_fdn[j], c_fdn[j]), S[j], acc0);
+      acc1 = ffma2(make_float2(c_fdn[11 - j], c_fdn[11 - j]), S[11 - j], acc1);
     }
+    const float2 acc = make_float2(acc0.x + acc1.x, acc0.y + acc1.y);
     if (i < valid) St2<TOut>::st(orow + (long long)i * ostride, acc);
     if constexpr (i + 1 < kTT) {
 #pragma unroll
       for (int j = 0; j < 10; ++j) S[j] = S[j + 2];
-      S[10] = s_local<2 * i + 12>(xw, a, ib);
-      S[11] = s_local<2 * i + 13>(xw, a, ib);
-      slide<i + 1>(xw, S, a, ib, orow, ostride, valid);
+      S[10] = s_val<2 * i + 12, kEdge>(xw, a, ib, ec);
+      S[11] = s_val<2 * i + 13, kEdge>(xw, a, ib, ec);
+      slide<i + 1, kEdge, TOut>(xw, S, a, ib, orow, ostride, valid, ec);
     }
   }
 }
 
-template <int n>
-__device__ __forceinline__ void fill_window(const float2 (&xw)[kTT + 10], float2 (&S)[12], float2 a, float2 ib) {
+template <int n, bool kEdge>
+__device__ __forceinline__ void fill_window(const float2 (&xw)[kTT + 10], float2 (&S)[12], float2 a, float2 ib,
+                                            const EdgeCtx& ec) {
   if constexpr (n < 12) {
-    S[n] = s_local<n>(xw, a, ib);
-    fill_window<n + 1>(xw, S, a, ib);
+    S[n] = s_val<n, kEdge>(xw, a, ib, ec);
+    fill_window<n + 1, kEdge>(xw, S, a, ib, ec);
   }
 }
 
-// sequence-edge threads: the 2x-rate index is clamped (replicate padding of the activated signal)
-template <typename TIn, typename TOut>
-__device__ __noinline__ void edge_path(const TIn* srow, int CT, float2 a, float2 ib, TOut* orow, long long ostride,
-                                       int valid, int n_lo, int n_hi) {
-  for (int i = 0; i < valid; ++i) {
-    float2 acc = make_float2(0.f, 0.f);
-    for (int j = 0; j < 12; ++j) {
-      int n = 2 * i + j;
-      n = n < n_lo ? n_lo : (n > n_hi ? n_hi : n);
-      const int base = (n & 1) ? (n - 1) / 2 : n / 2;
-      const int f0 = (n & 1) ? 11 : 10;
-      float2 u = make_float2(0.f, 0.f);
-      for (int k = 0; k < 6; ++k) {
-        const float2 xv = Ld2<TIn>::ld(srow + (long long)(base + k) * CT);
-        u.x = fmaf(c_fup[f0 - 2 * k], xv.x, u.x);
-        u.y = fmaf(c_fup[f0 - 2 * k], xv.y, u.y);
-      }
-      acc.x = fmaf(c_fdn[j], snake1(u.x, a.x, ib.x), acc.x);
-      acc.y = fmaf(c_fdn[j], snake1(u.y, a.y, ib.y), acc.y);
-    }
-    St2<TOut>::st(orow + (long long)i * ostride, acc);
+// activated sample at a RUN-TIME local index (only the two clamp targets of an edge thread), straight from the tile
+template <typename TIn>
+__device__ __forceinline__ float2 s_at(const TIn* srow, int CT, int n, float2 a, float2 ib) {
+  const int base = (n & 1) ? (n - 1) / 2 : n / 2;
+  const int f0 = (n & 1) ? 11 : 10;
+  float2 u = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float2 xv = Ld2<TIn>::ld(srow + (long long)(base + k) * CT);
+    const float c = c_fup[f0 - 2 * k];
+    u = ffma2(make_float2(c, c), xv, u);
   }
+  return snake2(u, a, ib);
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent blocks loop over (batch, time tile, channel tile) work items; the next item's (TB + 10) x CT input tile
+// is fetched with cp.async into the other shared-memory buffer while the current one is being computed, so the
+// HBM latency of the loads is never exposed (the one-tile-per-block version spent its time waiting on them).
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(kActThreads) act1d_kernel(const TIn* __restrict__ x, TOut* __restrict__ out,
+__global__ void __launch_bounds__(kActThreads, MA3_ACT_MINBLOCKS) act1d_kernel(const TIn* __restrict__ x, TOut* __restrict__ out,
                                                             const float* __restrict__ alpha,
-                                                            const float* __restrict__ beta, int T, int C, int CT,
-                                                            int tiles_c, int logscale) {
+                                                            const float* __restrict__ beta, int B, int T, int C, int CT,
+                                                            int tiles_c, int tiles_t, int logscale) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  TIn* tile = reinterpret_cast<TIn*>(smem_raw);
   pdl_launch_dependents();
   pdl_wait();
   const int CP = CT >> 1;                 // channel pairs per tile
   const int groups = kActThreads / CP;    // time groups per block
   const int TB = groups * kTT;
-  const int tile_c = blockIdx.x % tiles_c, tile_t = blockIdx.x / tiles_c;
-  const int b = blockIdx.y;
-  const int c0 = tile_c * CT, tb0 = tile_t * TB;
-  const TIn* xb = x + (long long)b * T * C;
-
-  // stage (TB + 10) x CT with 16-byte vectors; row index clamped to [0, T-1]
+  const int rows = TB + 10;
   constexpr int kVecElems = 16 / sizeof(TIn);
   const int vpr = CT / kVecElems;
-  const int rows = TB + 10;
-  for (int idx = threadIdx.x; idx < rows * vpr; idx += kActThreads) {
-    const int r = idx / vpr, v = idx - r * vpr;
-    int gr = tb0 - 5 + r;
-    gr = gr < 0 ? 0 : (gr > T - 1 ? T - 1 : gr);
-    const uint4 val = *reinterpret_cast<const uint4*>(xb + (long long)gr * C + c0 + v * kVecElems);
-    *reinterpret_cast<uint4*>(tile + (long long)r * CT + v * kVecElems) = val;
-  }
-  __syncthreads();
-
+  const size_t buf_bytes = (size_t)rows * CT * sizeof(TIn);
+  const int total = tiles_c * tiles_t * B;
   const int cp = threadIdx.x % CP, tg = threadIdx.x / CP;
-  const int t0 = tb0 + tg * kTT;
-  if (t0 >= T) return;
-  const int c = c0 + 2 * cp;
-  float2 a = make_float2(alpha[c], alpha[c + 1]);
-  float2 bb = beta ? make_float2(beta[c], beta[c + 1]) : a;
-  if (logscale) {
-    a = make_float2(__expf(a.x), __expf(a.y));
-    bb = make_float2(__expf(bb.x), __expf(bb.y));
-  }
-  const float2 ib = make_float2(1.f / (bb.x + 1e-9f), 1.f / (bb.y + 1e-9f));
-  const TIn* srow = tile + (long long)(tg * kTT) * CT + 2 * cp;  // window row 0 <-> x[t0 - 5]
-  TOut* orow = out + ((long long)b * T + t0) * C + c;
-  const int valid = min(kTT, T - t0);
-  const int n_lo = max(0, 5 - 2 * t0);
-  const int n_hi = min(2 * kTT + 9, 2 * (T - t0) + 4);
-  if (n_lo > 0 || n_hi < 2 * kTT + 9) {
-    edge_path<TIn, TOut>(srow, CT, a, ib, orow, C, valid, n_lo, n_hi);
-    return;
-  }
-  float2 xw[kTT + 10];
+
+  auto decode = [&](int item, int& b, int& tb0, int& c0) {
+    const int tile_c = item % tiles_c;
+    const int rest = item / tiles_c;
+    c0 = tile_c * CT;
+    tb0 = (rest % tiles_t) * TB;
+    b = rest / tiles_t;
+  };
+  // stage (TB + 10) x CT with 16-byte async copies; row index clamped to [0, T-1] (= replicate padding of x)
+  auto prefetch = [&](int item, int buf) {
+    int b, tb0, c0;
+    decode(item, b, tb0, c0);
+    const TIn* xb = x + (long long)b * T * C;
+    TIn* tile = reinterpret_cast<TIn*>(smem_raw + buf * buf_bytes);
+    for (int idx = threadIdx.x; idx < rows * vpr; idx += kActThreads) {
+      const int r = idx / vpr, v = idx - r * vpr;
+      int gr = tb0 - 5 + r;
+      gr = gr < 0 ? 0 : (gr > T - 1 ? T - 1 : gr);
+      cp_async16(tile + (long long)r * CT + v * kVecElems, xb + (long long)gr * C + c0 + v * kVecElems);
+    }
+  };
+
+  int it = 0;
+  if ((int)blockIdx.x < total) prefetch(blockIdx.x, 0);
+  cp_async_commit();
+  for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = item + gridDim.x;
+    if (next < total) prefetch(next, buf ^ 1);
+    cp_async_commit();
+    int b, tb0, c0;
+    decode(item, b, tb0, c0);
+    // per-channel Snake parameters: issued before waiting on the tile so their latency overlaps too
+    const int c = c0 + 2 * cp;
+    float2 a = make_float2(alpha[c], alpha[c + 1]);
+    float2 bb = beta ? make_float2(beta[c], beta[c + 1]) : a;
+    cp_async_wait<1>();
+    __syncthreads();
+    const TIn* tile = reinterpret_cast<const TIn*>(smem_raw + buf * buf_bytes);
+    const int t0 = tb0 + tg * kTT;
+    if (t0 < T) {
+      if (logscale) {
+        a = make_float2(__expf(a.x), __expf(a.y));
+        bb = make_float2(__expf(bb.x), __expf(bb.y));
+      }
+      const float2 ib = make_float2(1.f / (bb.x + 1e-9f), 1.f / (bb.y + 1e-9f));
+      const TIn* srow = tile + (long long)(tg * kTT) * CT + 2 * cp;  // window row 0 <-> x[t0 - 5]
+      TOut* orow = out + ((long long)b * T + t0) * C + c;
+      const int valid = min(kTT, T - t0);
+      const int n_lo = max(0, 5 - 2 * t0);
+      const int n_hi = min(2 * kTT + 9, 2 * (T - t0) + 4);
+      float2 xw[kTT + 10];
 #pragma unroll
-  for (int j = 0; j < kTT + 10; ++j) xw[j] = Ld2<TIn>::ld(srow + (long long)j * CT);
-  float2 S[12];
-  fill_window<0>(xw, S, a, ib);
-  slide<0, TOut>(xw, S, a, ib, orow, C, valid);
+      for (int j = 0; j < kTT + 10; ++j) xw[j] = Ld2<TIn>::ld(srow + (long long)j * CT);
+      float2 S[12];
+      EdgeCtx ec;
+      ec.n_lo = n_lo;
+      ec.n_hi = n_hi;
+      if (n_lo > 0 || n_hi < 2 * kTT + 9) {
+        ec.s_lo = s_at<TIn>(srow, CT, n_lo, a, ib);
+        ec.s_hi = s_at<TIn>(srow, CT, n_hi, a, ib);
+        fill_window<0, true>(xw, S, a, ib, ec);
+        slide<0, true, TOut>(xw, S, a, ib, orow, C, valid, ec);
+      } else {
+        fill_window<0, false>(xw, S, a, ib, ec);
+        slide<0, false, TOut>(xw, S, a, ib, orow, C, valid, ec);
+      }
+    }
+    __syncthreads();   // everyone is done with `buf` before the prefetch two items ahead overwrites it
+  }
 }
 
 static bool g_filter_set = false;
@@ -220,12 +294,24 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
   const int groups = kActThreads / (CT / 2);
   const int TB = groups * kTT;
   const int tiles_c = C / CT, tiles_t = (T + TB - 1) / TB;
-  dim3 grid((unsigned)(tiles_c * tiles_t), (unsigned)B);
-  const size_t smem = (size_t)(TB + 10) * CT * dtype_bytes(in_dtype);
+  const long long total = (long long)tiles_c * tiles_t * B;
+  const size_t smem = 2 * (size_t)(TB + 10) * CT * dtype_bytes(in_dtype);   // double-buffered input tile
+  // persistent grid: two blocks per SM (registers) when there is enough work
+  long long gridl = (long long)(MA3_ACT_MINBLOCKS > 2 ? MA3_ACT_MINBLOCKS : 2) * num_sms();
+  if (gridl > total) gridl = total;
+  dim3 grid((unsigned)gridl);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t le = cudaSuccess;
-#define ACT_CASE(TI, TO) \
-  le = launch_pdl(act1d_kernel<TI, TO>, grid, dim3(kActThreads), smem, st, 1, (const TI*)x, (TO*)out, alpha, beta, T, C, CT, tiles_c, logscale)
+#define ACT_CASE(TI, TO)                                                                                            \
+  do {                                                                                                              \
+    static bool configured = false;                                                                                 \
+    if (!configured) {                                                                                              \
+      cudaFuncSetAttribute(act1d_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);          \
+      configured = true;                                                                                            \
+    }                                                                                                               \
+    le = launch_pdl(act1d_kernel<TI, TO>, grid, dim3(kActThreads), smem, st, 1, (const TI*)x, (TO*)out, alpha, beta, \
+                    B, T, C, CT, tiles_c, tiles_t, logscale);                                                       \
+  } while (0)
   if (in_dtype == MA3_F16 && out_dtype == MA3_F16) ACT_CASE(__half, __half);
   else if (in_dtype == MA3_F32 && out_dtype == MA3_F16) ACT_CASE(float, __half);
   else if (in_dtype == MA3_BF16 && out_dtype == MA3_BF16) ACT_CASE(__nv_bfloat16, __nv_bfloat16);

@@ -215,6 +215,20 @@ __host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int fmt) {
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- packed fp32x2 math (Blackwell FFMA2 / FMUL2)
+__device__ __forceinline__ unsigned long long f2_as_u64(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ float2 u64_as_f2(unsigned long long v) { return *reinterpret_cast<float2*>(&v); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)), "l"(f2_as_u64(c)));
+  return u64_as_f2(d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+  return u64_as_f2(d);
+}
+
 // ---------------------------------------------------------------- misc math
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libma3b200.so")
+# MA3_LIB overrides the library path (used by tools/ to A/B kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("MA3_LIB") or os.path.join(_HERE, "csrc", "libma3b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 EPI_STORE, EPI_GATE_RES, EPI_SWIGLU, EPI_QKV_ROPE = 0, 1, 2, 3

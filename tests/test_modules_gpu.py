@@ -67,6 +67,43 @@ def test_dit_velocity_full_width(model, depth):
         assert O.max_rel_err(vo, vr) < 1e-2, (model, t_int)
 
 
+def test_dit_moe_full_width():
+    """Config 5 (video2audio-cfm-cfg-moe): M width, 4 time + 4 frequency experts, T=256, 40 video-feature tokens;
+    same timestep for the CFG pair (sampling) and different experts per sample (general forward())."""
+    from ma3_b200.pipeline import MODEL_CONFIGS
+    cfg = dict(MODEL_CONFIGS["MOE"], depth=2)
+    cfg.pop("max_len")
+    ne = cfg.pop("num_experts")
+    sd = W.dit_state_dict(**cfg, video=True, num_experts=ne, seed=6)
+    m = _dit(cfg, sd, video=True, num_experts=ne)
+    g = Cs.gen(61)
+    x = torch.randn(2, 20, 256, generator=g)
+    ctx = torch.randn(2, 40, 768, generator=g)
+    for t in (torch.tensor([583, 583]), torch.tensor([125, 958])):
+        ref = O.dit_forward(sd, x, t, ctx, heads=cfg["num_heads"], video=True, num_experts=ne)
+        out = m(x.cuda(), t.cuda(), context=ctx.cuda()).cpu()
+        assert O.max_rel_err(out, ref) < 1e-2, t.tolist()
+
+
+def test_dit_long_context_and_music_lengths():
+    """Config 3 (30 s clips: T = 936 latent frames, XXL width) and config 4 (music: 77 context tokens)."""
+    from ma3_b200.pipeline import MODEL_CONFIGS
+    for model, depth, T, L in (("XXL", 1, 936, 154), ("M", 2, 312, 77)):
+        cfg = dict(MODEL_CONFIGS[model], depth=depth)
+        cfg.pop("max_len")
+        sd = W.dit_state_dict(**cfg, seed=8)
+        m = _dit(cfg, sd)
+        g = Cs.gen(62)
+        x = torch.randn(2, 20, T, generator=g)
+        ctx = torch.randn(2, L, 1024, generator=g)
+        t = torch.tensor([333, 333])
+        ref = O.dit_forward(sd, x, t, ctx, heads=cfg["num_heads"])
+        out = m(x.cuda(), t.cuda(), context=ctx.cuda()).cpu()
+        assert O.max_rel_err(out, ref) < 1e-2, (model, T, L)
+    with pytest.raises(ValueError):
+        m(torch.randn(2, 20, 1001).cuda(), t.cuda(), context=ctx.cuda())   # beyond the RoPE table (max_len 1000)
+
+
 def test_sampler_golden(golden):
     from ma3_b200.sampler import CFMSampler
     sd = W.dit_state_dict(**Cs.DIT_TINY, seed=3)
