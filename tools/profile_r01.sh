@@ -3,11 +3,11 @@
 set -x
 CMD="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain.log; exit 1; }
-tail -c 600 gpurun_out/plain.log
-# (1) launch list of one full step (3 warm-up steps + 1 e2e warm-up skipped is not needed: skip the 3 warm-up steps)
-ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip-before-match 0 -s 15400 -c 5200 --csv \
+tail -c 400 gpurun_out/plain.log
+# (1) launch list of one full step: skip the launches of the 3 warm-up steps (5089 launches per step, eager)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 15300 -c 5100 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
-# (2) full-set captures of the top kernels
+# (2) full-set captures: the four DiT GEMMs of one block, attention, act1d, rmsnorm
 ncu --set full --clock-control none --import-source on -k regex:tap_gemm -s 400 -c 4 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:attn_kernel -s 30 -c 1 -o gpurun_out/prof_attn $CMD > gpurun_out/ncu_attn.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:act1d -s 40 -c 2 -o gpurun_out/prof_act1d $CMD > gpurun_out/ncu_act1d.log 2>&1
