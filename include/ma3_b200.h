@@ -107,12 +107,19 @@ typedef struct ma3_gemm {
   /* tiling overrides: 0 = library heuristic */
   int32_t tile_n;
   int32_t cta_group;      /* 1: one CTA per 128-row tile; 2: CTA pair (tcgen05 cta_group::2) per 256-row tile */
+  int32_t stream_k;       /* MA3_EPI_GATE_RES only.  0: library heuristic; 1: split the tiles x k-iterations space evenly
+                           * over the SMs (partial products are added by separate reductions: fp32 sums may differ in the
+                           * last bit from run to run); -1: whole tiles only (bit-reproducible) */
 } ma3_gemm_t;
 
 int ma3_gemm(const ma3_gemm_t* g, void* stream);
 /* diagnostics only: device buffer (>= 256 int64) that CTA 0 of later ma3_gemm launches fills with clock64() stamps of
  * its pipeline events; NULL switches tracing off (tools/probe_trace.py). */
 int ma3_debug_set_gemm_trace(void* buf);
+/* diagnostics only: 0 = normal; 1 = the producer signals stages full without issuing TMA loads; 2 = the MMA thread
+ * releases stages without issuing MMAs.  Isolates the feed side from the tensor side of the mainloop; the output of
+ * later ma3_gemm calls is garbage until mode 0 is restored (tools/probe_trace.py). */
+int ma3_debug_set_gemm_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused flash attention of one Next-DiT block: self-attention over the T latent tokens plus tanh-gated
@@ -122,6 +129,10 @@ int ma3_debug_set_gemm_trace(void* buf);
  * (flag_large_dit_moe.py:382-406).  q must already carry RoPE and the factor log2(e)/sqrt(hd) (MA3_EPI_QKV_ROPE).
  * Layouts (16-bit, `dtype`): q,k [NS*H, T, hdp]; vt [NS*H, hdp, Tp]; ky [NS*H, L, hdp]; vyt [NS*H, hdp, Lp];
  * gate [H] fp32 (raw parameter); out [NS, T, H*hd].  hdp in {64,128}; Tp, Lp multiples of 8.
+ * Pad columns [hd, hdp) of q, k, ky must be zero.  When hd < hdp, row hd of vt and of vyt must hold 1.0 for every
+ * token and rows (hd, hdp) zero: the P.V tensor-core product then also yields the softmax row sums (column hd of the
+ * accumulator), so the denominator is formed from exactly the rounded probabilities the MMA consumed.  The host side
+ * allocates such buffers once (ops.alloc_vt); MA3_EPI_QKV_ROPE only ever writes rows [0, hd).
  * ------------------------------------------------------------------------------------------------------------------ */
 int ma3_attention(const void* q, const void* k, const void* vt, const void* ky, const void* vyt, const float* gate,
                   void* out, int dtype, int NS, int H, int T, int Tp, int L, int Lp, int hd, int hdp, void* stream);

@@ -11,6 +11,8 @@
 #include "host_common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace ma3 {
 
 constexpr int kAttnThreads = 160;
@@ -356,6 +358,335 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ v2 kernel
+// Same contract and CTA shape as attn_kernel above, restructured to cut the softmax warps' instruction count ~3x
+// (they, not the tensor core, bound the kernel at these head dims):
+//  * S is read from TMEM once (64 registers per row) instead of once for the max and once for the exponentials;
+//  * O stays in TMEM and the PV MMAs accumulate into it.  The running maximum is only raised when a tile exceeds it
+//    by more than 2^8 (lazy rescaling: p <= 256 is harmless for bf16 P and the fp32 accumulator, and the result is
+//    exact because numerator and denominator share the stale reference); the rare correction multiplies O in place;
+//  * the softmax denominator is accumulated by the tensor core: V^T carries a row of ones at index HD, so column HD of
+//    O is sum_j p_ij of exactly the rounded probabilities the MMA consumed;
+//  * S = Q K^T only issues the ceil(HD/16) k-steps that carry data, and PV only N = HDO columns;
+//  * warps whose 32 query rows all lie beyond T (ragged last Q tile) do no work.
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+  return u64_as_f2(d);
+}
+
+// O[:, 0..HDO) *= alpha, in place in TMEM (thread <-> row)
+template <int HDO>
+__device__ __forceinline__ void rescale_o(uint32_t tO, float alpha) {
+#pragma unroll
+  for (int c = 0; c < HDO; c += 16) {
+    uint32_t r[16];
+    tmem_ld16(tO + c, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+    tmem_st16(tO + c, r);
+  }
+  tmem_st_wait();
+}
+
+// Segment epilogue over O columns [OFF, HD) in pieces of 16 / 8: kFinal = false parks O * f as packed bf16 pairs,
+// kFinal = true adds the parked self-attention result and writes the 16-bit output row.
+template <int HD, bool kFinal, int OFF = 0>
+__device__ __forceinline__ void drain_o(uint32_t tO, float f, uint32_t (&stash)[HD / 2], uint16_t* orow, bool bf16,
+                                        bool store) {
+  if constexpr (OFF < HD) {
+    constexpr int W = (HD - OFF >= 16) ? 16 : 8;
+    uint32_t r[W];
+    tmem_ld_n<W>(tO + OFF, r);
+    tmem_ld_wait();
+    if constexpr (!kFinal) {
+#pragma unroll
+      for (int e = 0; e < W; e += 2)
+        stash[(OFF + e) >> 1] = pack_bf16(__uint_as_float(r[e]) * f, __uint_as_float(r[e + 1]) * f);
+    } else {
+#pragma unroll
+      for (int e = 0; e < W; e += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const float2 sv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&stash[(OFF + e + i) >> 1]));
+          v[i] = fmaf(__uint_as_float(r[e + i]), f, sv.x);
+          v[i + 1] = fmaf(__uint_as_float(r[e + i + 1]), f, sv.y);
+        }
+        uint4 u;
+        if (bf16)
+          u = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        else
+          u = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
+        if (store) *reinterpret_cast<uint4*>(orow + OFF + e) = u;
+      }
+    }
+    drain_o<HD, kFinal, OFF + W>(tO, f, stash, orow, bf16, store);
+  }
+}
+
+template <int HDP, int HD, int BKV>
+__global__ void __launch_bounds__(kAttnThreads, 2) attn2_kernel(const __grid_constant__ AttnParams p) {
+  static_assert(BKV == 64, "one 64-key chunk per KV tile");
+  constexpr int HDC = HDP / 64;
+  constexpr int HDO = (HD + 1 + 15) / 16 * 16;   // O columns: HD values, the row-sum column, zero padding
+  constexpr int KS = (HD + 15) / 16;             // k-steps of S = Q K^T that carry data (pad columns are zero)
+  static_assert(HDO <= HDP, "needs a spare V^T row for the row sums");
+  constexpr uint32_t kQBytes = 128 * HDP * 2;
+  constexpr uint32_t kKBytes = BKV * HDP * 2;
+  constexpr uint32_t kStageBytes = 2 * kKBytes;
+  constexpr uint32_t kPBytes = 128 * BKV * 2;
+  constexpr uint32_t kTmemCols = 256;            // S0: [0, 64)  S1: [64, 128)  O: [128, 128 + HDO)
+  static_assert(2 * BKV + HDO <= 256, "TMEM budget");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sQ = smem_raw;
+  uint8_t* sKV = sQ + kQBytes;
+  uint8_t* sP = sKV + 2 * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;
+  uint64_t* p_full = bars + 11;
+  uint64_t* o_full = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, ns = blockIdx.z;
+  const int bh = ns * p.H + h;
+  const int n_self = (p.T + BKV - 1) / BKV, n_cross = (p.L + BKV - 1) / BKV;
+  const int n_tiles = n_self + n_cross;
+  const int n_active = min(4, (p.T - q0 + 31) / 32);   // softmax warps owning at least one query row < T
+
+  if (warp == 4) {
+    if (lane == 0) {
+      prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmVt);
+      prefetch_tmap(&p.tmKy); prefetch_tmap(&p.tmVyt);
+      mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+        mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+        mbar_init(&s_full[i], 1);
+      }
+      mbar_init(p_full, 32 * n_active);
+      mbar_init(o_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kTmemCols);
+  }
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * BKV;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      auto load_k = [&](int i) {
+        const int st = i & 1;
+        const bool cross = i >= n_self;
+        const int kv0 = (cross ? i - n_self : i) * BKV;
+        uint8_t* dK = sKV + st * kStageBytes;
+        mbar_arrive_expect_tx(&k_full[st], kKBytes);
+#pragma unroll
+        for (int c = 0; c < HDC; ++c)
+          tma_load_3d(dK + c * (BKV * 128), cross ? &p.tmKy : &p.tmK, &k_full[st], c * 64, kv0, bh);
+      };
+      auto load_v = [&](int i) {
+        const int st = i & 1;
+        const bool cross = i >= n_self;
+        const int kv0 = (cross ? i - n_self : i) * BKV;
+        uint8_t* dV = sKV + st * kStageBytes + kKBytes;
+        mbar_arrive_expect_tx(&v_full[st], kKBytes);
+        tma_load_3d(dV, cross ? &p.tmVyt : &p.tmVt, &v_full[st], kv0, 0, bh);
+      };
+      const uint32_t idesc_s = umma_idesc(128, BKV, p.dtype == MA3_BF16 ? 1 : 0);
+      const uint32_t idesc_o = umma_idesc(128, HDO, p.dtype == MA3_BF16 ? 1 : 0);
+      auto issue_s = [&](int i) {
+        const int st = i & 1;
+        mbar_wait(&k_full[st], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sKV + st * kStageBytes);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const uint64_t da = umma_desc_kmajor(qa + (k / 4) * (128 * 128) + (k % 4) * 32, 128);
+          const uint64_t db = umma_desc_kmajor(ka + (k / 4) * (BKV * 128) + (k % 4) * 32, 128);
+          umma_f16(tmem_S + st * BKV, da, db, idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[st]);
+        umma_commit(&k_empty[st]);
+      };
+
+      mbar_arrive_expect_tx(q_full, kQBytes);
+#pragma unroll
+      for (int c = 0; c < HDC; ++c) tma_load_3d(sQ + c * (128 * 128), &p.tmQ, q_full, c * 64, q0, bh);
+      load_k(0);
+      load_v(0);
+      if (n_tiles > 1) { load_k(1); load_v(1); }
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (n_tiles > 1) issue_s(1);
+      for (int i = 0; i < n_tiles; ++i) {
+        const int st = i & 1;
+        if (i + 2 < n_tiles) {
+          mbar_wait(&k_empty[st], (i >> 1) & 1);
+          load_k(i + 2);
+        }
+        attn_trace(p, i, 8);
+        mbar_wait(p_full, i & 1);     // P(i) in smem, S buffer st drained, O rescaled / consumed as needed
+        attn_trace(p, i, 9);
+        mbar_wait(&v_full[st], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP), va = smem_u32(sKV + st * kStageBytes + kKBytes);
+        const bool fresh = i == 0 || i == n_self;   // first tile of a segment overwrites O
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint64_t da = umma_desc_kmajor(pa + k * 32, 128);
+          const uint64_t db = umma_desc_kmajor(va + k * 32, 128);
+          umma_f16(tmem_O, da, db, idesc_o, (k != 0 || !fresh) ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&v_empty[st]);
+        attn_trace(p, i, 10);
+        if (i + 2 < n_tiles) {
+          issue_s(i + 2);
+          mbar_wait(&v_empty[st], (i >> 1) & 1);
+          load_v(i + 2);
+        }
+      }
+    }
+  } else if (warp < n_active) {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t tO = tmem_O + lane_base;
+    const bool bf16 = p.dtype == MA3_BF16;
+    uint8_t* prow = sP + row * 128;
+    uint32_t stash[HD / 2];
+#pragma unroll
+    for (int e = 0; e < HD / 2; ++e) stash[e] = 0u;
+    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + ((long long)ns * p.T + q0 + row) * p.D + (long long)h * HD;
+    const bool row_ok = q0 + row < p.T;
+    int it = 0;
+    for (int seg = 0; seg < 2; ++seg) {
+      const int ntl = seg ? n_cross : n_self;
+      const int kvlen = seg ? p.L : p.T;
+      if (ntl == 0) continue;
+      float m = 0.f;
+      for (int j = 0; j < ntl; ++j, ++it) {
+        const bool tr = warp == 0 && lane == 0;
+        if (tr) attn_trace(p, it, 0);
+        mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+        if (tr) attn_trace(p, it, 1);
+        tc_fence_after();
+        const uint32_t tS = tmem_S + (it & 1) * BKV + lane_base;
+        uint32_t s[64];
+        tmem_ld_n<32>(tS, s);
+        tmem_ld_n<32>(tS + 32, s + 32);
+        tmem_ld_wait();
+        const int valid = kvlen - j * BKV;
+        if (valid < BKV) {   // ragged last tile of a segment: keys beyond the sequence get -inf
+#pragma unroll
+          for (int e = 0; e < 64; ++e)
+            if (e >= valid) s[e] = 0xff800000u;
+        }
+        float mx4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 4]));
+#pragma unroll
+        for (int e = 8; e < 64; e += 8) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mx4[c] = fmax3(mx4[c], __uint_as_float(s[e + c]), __uint_as_float(s[e + c + 4]));
+        }
+        const float mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]);
+        if (tr) attn_trace(p, it, 2);
+        bool waited = false;
+        if (j == 0) {
+          m = mx;
+        } else if (__any_sync(0xffffffffu, mx > m + 8.f)) {
+          mbar_wait(o_full, (it - 1) & 1);   // PV(it-1) complete: O may be modified
+          tc_fence_after();
+          waited = true;
+          const float m_new = fmaxf(m, mx);
+          rescale_o<HDO>(tO, ex2_approx(m - m_new));
+          m = m_new;
+        }
+        if (tr) attn_trace(p, it, 3);
+        uint32_t pk[32];
+        const float2 nm = make_float2(-m, -m);
+        if (bf16) {
+#pragma unroll
+          for (int e = 0; e < 64; e += 2) {
+            const float2 d = fadd2(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), nm);
+            pk[e >> 1] = pack_bf16(ex2_approx(d.x), ex2_approx(d.y));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 64; e += 2) {
+            const float2 d = fadd2(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), nm);
+            pk[e >> 1] = pack_f16(ex2_approx(d.x), ex2_approx(d.y));
+          }
+        }
+        if (tr) attn_trace(p, it, 4);
+        if (it > 0 && !waited) mbar_wait(o_full, (it - 1) & 1);   // PV(it-1) has finished reading P
+        if (tr) attn_trace(p, it, 5);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          *reinterpret_cast<uint4*>(prow + ((u ^ (row & 7)) * 16)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(p_full);
+        if (tr) attn_trace(p, it, 6);
+      }
+      mbar_wait(o_full, (it - 1) & 1);
+      tc_fence_after();
+      uint32_t rl[16];
+      tmem_ld16(tO + HDO - 16, rl);
+      tmem_ld_wait();
+      const float l = __uint_as_float(rl[HD - (HDO - 16)]);
+      const float f = __fdividef(seg ? tanhf(p.gate[h]) : 1.f, l);
+      if (seg == 0 && n_cross > 0) drain_o<HD, false>(tO, f, stash, orow, bf16, row_ok);
+      else drain_o<HD, true>(tO, f, stash, orow, bf16, row_ok);
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int HDP, int HD, int BKV>
+static int launch_attn2(const AttnParams& p, int NS, cudaStream_t st) {
+  constexpr size_t smem = 128 * HDP * 2 + 2 * (2 * BKV * HDP * 2) + 128 * BKV * 2 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn2_kernel<HDP, HD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(attn2): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid((unsigned)((p.T + 127) / 128), (unsigned)p.H, (unsigned)NS);
+  cudaError_t le = launch_pdl(attn2_kernel<HDP, HD, BKV>, grid, dim3(kAttnThreads), smem, st, 1, p);
+  if (le != cudaSuccess) MA3_FAIL((int)le, "attention launch: %s", cudaGetErrorString(le));
+  MA3_LAUNCH_CHECK("attention");
+  return 0;
+}
+
 template <int HDP, int HD, int BKV>
 static int launch_attn(const AttnParams& p, int NS, cudaStream_t st) {
   constexpr size_t smem = 128 * HDP * 2 + 2 * (2 * BKV * HDP * 2) + 128 * BKV * 2 + 256;
@@ -421,13 +752,20 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
     p.tmVyt = p.tmVt;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // v2 (O resident in TMEM, row sums through the ones row of V^T) whenever the padded head has a spare row;
+  // MA3_ATTN_V1=1 forces the first-generation kernel (diagnostics)
+  static const bool force_v1 = getenv("MA3_ATTN_V1") != nullptr && getenv("MA3_ATTN_V1")[0] == '1';
+  if (!force_v1) {
+    if (hdp == 64 && hd == 16) return launch_attn2<64, 16, 64>(p, NS, st);
+    if (hdp == 64 && hd == 24) return launch_attn2<64, 24, 64>(p, NS, st);
+    if (hdp == 64 && hd == 32) return launch_attn2<64, 32, 64>(p, NS, st);
+    if (hdp == 64 && hd == 48) return launch_attn2<64, 48, 64>(p, NS, st);
+    if (hdp == 128 && hd == 72) return launch_attn2<128, 72, 64>(p, NS, st);
+    if (hdp == 128 && hd == 96) return launch_attn2<128, 96, 64>(p, NS, st);
+  }
   if (hdp == 64 && hd == 24) return launch_attn<64, 24, 64>(p, NS, st);
-  if (hdp == 64 && hd == 16) return launch_attn<64, 16, 64>(p, NS, st);
-  if (hdp == 64 && hd == 32) return launch_attn<64, 32, 64>(p, NS, st);
-  if (hdp == 64 && hd == 48) return launch_attn<64, 48, 64>(p, NS, st);
   if (hdp == 64 && hd == 64) return launch_attn<64, 64, 64>(p, NS, st);
   if (hdp == 128 && hd == 72) return launch_attn<128, 72, 64>(p, NS, st);
-  if (hdp == 128 && hd == 96) return launch_attn<128, 96, 64>(p, NS, st);
   if (hdp == 128 && hd == 128) return launch_attn<128, 128, 64>(p, NS, st);
   MA3_FAIL(MA3_EINVAL, "attention: head_dim %d (pad %d) not instantiated", hd, hdp);
 }

@@ -7,6 +7,8 @@
 #include "host_common.h"
 #include "ptx.cuh"
 
+#include <math.h>
+
 namespace ma3 {
 
 constexpr int kBM = 128;
@@ -46,8 +48,50 @@ struct GemmKParams {
   int first_section;
   int op_dtype;
   float inv_rows_per_sample, inv_tokens, inv_head_dim;  // exact-division helpers (see fast_div)
+  int debug_mode;    // diagnostics: 1 = no TMA loads, 2 = no MMAs
+  int stream_k;      // GATE_RES only: workers take equal contiguous ranges of (tile, k-iteration) instead of whole tiles
   long long* trace;  // diagnostics: when non-null, CTA 0 records clock64() at pipeline events (tools/probe_trace.py)
 };
+
+// Work distribution.  Tile mode: worker w owns tiles w, w + n_workers, ... with the full reduction each.  Stream-K mode
+// (epilogues that add into the output with fire-and-forget reductions): the tiles x k-iterations space is cut into
+// n_workers equal contiguous ranges, so every SM gets the same number of MMA k-steps whatever the tile count; a tile cut
+// by a range boundary is finished by two workers, each adding its partial product.
+struct WorkState {
+  long long cur, end;
+  int step;
+};
+__device__ __forceinline__ WorkState work_begin(const GemmKParams& p, int worker, int n_workers, int total_tiles, int iters) {
+  WorkState ws;
+  if (p.stream_k) {
+    const long long total = (long long)total_tiles * iters;
+    ws.cur = total * worker / n_workers;
+    ws.end = total * (worker + 1) / n_workers;
+    ws.step = 0;
+  } else {
+    ws.cur = worker;
+    ws.end = total_tiles;
+    ws.step = n_workers;
+  }
+  return ws;
+}
+// next item: tile index, first k-iteration and number of k-iterations; false when the worker is done
+__device__ __forceinline__ bool work_next(const GemmKParams& p, WorkState& ws, int iters, int& tile, int& k0, int& kn) {
+  if (ws.cur >= ws.end) return false;
+  if (p.stream_k) {
+    tile = (int)(ws.cur / iters);
+    k0 = (int)(ws.cur - (long long)tile * iters);
+    const long long left = ws.end - ws.cur;
+    kn = left < (long long)(iters - k0) ? (int)left : iters - k0;
+    ws.cur += kn;
+  } else {
+    tile = (int)ws.cur;
+    k0 = 0;
+    kn = iters;
+    ws.cur += ws.step;
+  }
+  return true;
+}
 
 __device__ __forceinline__ void trace_evt(const GemmKParams& p, int tile_local, int slot) {
   if (p.trace && blockIdx.x == 0 && tile_local < 16) p.trace[tile_local * 16 + slot] = clock64();
@@ -180,6 +224,14 @@ __device__ __forceinline__ void make_row_ctx(const GemmKParams& p, int z, int m0
       rc.off[pass] = m < p.M ? ((long long)sample * p.heads * p.tokens + t) * p.head_dim_pad : -1;
       rc.aux[pass] = (long long)t * p.head_dim;
     }
+    // V^T token groups (8 consecutive tokens from m0 + 8 g; never straddle a sample when tokens % 8 == 0):
+    // offset of (sample, head 0, d 0, t)
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      const int m = m0 + gq * 8;
+      const int sample = fast_div(m, p.inv_tokens), t = m - sample * p.tokens;
+      rc.off[4 + gq] = m < p.M ? (long long)sample * p.heads * p.head_dim_pad * p.tokens_pad + t : -1;
+    }
   }
 }
 
@@ -191,8 +243,10 @@ __device__ __forceinline__ void make_row_ctx(const GemmKParams& p, int z, int m0
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int n0, int w, const uint32_t* r,
                                                float* stg, int lane, const RowCtx& rc) {
-  if constexpr (EPI == MA3_EPI_QKV_ROPE) {
-    // V^T scatter straight from registers: lanes = consecutive tokens -> contiguous 2-byte stores per column
+  // V^T: with tokens % 8 == 0 the chunk is transposed through the staging patch below (16-byte stores along the token
+  // axis); otherwise it is scattered straight from registers (lanes = consecutive tokens, 2-byte stores per column).
+  const bool vt_fast = EPI == MA3_EPI_QKV_ROPE && (p.tokens & 7) == 0;
+  if (EPI == MA3_EPI_QKV_ROPE && !vt_fast) {
     const int m = m0 + lane;
     const int sec0 = (n0 >= p.model_dim) + (n0 >= 2 * p.model_dim);
     const int sec1 = (n0 + w - 1 >= p.model_dim) + (n0 + w - 1 >= 2 * p.model_dim);
@@ -337,7 +391,36 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
         sp += 8 * kStagePitch;
       }
     }
-  } else {  // MA3_EPI_QKV_ROPE: q / k columns (v was scattered above); 4 lanes x 8 columns per row
+  } else {  // MA3_EPI_QKV_ROPE
+    if (vt_fast) {
+      // lane <-> column (one head dimension), 4 groups of 8 consecutive tokens: conflict-free column reads of the
+      // patch, one 16-byte store per group into vt[(sample, head, d), t .. t+8)
+      const int vcol = n0 + lane;
+      const int vsec = (vcol >= p.model_dim) + (vcol >= 2 * p.model_dim);
+      if (lane < w && vcol < p.N && vsec + p.first_section == 2) {
+        const int within = vcol - vsec * p.model_dim;
+        const int head = fast_div(within, p.inv_head_dim);
+        const int d = within - head * p.head_dim;
+        const long long cpart = ((long long)head * p.head_dim_pad + d) * p.tokens_pad;
+        uint16_t* vt = reinterpret_cast<uint16_t*>(p.vt_out);
+        const float* sp = stg + lane;
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          if (rc.off[4 + gq] >= 0) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = sp[(gq * 8 + e) * kStagePitch];
+            uint4 u;
+            if (p.op_dtype == MA3_BF16)
+              u = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            else
+              u = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
+            *reinterpret_cast<uint4*>(vt + rc.off[4 + gq] + cpart) = u;
+          }
+        }
+      }
+    }
+    // q / k columns: 4 lanes x 8 columns per row
     const int cg = (lane & 3) * 8;
     const int col = n0 + cg;
     const int sec = (col >= p.model_dim) + (col >= 2 * p.model_dim);
@@ -449,64 +532,95 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
   const int kchunks = p.K / p.BK;
   const int iters = p.taps * kchunks;
 
+  // The producer and the MMA issuer are single threads running dependent instruction chains (~5 clk per instruction):
+  // their loops are kept to a handful of instructions per k-iteration -- parameters hoisted out of constant memory,
+  // stage index / phase advanced incrementally (no division), descriptors rebuilt from one 32-bit add per stage and the
+  // four K = 16 steps of a 64-wide stage unrolled.  (A generic loop measured ~155 clk per MMA, above the 128-clk
+  // tensor-pipe floor of a 128 x 256 x 16 MMA, which made every tile shape issue-bound.)
   if (warp == 0) {
     if (elect_one()) {
-      int it = 0;
-      for (int tile = worker; tile < total_tiles; tile += n_workers) {
-        const int n_t = tile % p.tiles_n;
-        const int rest = tile / p.tiles_n;
-        const int m_t = rest % p.tiles_m;
-        const int z = rest / p.tiles_m;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int arow = (m_t * CG + (int)rank) * kBM + p.a_shift[tap];
-          const int brow = n_t * p.BN + (int)rank * (p.BN / CG) + p.b_row[tap];
-          for (int kc = 0; kc < kchunks; ++kc, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* dst = tiles + (size_t)s * stage_bytes;
-            if constexpr (CG == 2) {
-              if (leader) mbar_arrive_expect_tx(&full[s], 2 * stage_bytes);   // bytes of both CTAs land on the leader
-              tma_load_3d_2cta(dst, &p.tmA, &full[s], kc * p.BK, arow, p.a_batched ? z : 0);
-              tma_load_3d_2cta(dst + a_bytes, &p.tmB, &full[s], kc * p.BK, brow, p.b_batched ? z : 0);
-            } else {
-              mbar_arrive_expect_tx(&full[s], stage_bytes);
-              tma_load_3d(dst, &p.tmA, &full[s], kc * p.BK, arow, p.a_batched ? z : 0);
-              tma_load_3d(dst + a_bytes, &p.tmB, &full[s], kc * p.BK, brow, p.b_batched ? z : 0);
-            }
+      const int stages = p.stages, BK = p.BK, BN = p.BN, tiles_n = p.tiles_n, tiles_m = p.tiles_m;
+      const bool a_b = p.a_batched != 0, b_b = p.b_batched != 0;
+      const int dbg = p.debug_mode;
+      const uint32_t tiles_u32 = smem_u32(tiles), full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
+      int s = 0;
+      uint32_t ph = 1;   // parity to wait for on empty[s]: a fresh barrier passes a wait on parity 1
+      WorkState ws = work_begin(p, worker, n_workers, total_tiles, iters);
+      int tile, k0, kn;
+      while (work_next(p, ws, iters, tile, k0, kn)) {
+        const int n_t = tile % tiles_n;
+        const int rest = tile / tiles_n;
+        const int m_t = rest % tiles_m;
+        const int z = rest / tiles_m;
+        const int za = a_b ? z : 0, zb = b_b ? z : 0;
+        const int arow0 = (m_t * CG + (int)rank) * kBM, brow0 = n_t * BN + (int)rank * (BN / CG);
+        int tap = k0 / kchunks, kc = k0 - tap * kchunks;
+        int arow = arow0 + p.a_shift[tap], brow = brow0 + p.b_row[tap], kx = kc * BK;
+        for (int i = 0; i < kn; ++i) {
+          while (!mbar_try_wait(empty_u32 + 8 * s, ph)) {
+          }
+          const uint32_t dst = tiles_u32 + (uint32_t)s * stage_bytes, bar = full_u32 + 8 * s;
+          if (dbg == 1) {
+            if (leader) mbar_arrive_u32(bar);
+          } else if constexpr (CG == 2) {
+            if (leader) mbar_arrive_expect_tx_u32(bar, 2 * stage_bytes);   // bytes of both CTAs land on the leader
+            tma_load_3d_2cta_u32(dst, &p.tmA, bar, kx, arow, za);
+            tma_load_3d_2cta_u32(dst + a_bytes, &p.tmB, bar, kx, brow, zb);
+          } else {
+            mbar_arrive_expect_tx_u32(bar, stage_bytes);
+            tma_load_3d_u32(dst, &p.tmA, bar, kx, arow, za);
+            tma_load_3d_u32(dst + a_bytes, &p.tmB, bar, kx, brow, zb);
+          }
+          if (++s == stages) { s = 0; ph ^= 1; }
+          kx += BK;
+          if (++kc == kchunks) {
+            kc = 0; kx = 0; ++tap;
+            if (i + 1 < kn) { arow = arow0 + p.a_shift[tap]; brow = brow0 + p.b_row[tap]; }
           }
         }
       }
     }
   } else if (warp == 1) {
     if (leader && elect_one()) {
-      int it = 0, lt = 0;
+      int lt = 0;
+      const int stages = p.stages, dbg = p.debug_mode;
+      const uint32_t idesc = p.idesc, acc_cols = p.tmem_stage_cols;
       const int sw = p.BK * 2;
       const int ksteps = p.BK / 16;
-      for (int tile = worker; tile < total_tiles; tile += n_workers, ++lt) {
+      // descriptor = lo | hi << 32 with only the 14-bit start-address field of lo changing from stage to stage
+      const uint64_t desc0 = umma_desc_kmajor(smem_u32(tiles), sw);
+      const uint32_t desc_hi = (uint32_t)(desc0 >> 32), lo0 = (uint32_t)desc0;
+      const uint32_t stage16 = stage_bytes >> 4, a16 = a_bytes >> 4;
+      const uint32_t full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
+      int s = 0;
+      uint32_t ph = 0;
+      WorkState ws = work_begin(p, worker, n_workers, total_tiles, iters);
+      int tile, k0, kn;
+      for (; work_next(p, ws, iters, tile, k0, kn); ++lt) {
         const int as = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
         trace_evt(p, lt, 0);
         mbar_wait(&tempty[as], aph ^ 1);
         trace_evt(p, lt, 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * p.tmem_stage_cols;
-        for (int i = 0; i < iters; ++i, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
-          const uint64_t da = umma_desc_kmajor(a_addr, sw);
-          const uint64_t db = umma_desc_kmajor(a_addr + a_bytes, sw);
-          for (int k = 0; k < ksteps; ++k) {
-            if constexpr (CG == 2)
-              umma_f16_2cta(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (i | k) != 0 ? 1u : 0u);
-            else
-              umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (i | k) != 0 ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + as * acc_cols;
+        for (int i = 0; i < kn; ++i) {
+          while (!mbar_try_wait(full_u32 + 8 * s, ph)) {
           }
-          if constexpr (CG == 2) umma_commit_2cta(&empty[s]);   // frees the stage in both CTAs
-          else umma_commit(&empty[s]);
+          const uint32_t alo = lo0 + (uint32_t)s * stage16, blo = alo + a16;
+          if (dbg != 2) {
+            if (ksteps == 4) {
+              umma_f16_lohi<CG>(d_tmem, alo, blo, desc_hi, idesc, i != 0 ? 1u : 0u);
+              umma_f16_lohi<CG>(d_tmem, alo + 2, blo + 2, desc_hi, idesc, 1u);
+              umma_f16_lohi<CG>(d_tmem, alo + 4, blo + 4, desc_hi, idesc, 1u);
+              umma_f16_lohi<CG>(d_tmem, alo + 6, blo + 6, desc_hi, idesc, 1u);
+            } else {
+              for (int k = 0; k < ksteps; ++k)
+                umma_f16_lohi<CG>(d_tmem, alo + 2 * k, blo + 2 * k, desc_hi, idesc, (i | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit_u32<CG>(empty_u32 + 8 * s);   // frees the stage (in both CTAs of a pair)
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
         if constexpr (CG == 2) umma_commit_2cta(&tfull[as]);
         else umma_commit(&tfull[as]);
@@ -518,7 +632,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
     const int ew = warp - 2;                // epilogue warp index 0..7
     const int half = ew >> 2;               // which alternating set of 32-column chunks it owns
     int lt = 0;
-    for (int tile = worker; tile < total_tiles; tile += n_workers, ++lt) {
+    WorkState ws = work_begin(p, worker, n_workers, total_tiles, iters);
+    int tile, k0, kn;
+    for (; work_next(p, ws, iters, tile, k0, kn); ++lt) {
       const int n_t = tile % p.tiles_n;
       const int rest = tile / p.tiles_n;
       const int m_t = rest % p.tiles_m;
@@ -598,6 +714,33 @@ static int launch(const GemmKParams& kp, size_t smem, int grid, int cta_group, c
   return cta_group == 2 ? launch_cg<EPI, 2>(kp, smem, grid, st) : launch_cg<EPI, 1>(kp, smem, grid, st);
 }
 
+// Modelled critical path (SM clocks) of one launch for a tile shape.  Per 64-wide k-iteration the tensor pipe needs
+// 2 * BN clocks (128 x BN x 64 at 8192 flop/clk), the single issuing thread ~95 clocks per MMA, and the TMA feed
+// 120 + 1.5 BN (one CTA) or 200 + 0.6 BN (CTA pair: half of B per SM); a tile's epilogue (clocks per accumulator
+// column, per epilogue kind) overlaps the next tile's mainloop, so a tile costs max(mainloop, epilogue) and the last
+// epilogue is exposed.  Numbers from tools/probe_trace.py on B200.
+static double tile_cost(const ma3_gemm_t* g, int BN, int CG, int BK) {
+  const int workers = num_sms() / CG;
+  const long tiles_m = (g->M + kBM * CG - 1) / (kBM * CG), tiles_n = (g->N + BN - 1) / BN;
+  const long tiles = tiles_m * tiles_n * g->batch;
+  const long iters = (long)g->taps * (g->K / BK);
+  const double ks = BK / 64.0;
+  const double mma = fmax(2.0 * BN * ks, 95.0 * (BK / 16));
+  const double feed = CG == 1 ? 120.0 + 1.5 * BN * ks : 200.0 + 0.6 * BN * ks;
+  const double iter = fmax(mma, feed);
+  double per_col;
+  switch (g->epi) {
+    case MA3_EPI_GATE_RES: per_col = 27.0; break;
+    case MA3_EPI_SWIGLU: per_col = 21.0; break;
+    case MA3_EPI_QKV_ROPE: per_col = 33.0; break;
+    default: per_col = g->out_dtype == MA3_F32 ? 45.0 : 37.0; break;
+  }
+  const double epi = 400.0 + per_col * BN;
+  const double tile = fmax((double)iters * iter, epi);
+  const long waves = (tiles + workers - 1) / workers;
+  return (double)waves * tile + epi + (CG == 2 ? 900.0 : 0.0);
+}
+
 }  // namespace ma3
 
 extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
@@ -617,23 +760,29 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   memset(&kp, 0, sizeof(kp));
   const int BK = g->K % 64 == 0 ? 64 : (g->K % 32 == 0 ? 32 : 16);
   int BN = g->tile_n;
-  if (BN <= 0) {
-    if (g->N <= 256) {
-      BN = (g->N + 15) / 16 * 16;
-    } else {
-      const int cands[3] = {256, 192, 128};
-      long best = -1;
-      for (int c : cands) {
-        long padded = (long)((g->N + c - 1) / c) * c;
-        if (best < 0 || padded < best) { best = padded; BN = c; }
-      }
-    }
-  }
-  MA3_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm: tile_n=%d must be a multiple of 16 in [16,256]", BN);
-  // CTA pairs (cta_group::2, 256-row tiles) for the large GEMMs: each SM pulls only half of the B tile through L2.
   int CG = g->cta_group;
   MA3_REQUIRE(CG >= 0 && CG <= 2, "gemm: cta_group must be 0 (auto), 1 or 2");
-  if (CG == 0) CG = (g->M >= 1024 && BN >= 128 && BN % 32 == 0) ? 2 : 1;
+  if (BN <= 0 || CG == 0) {
+    // pick (tile_n, cta_group) by the modelled critical path in SM clocks (constants measured with tools/probe_trace.py)
+    int cands[4] = {256, 192, 128, 0}, ncand = 3;
+    if (g->N < 256) { cands[0] = (g->N + 15) / 16 * 16; ncand = 1; }
+    double best = -1.0;
+    int bBN = cands[0], bCG = 1;
+    for (int ci = 0; ci < ncand; ++ci) {
+      if (g->tile_n > 0 && ci > 0) break;
+      const int bn = g->tile_n > 0 ? g->tile_n : cands[ci];
+      for (int cg = 1; cg <= 2; ++cg) {
+        if (g->cta_group != 0 && cg != g->cta_group) continue;
+        if (cg == 2 && (bn % 32 != 0 || bn < 64 || g->M < 256)) continue;
+        const double c = tile_cost(g, bn, cg, BK);
+        if (best < 0 || c < best) { best = c; bBN = bn; bCG = cg; }
+      }
+    }
+    if (best < 0) { bBN = g->tile_n > 0 ? g->tile_n : cands[0]; bCG = g->cta_group ? g->cta_group : 1; }
+    BN = bBN;
+    CG = bCG;
+  }
+  MA3_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm: tile_n=%d must be a multiple of 16 in [16,256]", BN);
   if (CG == 2) MA3_REQUIRE(BN % 32 == 0, "gemm: cta_group 2 needs tile_n %% 32 == 0 (got %d)", BN);
   const size_t stage_bytes = (size_t)(kBM + BN / CG) * BK * 2;   // per CTA
   const size_t kTail = 256 + kEpiWarps * 32 * kStagePitch * sizeof(float);  // barriers + epilogue staging
@@ -684,6 +833,7 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   kp.inv_tokens = g->tokens > 0 ? 1.0f / (float)g->tokens : 0.f;
   kp.inv_head_dim = g->head_dim > 0 ? 1.0f / (float)g->head_dim : 0.f;
   kp.trace = g_trace;
+  kp.debug_mode = g_gemm_debug_mode;
 
   const int total_tiles = kp.tiles_m * kp.tiles_n * kp.batch;
   const int workers = num_sms() / CG;   // CTAs (CG = 1) or CTA pairs (CG = 2)
@@ -716,6 +866,20 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
       MA3_REQUIRE(g->batch == 1, "gemm/gate_res: batch must be 1 (flatten samples into M)");
       MA3_REQUIRE(g->N % 4 == 0 && g->out_ld % 4 == 0 && g->gate_ld % 4 == 0 && aligned16(g->out) && aligned16(g->gate),
                   "gemm/gate_res: N, out_ld, gate_ld must be multiples of 4 and pointers 16-byte aligned");
+      MA3_REQUIRE(g->stream_k >= -1 && g->stream_k <= 1, "gemm/gate_res: stream_k must be -1, 0 or 1");
+      {
+        // stream-K when whole tiles would leave a large part of the last wave idle and every worker still gets a
+        // reasonable run of k-iterations
+        const long long total_iters = (long long)total_tiles * kp.taps * (kp.K / kp.BK);
+        const int waves = (total_tiles + workers - 1) / workers;
+        const bool unbalanced = (long long)total_tiles * 100 < (long long)waves * workers * 92;
+        // measured neutral-to-slower on the DiT shapes (the partial tiles add RED-bound epilogues), so only on request
+        const bool on = g->stream_k == 1 && unbalanced;
+        if (on && total_iters >= workers) {
+          kp.stream_k = 1;
+          return launch<MA3_EPI_GATE_RES>(kp, smem, workers * CG, CG, st);
+        }
+      }
       return launch<MA3_EPI_GATE_RES>(kp, smem, grid, CG, st);
     case MA3_EPI_SWIGLU:
       MA3_REQUIRE(g->out && g->batch == 1, "gemm/swiglu: out required, batch must be 1");
@@ -741,6 +905,10 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
 
 /* diagnostics: device buffer of >= 256 int64 that CTA 0 of subsequent ma3_gemm launches fills with clock64()
  * timestamps (per tile: MMA thread slots 0-2, epilogue warp slots 4-6); pass NULL to switch tracing off. */
+extern "C" int ma3_debug_set_gemm_mode(int mode) {
+  ma3::g_gemm_debug_mode = mode;
+  return 0;
+}
 extern "C" int ma3_debug_set_gemm_trace(void* buf) {
   ma3::g_trace = reinterpret_cast<long long*>(buf);
   return 0;

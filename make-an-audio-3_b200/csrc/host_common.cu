@@ -11,6 +11,7 @@ namespace ma3 {
 std::atomic<int64_t> g_launches{0};
 thread_local char g_err[512] = {0};
 long long* g_trace = nullptr;
+int g_gemm_debug_mode = 0;
 
 bool pdl_enabled() {
   static int v = -1;

@@ -13,6 +13,7 @@ namespace ma3 {
 
 extern std::atomic<int64_t> g_launches;
 extern thread_local char g_err[512];
+extern int g_gemm_debug_mode;  // diagnostics (ma3_debug_set_gemm_mode): 1 = skip TMA loads, 2 = skip MMAs; results are garbage
 extern long long* g_trace;  // diagnostics buffer (ma3_debug_set_gemm_trace); nullptr = off
 
 #define MA3_FAIL(code, ...)                       \

@@ -271,7 +271,7 @@ class TxtFlagLargeDiT(nn.Module):
             w.u = torch.empty(N * T, D, device=dev, dtype=bf)
             w.q = torch.zeros(N, H, T, hdp, device=dev, dtype=bf)
             w.k = torch.zeros(N, H, T, hdp, device=dev, dtype=bf)
-            w.vt = torch.zeros(N, H, hdp, Tp, device=dev, dtype=bf)
+            w.vt = ops.alloc_vt(N, H, hd=hd, hdp=hdp, tokens_pad=Tp, device=dev, dtype=bf)
             w.att = torch.empty(N * T, D, device=dev, dtype=bf)
             w.mid = torch.empty(N * T, F, device=dev, dtype=bf)
             if self.num_experts:
@@ -297,7 +297,7 @@ class TxtFlagLargeDiT(nn.Module):
             c = {"shape": (N, Lc, Cd)}
             c["yn"] = torch.empty(N * Lc, self.y_dim, device=dev, dtype=bf)
             c["ky"] = torch.zeros(self.depth, N, H, Lc, hdp, device=dev, dtype=bf)
-            c["vyt"] = torch.zeros(self.depth, N, H, hdp, Lp, device=dev, dtype=bf)
+            c["vyt"] = ops.alloc_vt(self.depth, N, H, hd=hd, hdp=hdp, tokens_pad=Lp, device=dev, dtype=bf)
             c["pool"] = torch.empty(N, self.y_dim, device=dev, dtype=bf)
             c["cap"] = torch.empty(N, D, device=dev, dtype=torch.float32)
             if self._video:

@@ -65,7 +65,7 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
          out_row_mul=1, out_row_off=0, bias=None, bias_per_row=False, res=None, res_ld=None, res_batch_stride=0,
          alpha=1.0, accumulate=False, gate=None, rows_per_sample=0, q_out=None, k_out=None, vt_out=None, rope=None,
          model_dim=0, head_dim=0, head_dim_pad=0, tokens=0, tokens_pad=0, q_scale=1.0, first_section=0, act=0,
-         tile_n=0, cta_group=0):
+         tile_n=0, cta_group=0, stream_k=0):
     """acc[z,m,n] = sum_taps sum_k A[z, m + a_shift, k] * B[z, n + b_row, k]; see include/ma3_b200.h."""
     lib = L.require_device()
     assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float16)
@@ -117,6 +117,7 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
     d.act = act
     d.tile_n = tile_n
     d.cta_group = cta_group
+    d.stream_k = stream_k
     with _Span("tap_gemm/" + _EPI_NAMES[epi], 2.0 * M * N * K * len(taps) * batch):
         L.check(lib.ma3_gemm(C.byref(d), L.stream_ptr()), "ma3_gemm")
     return out
@@ -253,8 +254,19 @@ def kaiser_sinc_taps(cutoff=0.25, half_width=0.3, kernel_size=12):
     return [float(v) for v in f]
 
 
+def alloc_vt(*lead, hd, hdp, tokens_pad, device, dtype=torch.bfloat16):
+    """Zeroed V^T buffer [*lead, hdp, tokens_pad] in the layout ma3_attention expects: rows [0, hd) are written by
+    the QKV GEMM epilogue, row hd (when hd < hdp) holds ones so that the P.V MMA also produces the softmax row sums
+    (include/ma3_b200.h, ma3_attention), the remaining pad rows stay zero."""
+    vt = torch.zeros(*lead, hdp, tokens_pad, device=device, dtype=dtype)
+    if hd < hdp:
+        vt[..., hd, :] = 1
+    return vt
+
+
 def attention(q, k, vt, ky, vyt, gate, out, *, hd):
-    """q,k [NS,H,T,hdp]; vt [NS,H,hdp,Tp]; ky [NS,H,L,hdp]; vyt [NS,H,hdp,Lp]; out [NS,T,H*hd]."""
+    """q,k [NS,H,T,hdp]; vt [NS,H,hdp,Tp]; ky [NS,H,L,hdp]; vyt [NS,H,hdp,Lp]; out [NS,T,H*hd].
+    vt / vyt must come from alloc_vt (ones in row hd)."""
     NS, H, T, hdp = q.shape
     Tp = vt.shape[-1]
     Lc = ky.shape[2] if ky is not None else 0

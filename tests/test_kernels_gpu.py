@@ -113,6 +113,26 @@ def test_gemm_gate_residual_and_swiglu(ops):
     assert rel(o, ref) < 8e-3
 
 
+@pytest.mark.parametrize("M,N,K,cg", [(4992, 1152, 1152, 1), (4992, 1152, 3072, 2), (624, 768, 2048, 1), (1000, 192, 512, 2)])
+def test_gemm_gate_residual_stream_k(ops, M, N, K, cg):
+    """Stream-K work split (equal k-iteration ranges per SM, partial products added by separate reductions) against
+    the same fp32 expression and against the whole-tile schedule (differences only from fp32 summation order)."""
+    from ma3_b200 import lib as L
+    T = 8
+    a = torch.randn(M, K, generator=g(40)).bfloat16().cuda()
+    b = (torch.randn(N, K, generator=g(41)) / K ** .5).bfloat16().cuda()
+    h0 = torch.randn(M, N, generator=g(42)).cuda()
+    gate = torch.randn(M // T, N, generator=g(43)).cuda()
+    ref = h0 + gate.repeat_interleave(T, 0) * (a.float() @ b.float().t())
+    outs = []
+    for sk in (1, -1):
+        h = h0.clone()
+        ops.gemm(a, b, M=M, N=N, K=K, epi=L.EPI_GATE_RES, out=h, gate=gate, rows_per_sample=T, cta_group=cg, stream_k=sk)
+        assert rel(h, ref) < 1e-4
+        outs.append(h)
+    assert rel(outs[0], outs[1]) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------ QKV+RoPE, attention
 def _qkv_attention_case(ops, D, H, T, L, Ns, seed):
     """QKV GEMM with RoPE scatter followed by the fused self+cross attention, against oracle.attention pieces."""
@@ -139,16 +159,22 @@ def _qkv_attention_case(ops, D, H, T, L, Ns, seed):
     rope = torch.stack([cos, sin], -1).contiguous().to(dev)
     q = torch.zeros(Ns, H, T, hdp, device=dev, dtype=torch.bfloat16)
     k = torch.zeros_like(q)
-    vt = torch.zeros(Ns, H, hdp, Tp, device=dev, dtype=torch.bfloat16)
+    vt = ops.alloc_vt(Ns, H, hd=hd, hdp=hdp, tokens_pad=Tp, device=dev)
     ops.gemm(xb, wqkv, M=Ns * T, N=3 * D, K=D, epi=L_.EPI_QKV_ROPE, q_out=q, k_out=k, vt_out=vt, rope=rope,
              model_dim=D, head_dim=hd, head_dim_pad=hdp, tokens=T, tokens_pad=Tp,
              q_scale=math.log2(math.e) / math.sqrt(hd))
     yb = y.bfloat16().to(dev).view(Ns * L, D)
     wkv = torch.cat([sd["wk_y.weight"], sd["wv_y.weight"]]).bfloat16().to(dev)
     ky = torch.zeros(Ns, H, L, hdp, device=dev, dtype=torch.bfloat16)
-    vyt = torch.zeros(Ns, H, hdp, Lp, device=dev, dtype=torch.bfloat16)
+    vyt = ops.alloc_vt(Ns, H, hd=hd, hdp=hdp, tokens_pad=Lp, device=dev)
     ops.gemm(yb, wkv, M=Ns * L, N=2 * D, K=D, epi=L_.EPI_QKV_ROPE, q_out=ky, k_out=ky, vt_out=vyt, rope=None,
              model_dim=D, head_dim=hd, head_dim_pad=hdp, tokens=L, tokens_pad=Lp, first_section=1)
+    # layout contract of the epilogue: rows [0, hd) of V^T hold v, the ones row and the zero pads are untouched
+    full = (xb.float() @ wqkv.float().t()).view(Ns, T, 3, H, hd)
+    assert rel(vt[:, :, :hd, :T], full[:, :, 2].permute(0, 2, 3, 1)) < 1e-2
+    if hd < hdp:
+        assert bool((vt[:, :, hd] == 1).all()) and bool((vt[:, :, hd + 1:] == 0).all())
+    assert bool((q[..., hd:] == 0).all()) and bool((k[..., hd:] == 0).all())
     out = torch.empty(Ns, T, D, device=dev, dtype=torch.bfloat16)
     ops.attention(q, k, vt, ky, vyt, sd["gate"].to(dev), out, hd=hd)
     torch.cuda.synchronize()
@@ -160,6 +186,32 @@ def _qkv_attention_case(ops, D, H, T, L, Ns, seed):
 def test_qkv_rope_attention(ops, D, H, T, L, Ns):
     # bf16 q/k/v/p storage: 2^-8 relative per rounding, a handful of roundings
     assert _qkv_attention_case(ops, D, H, T, L, Ns, seed=20) < 2e-2
+
+
+def test_attention_lazy_rescale_large_logits(ops):
+    """Logits with a large, growing spread across KV tiles force the in-TMEM rescale of O (running maximum raised by
+    more than 2^8) on most tiles; compared with an fp32 softmax of the same bf16 operands."""
+    Ns, H, T, L, hd, hdp = 2, 4, 312, 154, 72, 128
+    dev = "cuda"
+    gg = g(21)
+    q = torch.zeros(Ns, H, T, hdp); k = torch.zeros(Ns, H, T, hdp); ky = torch.zeros(Ns, H, L, hdp)
+    q[..., :hd] = torch.randn(Ns, H, T, hd, generator=gg) * 0.8
+    k[..., :hd] = torch.randn(Ns, H, T, hd, generator=gg) * torch.linspace(0.5, 4.0, T)[None, None, :, None]
+    ky[..., :hd] = torch.randn(Ns, H, L, hd, generator=gg) * torch.linspace(0.5, 3.0, L)[None, None, :, None]
+    v = torch.randn(Ns, H, T, hd, generator=gg); vy = torch.randn(Ns, H, L, hd, generator=gg)
+    gate = torch.randn(H, generator=gg)
+    b = lambda t: t.bfloat16()
+    Tp, Lp = T, (L + 7) // 8 * 8
+    vt = ops.alloc_vt(Ns, H, hd=hd, hdp=hdp, tokens_pad=Tp, device=dev); vt[:, :, :hd, :T] = b(v).transpose(2, 3).to(dev)
+    vyt = ops.alloc_vt(Ns, H, hd=hd, hdp=hdp, tokens_pad=Lp, device=dev); vyt[:, :, :hd, :L] = b(vy).transpose(2, 3).to(dev)
+    out = torch.empty(Ns, T, H * hd, device=dev, dtype=torch.bfloat16)
+    ops.attention(b(q).to(dev), b(k).to(dev), vt, b(ky).to(dev), vyt, gate.to(dev), out, hd=hd)
+    ln2 = math.log(2.0)
+    qf, kf, kyf = b(q).float()[..., :hd], b(k).float()[..., :hd], b(ky).float()[..., :hd]
+    ps = torch.softmax(qf @ kf.transpose(2, 3) * ln2, -1) @ b(v).float()
+    pc = torch.softmax(qf @ kyf.transpose(2, 3) * ln2, -1) @ b(vy).float()
+    ref = (ps + torch.tanh(gate)[None, :, None, None] * pc).permute(0, 2, 1, 3).reshape(Ns, T, H * hd)
+    assert rel(out, ref) < 2e-2
 
 
 # ------------------------------------------------------------------------------------------------ elementwise

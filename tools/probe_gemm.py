@@ -86,7 +86,7 @@ wqkv = (torch.randn(3 * D, K, device=dev) / K ** .5).bfloat16()
 ang = torch.outer(torch.arange(T, device=dev).float(), 1.0 / (10000 ** (torch.arange(0, hd, 2, device=dev).float() / hd)))
 rope = torch.stack([ang.cos(), ang.sin()], -1).contiguous()
 q = torch.zeros(Ns, H, T, hdp, device=dev, dtype=torch.bfloat16); kk = torch.zeros_like(q)
-vt = torch.zeros(Ns, H, hdp, Tp, device=dev, dtype=torch.bfloat16)
+vt = ops.alloc_vt(Ns, H, hd=hd, hdp=hdp, tokens_pad=Tp, device=dev)
 ops.gemm(a, wqkv, M=M, N=3 * D, K=K, epi=L.EPI_QKV_ROPE, q_out=q, k_out=kk, vt_out=vt, rope=rope,
          model_dim=D, head_dim=hd, head_dim_pad=hdp, tokens=T, tokens_pad=Tp, q_scale=0.5)
 full = (a.float() @ wqkv.float().t()).view(Ns, T, 3, H, hd)
@@ -97,5 +97,5 @@ def rot(x):
 ok &= check("rope q", q[..., :hd], 0.5 * rot(full[:, :, 0]).permute(0, 2, 1, 3), 1e-2)
 ok &= check("rope k", kk[..., :hd], rot(full[:, :, 1]).permute(0, 2, 1, 3), 1e-2)
 ok &= check("vt", vt[:, :, :hd, :T], full[:, :, 2].permute(0, 2, 3, 1), 1e-2)
-ok &= bool((q[..., hd:] == 0).all() and (vt[:, :, hd:] == 0).all())
+ok &= bool((q[..., hd:] == 0).all() and (vt[:, :, hd + 1:] == 0).all() and (vt[:, :, hd] == 1).all())
 print("ALL OK" if ok else "SOME BAD")

@@ -17,8 +17,8 @@ mod = torch.randn(N, 6 * D, device=dev) * 0.1
 wn = torch.randn(D, device=dev)
 wqkv = (torch.randn(3 * D, D, device=dev) / D ** .5).to(bf); wo = (torch.randn(D, D, device=dev) / D ** .5).to(bf)
 w13 = (torch.randn(2 * F, D, device=dev) / D ** .5).to(bf); w2 = (torch.randn(D, F, device=dev) / F ** .5).to(bf)
-q = torch.zeros(N, H, T, hdp, device=dev, dtype=bf); k = torch.zeros_like(q); vt = torch.zeros(N, H, hdp, Tp, device=dev, dtype=bf)
-ky = torch.randn(N, H, Lc, hdp, device=dev).to(bf); vyt = torch.randn(N, H, hdp, Lp, device=dev).to(bf)
+q = torch.zeros(N, H, T, hdp, device=dev, dtype=bf); k = torch.zeros_like(q); vt = ops.alloc_vt(N, H, hd=hd, hdp=hdp, tokens_pad=Tp, device=dev)
+ky = torch.randn(N, H, Lc, hdp, device=dev).to(bf); vyt = torch.randn(N, H, hdp, Lp, device=dev).to(bf); vyt[:, :, hd:] = 0; vyt[:, :, hd] = 1
 gate = torch.randn(H, device=dev); att = torch.empty(M, D, device=dev, dtype=bf); mid = torch.empty(M, F, device=dev, dtype=bf)
 ang = torch.outer(torch.arange(1000, device=dev).float(), 1.0 / (10000 ** (torch.arange(0, hd, 2, device=dev).float() / hd)))
 rope = torch.stack([ang.cos(), ang.sin()], -1).contiguous()
@@ -26,6 +26,9 @@ qs = math.log2(math.e) / math.sqrt(hd)
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
 def bench(name, fn, flops=0, bytes_=0, n=10):
+    """Two timings per kernel: `cold` = one launch after an L2 flush (CUDA events; includes any CPU launch gap when
+    the host has not run ahead), `graph` = 10 launches captured in a CUDA graph and replayed (no host in the loop,
+    operands L2-warm as in the sampler loop)."""
     for _ in range(2): fn()
     torch.cuda.synchronize()
     tot = 0.0
@@ -35,9 +38,22 @@ def bench(name, fn, flops=0, bytes_=0, n=10):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
     ms = tot / n
-    s = f"{name:28s} {ms*1e3:8.1f} us"
-    if flops: s += f"  {flops/ms/1e9:7.1f} TFLOP/s"
-    if bytes_: s += f"  {bytes_/ms/1e6:7.1f} GB/s"
+    g = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        fn(); torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(10): fn()
+    torch.cuda.synchronize()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(3): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    mg = e0.elapsed_time(e1) / 30
+    s = f"{name:44s} cold {ms*1e3:7.1f} us  graph {mg*1e3:7.1f} us"
+    if flops: s += f"  {flops/mg/1e9:7.1f} TFLOP/s"
+    if bytes_: s += f"  {bytes_/mg/1e6:7.1f} GB/s"
     print(s, flush=True)
 
 bench("rmsnorm_modulate", lambda: ops.rmsnorm_modulate(h, wn, u, mod=mod, shift_off=0, scale_off=D, rows_per_sample=T), bytes_=M * D * 6)
@@ -48,9 +64,11 @@ bench("w13 gemm + swiglu", lambda: ops.gemm(u, w13, M=M, N=2 * F, K=D, epi=L.EPI
 bench("w2 gemm + gate_res", lambda: ops.gemm(mid, w2, M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=h, gate=mod[:, 5 * D:6 * D], rows_per_sample=T), flops=2.0 * M * D * F)
 for cg in (1, 2):
     bench(f"qkv cta_group={cg}", lambda: ops.gemm(u, wqkv, M=M, N=3 * D, K=D, epi=L.EPI_QKV_ROPE, q_out=q, k_out=k, vt_out=vt, rope=rope, model_dim=D, head_dim=hd, head_dim_pad=hdp, tokens=T, tokens_pad=Tp, q_scale=qs, cta_group=cg), flops=2.0 * M * 3 * D * D)
-    bench(f"wo cta_group={cg}", lambda: ops.gemm(att, wo, M=M, N=D, K=D, epi=L.EPI_GATE_RES, out=h, gate=mod[:, 2 * D:3 * D], rows_per_sample=T, cta_group=cg), flops=2.0 * M * D * D)
     bench(f"w13 cta_group={cg}", lambda: ops.gemm(u, w13, M=M, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=mid, out_ld=F, cta_group=cg), flops=2.0 * M * 2 * F * D)
-    bench(f"w2 cta_group={cg}", lambda: ops.gemm(mid, w2, M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=h, gate=mod[:, 5 * D:6 * D], rows_per_sample=T, cta_group=cg), flops=2.0 * M * D * F)
+    for sk in (-1, 1):
+        for tn in (128, 192, 256):
+            bench(f"wo cta_group={cg} stream_k={sk} tile_n={tn}", lambda: ops.gemm(att, wo, M=M, N=D, K=D, epi=L.EPI_GATE_RES, out=h, gate=mod[:, 2 * D:3 * D], rows_per_sample=T, cta_group=cg, stream_k=sk, tile_n=tn), flops=2.0 * M * D * D)
+            bench(f"w2 cta_group={cg} stream_k={sk} tile_n={tn}", lambda: ops.gemm(mid, w2, M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=h, gate=mod[:, 5 * D:6 * D], rows_per_sample=T, cta_group=cg, stream_k=sk, tile_n=tn), flops=2.0 * M * D * F)
 sys.exit(0)
 for tn in (128, 192, 256):
     bench(f"w13 swiglu tile_n={tn}", lambda: ops.gemm(u, w13, M=M, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=mid, out_ld=F, tile_n=tn), flops=2.0 * M * 2 * F * D)

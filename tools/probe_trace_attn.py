@@ -8,8 +8,8 @@ lib.ma3_debug_set_gemm_trace.argtypes = [ctypes.c_void_p]
 dev = "cuda"; bf = torch.bfloat16
 N, T, Lc, D, H = 16, 312, 154, 1152, 16
 hd = D // H; hdp = 128; Tp = 312; Lp = 160
-q = torch.randn(N, H, T, hdp, device=dev).to(bf); k = torch.randn_like(q); vt = torch.randn(N, H, hdp, Tp, device=dev).to(bf)
-ky = torch.randn(N, H, Lc, hdp, device=dev).to(bf); vyt = torch.randn(N, H, hdp, Lp, device=dev).to(bf)
+q = torch.randn(N, H, T, hdp, device=dev).to(bf); k = torch.randn_like(q); vt = torch.randn(N, H, hdp, Tp, device=dev).to(bf); vt[:, :, hd:] = 0; vt[:, :, hd] = 1
+ky = torch.randn(N, H, Lc, hdp, device=dev).to(bf); vyt = torch.randn(N, H, hdp, Lp, device=dev).to(bf); vyt[:, :, hd:] = 0; vyt[:, :, hd] = 1
 gate = torch.randn(H, device=dev); att = torch.empty(N * T, D, device=dev, dtype=bf)
 ops.attention(q, k, vt, ky, vyt, gate, att, hd=hd); torch.cuda.synchronize()
 tr = torch.zeros(256, dtype=torch.int64, device=dev)
