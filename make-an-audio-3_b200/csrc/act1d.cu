@@ -16,6 +16,8 @@
 #include "host_common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace ma3 {
 
 __constant__ float c_fdn[12];  // f
@@ -259,6 +261,180 @@ __global__ void __launch_bounds__(kActThreads, MA3_ACT_MINBLOCKS) act1d_kernel(c
   }
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-core variant
+// The fp32 kernel above is bound by the FMA pipe (24 filter FMAs per element against 4 bytes of HBM traffic).  This
+// variant moves both 12-tap filters onto the tensor cores as small banded-Toeplitz products, which leaves the FP32 / SFU
+// pipes with only the Snake non-linearity (fp16 in / fp16 out, T % 8 == 0):
+//   stage 1  U^T[16 ch x 16 samples] = X^T[16 ch x 16 rows] . G^T      (2 x mma.m16n8k16; X^T via ldmatrix.trans)
+//   snake    s = u + sin^2(a u) / b on the fp32 accumulator fragments, replicate padding of s at the sequence ends
+//   stage 2  out^T[16 ch x 8] = [S_prev | S_cur]^T[16 ch x 32 samples] . F^T   (2 x mma; the accumulator fragment of
+//            stage 1 is exactly the A fragment stage 2 needs, so s never leaves registers)
+// and the result goes back to channels-last through stmatrix.trans + a coalesced 16-byte copy.  A warp owns 16 channels
+// and a run of TS outputs; sample block j covers 2x-rate samples [2 tw0 - 6 + 16 j, +16) and needs input rows
+// [tw0 - 6 + 8 j, +16); output group j (8 outputs from tw0 + 8 j) consumes blocks j and j + 1.
+constexpr int kMmaTS = 64;                 // outputs per warp segment
+constexpr int kMmaWarps = 8;
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ void stmatrix_x2_trans(uint32_t addr, uint32_t r0, uint32_t r1) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(addr), "r"(r0), "r"(r1) : "memory");
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// up-sampling tap of 2x-rate sample i (block-local) on input row k (block-local): u[mb+i] = sum_k G[i][k] x[base+k]
+__device__ __forceinline__ float up_coef(int i, int k) {
+  const int kk = k - (i >> 1) - (i & 1);
+  return (kk >= 0 && kk <= 5) ? c_fup[((i & 1) ? 10 : 11) - 2 * kk] : 0.f;
+}
+// low-pass tap of window sample k (0..31) for output n (0..7): out[t0+n] = sum_k F[k][n] s[2 t0 - 6 + k]
+__device__ __forceinline__ float dn_coef(int k, int n) {
+  const int j = k - 2 * n - 1;
+  return (j >= 0 && j <= 11) ? c_fdn[j] : 0.f;
+}
+
+__global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __half* __restrict__ x, __half* __restrict__ out,
+                                                                      const float* __restrict__ alpha,
+                                                                      const float* __restrict__ beta, int B, int T, int C,
+                                                                      int CT, int tiles_c, int tiles_t, int logscale) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cgs = CT >> 4;                   // 16-channel groups per tile
+  const int tsplit = kMmaWarps / cgs;        // time segments per tile
+  const int TB = tsplit * kMmaTS;
+  const int rows = TB + 16;
+  const int pitch = CT * 2 + 16;             // bytes; +16 keeps the 8 rows of an ldmatrix / stmatrix on distinct banks
+  const int vpr = CT >> 3;                   // 16-byte vectors per row
+  const size_t in_bytes = (size_t)rows * pitch;
+  uint8_t* os = smem_raw + 2 * in_bytes;     // output tile [TB][pitch]
+  const int total = tiles_c * tiles_t * B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int cgi = warp % cgs, seg = warp / cgs;
+
+  // constant B fragments: G^T (two 8-sample halves) and F^T (two 16-sample k-steps)
+  uint32_t bu[2][2], bd[2][2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int k = 2 * tq + 8 * r;
+      bu[hh][r] = pack_f16(up_coef(8 * hh + g, k), up_coef(8 * hh + g, k + 1));
+      bd[hh][r] = pack_f16(dn_coef(16 * hh + k, g), dn_coef(16 * hh + k + 1, g));
+    }
+  }
+
+  auto decode = [&](int item, int& b, int& tb0, int& c0) {
+    const int tile_c = item % tiles_c;
+    const int rest = item / tiles_c;
+    c0 = tile_c * CT;
+    tb0 = (rest % tiles_t) * TB;
+    b = rest / tiles_t;
+  };
+  // stage rows [tb0 - 6, tb0 + TB + 10) x CT, row index clamped to [0, T-1] (= replicate padding of x)
+  auto prefetch = [&](int item, int buf) {
+    int b, tb0, c0;
+    decode(item, b, tb0, c0);
+    const __half* xb = x + (long long)b * T * C + c0;
+    uint8_t* tile = smem_raw + buf * in_bytes;
+    for (int idx = threadIdx.x; idx < rows * vpr; idx += kMmaWarps * 32) {
+      const int r = idx / vpr, v = idx - r * vpr;
+      int gr = tb0 - 6 + r;
+      gr = gr < 0 ? 0 : (gr > T - 1 ? T - 1 : gr);
+      cp_async16(tile + (size_t)r * pitch + v * 16, xb + (long long)gr * C + v * 8);
+    }
+  };
+
+  int it = 0;
+  if ((int)blockIdx.x < total) prefetch(blockIdx.x, 0);
+  cp_async_commit();
+  for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = item + gridDim.x;
+    if (next < total) prefetch(next, buf ^ 1);
+    cp_async_commit();
+    int b, tb0, c0;
+    decode(item, b, tb0, c0);
+    const int cw = c0 + cgi * 16;            // first channel of this warp
+    float a0 = alpha[cw + g], a1 = alpha[cw + g + 8];
+    float b0 = beta ? beta[cw + g] : a0, b1 = beta ? beta[cw + g + 8] : a1;
+    if (logscale) { a0 = __expf(a0); a1 = __expf(a1); b0 = __expf(b0); b1 = __expf(b1); }
+    const float ib0 = 1.f / (b0 + 1e-9f), ib1 = 1.f / (b1 + 1e-9f);
+    cp_async_wait<1>();
+    __syncthreads();
+    const int tw0 = tb0 + seg * kMmaTS;      // first output of this warp's segment
+    if (tw0 < T) {
+      const uint32_t xs = smem_u32(smem_raw + buf * in_bytes);
+      const int ngroups = min(kMmaTS, T - tw0) >> 3;
+      // ldmatrix row address of this lane for block 0: matrix mi = lane / 8 -> rows (mi / 2) * 8 + lane % 8, channels
+      // (mi % 2) * 8 of the warp's group
+      const uint32_t xaddr0 = xs + (uint32_t)((seg * kMmaTS + ((lane >> 4) << 3) + (lane & 7)) * pitch) +
+                              (uint32_t)((cgi * 16 + ((lane >> 3) & 1) * 8) * 2);
+      const uint32_t oaddr0 = smem_u32(os) + (uint32_t)((seg * kMmaTS + (lane & 7)) * pitch) +
+                              (uint32_t)((cgi * 16 + ((lane >> 3) & 1) * 8) * 2);
+      uint32_t sp[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 3
+      for (int j = 0; j <= ngroups; ++j) {
+        uint32_t xa[4];
+        ldmatrix_x4_trans(xa, xaddr0 + (uint32_t)(j * 8 * pitch));
+        float ul[4] = {0.f, 0.f, 0.f, 0.f}, uh[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(ul, xa, bu[0][0], bu[0][1]);
+        mma_f16(uh, xa, bu[1][0], bu[1][1]);
+        // snake: [0], [1] -> channel g; [2], [3] -> channel g + 8
+        float sl[4], sh[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = e < 2 ? a0 : a1, ib = e < 2 ? ib0 : ib1;
+          const float s0 = __sinf(ul[e] * a), s1 = __sinf(uh[e] * a);
+          sl[e] = fmaf(ib * s0, s0, ul[e]);
+          sh[e] = fmaf(ib * s1, s1, uh[e]);
+        }
+        // replicate padding of the activated signal: samples m < 0 take s[0], samples m > 2T-1 take s[2T-1]
+        const int mb = 2 * tw0 - 6 + 16 * j;
+        if (mb < 0) {             // only block 0 of a sequence: m = 0 is local sample 6 (lane tq = 3, low half, e = 0)
+          const float v0 = __shfl_sync(0xffffffffu, sl[0], (lane & ~3) | 3);
+          const float v1 = __shfl_sync(0xffffffffu, sl[2], (lane & ~3) | 3);
+          if (tq < 3) { sl[0] = v0; sl[1] = v0; sl[2] = v1; sl[3] = v1; }
+        }
+        if (mb + 15 > 2 * T - 1) {   // last block of a sequence (T % 8 == 0): m = 2T-1 is local sample 5 (tq = 2, e = 1)
+          const float v0 = __shfl_sync(0xffffffffu, sl[1], (lane & ~3) | 2);
+          const float v1 = __shfl_sync(0xffffffffu, sl[3], (lane & ~3) | 2);
+          if (tq == 3) { sl[0] = v0; sl[1] = v0; sl[2] = v1; sl[3] = v1; }
+          sh[0] = v0; sh[1] = v0; sh[2] = v1; sh[3] = v1;
+        }
+        uint32_t sc[4] = {pack_f16(sl[0], sl[1]), pack_f16(sl[2], sl[3]), pack_f16(sh[0], sh[1]), pack_f16(sh[2], sh[3])};
+        if (j > 0) {
+          float o[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_f16(o, sp, bd[0][0], bd[0][1]);
+          mma_f16(o, sc, bd[1][0], bd[1][1]);
+          stmatrix_x2_trans(oaddr0 + (uint32_t)((j - 1) * 8 * pitch), pack_f16(o[0], o[1]), pack_f16(o[2], o[3]));
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sp[e] = sc[e];
+      }
+    }
+    __syncthreads();
+    // coalesced copy of the output tile to channels-last global memory
+    {
+      __half* ob = out + ((long long)b * T + tb0) * C + c0;
+      const int nrows = min(TB, T - tb0);
+      for (int idx = threadIdx.x; idx < nrows * vpr; idx += kMmaWarps * 32) {
+        const int r = idx / vpr, v = idx - r * vpr;
+        *reinterpret_cast<uint4*>(ob + (long long)r * C + v * 8) = *reinterpret_cast<const uint4*>(os + (size_t)r * pitch + v * 16);
+      }
+    }
+  }
+}
+
 static bool g_filter_set = false;
 
 }  // namespace ma3
@@ -290,6 +466,29 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
   MA3_REQUIRE(x && out && alpha && B > 0 && T > 0, "act1d: null pointer or empty");
   MA3_REQUIRE(C % 16 == 0, "act1d: C=%d must be a multiple of 16 (pad channels)", C);
   MA3_REQUIRE(aligned16(x) && aligned16(out), "act1d: pointers must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool no_mma = getenv("MA3_ACT_FP32") != nullptr && getenv("MA3_ACT_FP32")[0] == '1';
+  if (!no_mma && in_dtype == MA3_F16 && out_dtype == MA3_F16 && T % 8 == 0) {
+    // tensor-core variant (filters as banded-Toeplitz MMAs)
+    const int CT = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
+    const int TB = (kMmaWarps / (CT / 16)) * kMmaTS;
+    const int tiles_c = C / CT, tiles_t = (T + TB - 1) / TB;
+    const long long total = (long long)tiles_c * tiles_t * B;
+    const int pitch = CT * 2 + 16;
+    const size_t smem = 2 * (size_t)(TB + 16) * pitch + (size_t)TB * pitch;
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(act1d_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      configured = true;
+    }
+    long long gridl = 3LL * num_sms();
+    if (gridl > total) gridl = total;
+    cudaError_t le = launch_pdl(act1d_mma_kernel, dim3((unsigned)gridl), dim3(kMmaWarps * 32), smem, st, 1,
+                                (const __half*)x, (__half*)out, alpha, beta, B, T, C, CT, tiles_c, tiles_t, logscale);
+    if (le != cudaSuccess) MA3_FAIL((int)le, "act1d launch: %s", cudaGetErrorString(le));
+    MA3_LAUNCH_CHECK("act1d");
+    return 0;
+  }
   const int CT = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
   const int groups = kActThreads / (CT / 2);
   const int TB = groups * kTT;
@@ -300,7 +499,6 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
   long long gridl = (long long)(MA3_ACT_MINBLOCKS > 2 ? MA3_ACT_MINBLOCKS : 2) * num_sms();
   if (gridl > total) gridl = total;
   dim3 grid((unsigned)gridl);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t le = cudaSuccess;
 #define ACT_CASE(TI, TO)                                                                                            \
   do {                                                                                                              \

@@ -375,11 +375,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
-  return u64_as_f2(d);
-}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 
 // O[:, 0..HDO) *= alpha, in place in TMEM (thread <-> row)
 template <int HDO>
@@ -432,16 +428,73 @@ __device__ __forceinline__ void drain_o(uint32_t tO, float f, uint32_t (&stash)[
   }
 }
 
+constexpr int kAttn2Threads = 288;   // warps 0-7: softmax, two threads per query row (32 keys each); warp 8: TMA + MMA
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Segment epilogue over this thread's O columns [C0, C1) in pieces of 8: kFinal = false parks O * f as packed bf16
+// pairs, kFinal = true adds the parked self-attention result and writes the 16-bit output row.
+template <int C0, int C1, bool kFinal, int NS>
+__device__ __forceinline__ void drain_cols(uint32_t tO, float f, uint32_t (&stash)[NS], uint16_t* orow, bool bf16,
+                                           bool store) {
+  if constexpr (C0 < C1) {
+    uint32_t r[8];
+    tmem_ld8(tO + C0, r);
+    tmem_ld_wait();
+    constexpr int SI = (C0 % (2 * NS)) / 2;   // stash index of this group's first pair (thread-local)
+    if constexpr (!kFinal) {
+#pragma unroll
+      for (int e = 0; e < 8; e += 2)
+        stash[SI + (e >> 1)] = pack_bf16(__uint_as_float(r[e]) * f, __uint_as_float(r[e + 1]) * f);
+    } else {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        const float2 sv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&stash[SI + (e >> 1)]));
+        v[e] = fmaf(__uint_as_float(r[e]), f, sv.x);
+        v[e + 1] = fmaf(__uint_as_float(r[e + 1]), f, sv.y);
+      }
+      uint4 u;
+      if (bf16)
+        u = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      else
+        u = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
+      if (store) *reinterpret_cast<uint4*>(orow + C0) = u;
+    }
+    drain_cols<C0 + 8, C1, kFinal, NS>(tO, f, stash, orow, bf16, store);
+  }
+}
+
+// O[:, C0..C1) *= alpha in place (8-column pieces)
+template <int C0, int C1>
+__device__ __forceinline__ void rescale_cols(uint32_t tO, float alpha) {
+  if constexpr (C0 < C1) {
+    uint32_t r[8];
+    tmem_ld8(tO + C0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+    tmem_st8(tO + C0, r);
+    rescale_cols<C0 + 8, C1>(tO, alpha);
+  }
+}
+
 template <int HDP, int HD, int BKV>
-__global__ void __launch_bounds__(kAttnThreads, 2) attn2_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_constant__ AttnParams p) {
   static_assert(BKV == 64, "one 64-key chunk per KV tile");
   constexpr int HDC = HDP / 64;
   constexpr int HDO = (HD + 1 + 15) / 16 * 16;   // O columns: HD values, the row-sum column, zero padding
   constexpr int KS = (HD + 15) / 16;             // k-steps of S = Q K^T that carry data (pad columns are zero)
   static_assert(HDO <= HDP, "needs a spare V^T row for the row sums");
+  // column split of O between the two threads of a row (multiples of 8; thread 0 takes the larger part)
+  constexpr int HSPLIT = ((HD / 8 + 1) / 2) * 8;
+  constexpr int NSTASH = HSPLIT / 2;
   constexpr uint32_t kQBytes = 128 * HDP * 2;
   constexpr uint32_t kKBytes = BKV * HDP * 2;
-  constexpr uint32_t kStageBytes = 2 * kKBytes;
+  constexpr uint32_t kVBytes = HDO * 128;        // only the HDO rows of V^T the PV MMA reads are staged
+  constexpr uint32_t kStageBytes = kKBytes + kVBytes;
   constexpr uint32_t kPBytes = 128 * BKV * 2;
   constexpr uint32_t kTmemCols = 256;            // S0: [0, 64)  S1: [64, 128)  O: [128, 128 + HDO)
   static_assert(2 * BKV + HDO <= 256, "TMEM budget");
@@ -460,15 +513,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn2_kernel(const __grid_con
   uint64_t* p_full = bars + 11;
   uint64_t* o_full = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* xch = reinterpret_cast<float*>(bars + 16);   // [tile parity][column half][row]: per-tile row maxima
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, ns = blockIdx.z;
   const int bh = ns * p.H + h;
   const int n_self = (p.T + BKV - 1) / BKV, n_cross = (p.L + BKV - 1) / BKV;
   const int n_tiles = n_self + n_cross;
-  const int n_active = min(4, (p.T - q0 + 31) / 32);   // softmax warps owning at least one query row < T
+  const int n_active = min(4, (p.T - q0 + 31) / 32);   // 32-row groups owning at least one query row < T
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmVt);
       prefetch_tmap(&p.tmKy); prefetch_tmap(&p.tmVyt);
@@ -478,7 +532,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn2_kernel(const __grid_con
         mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         mbar_init(&s_full[i], 1);
       }
-      mbar_init(p_full, 32 * n_active);
+      mbar_init(p_full, 2 * n_active);   // one arrival per active softmax warp
       mbar_init(o_full, 1);
       fence_barrier_init();
     }
@@ -493,7 +547,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn2_kernel(const __grid_con
   pdl_wait();
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * BKV;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       auto load_k = [&](int i) {
         const int st = i & 1;
@@ -510,22 +564,23 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn2_kernel(const __grid_con
         const bool cross = i >= n_self;
         const int kv0 = (cross ? i - n_self : i) * BKV;
         uint8_t* dV = sKV + st * kStageBytes + kKBytes;
-        mbar_arrive_expect_tx(&v_full[st], kKBytes);
+        mbar_arrive_expect_tx(&v_full[st], kVBytes);
         tma_load_3d(dV, cross ? &p.tmVyt : &p.tmVt, &v_full[st], kv0, 0, bh);
       };
       const uint32_t idesc_s = umma_idesc(128, BKV, p.dtype == MA3_BF16 ? 1 : 0);
       const uint32_t idesc_o = umma_idesc(128, HDO, p.dtype == MA3_BF16 ? 1 : 0);
+      const uint64_t dq0 = umma_desc_kmajor(smem_u32(sQ), 128);
+      const uint64_t dp0 = umma_desc_kmajor(smem_u32(sP), 128);
+      const uint64_t dk0 = umma_desc_kmajor(smem_u32(sKV), 128);
+      const uint64_t dv0 = umma_desc_kmajor(smem_u32(sKV + kKBytes), 128);
       auto issue_s = [&](int i) {
         const int st = i & 1;
         mbar_wait(&k_full[st], (i >> 1) & 1);
-        tc_fence_after();
-        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sKV + st * kStageBytes);
+        const uint64_t db = dk0 + (uint64_t)(st * (kStageBytes >> 4));
 #pragma unroll
-        for (int k = 0; k < KS; ++k) {
-          const uint64_t da = umma_desc_kmajor(qa + (k / 4) * (128 * 128) + (k % 4) * 32, 128);
-          const uint64_t db = umma_desc_kmajor(ka + (k / 4) * (BKV * 128) + (k % 4) * 32, 128);
-          umma_f16(tmem_S + st * BKV, da, db, idesc_s, k != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < KS; ++k)
+          umma_f16(tmem_S + st * BKV, dq0 + (uint64_t)((k / 4) * (128 * 128 / 16) + (k % 4) * 2),
+                   db + (uint64_t)((k / 4) * (BKV * 128 / 16) + (k % 4) * 2), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[st]);
         umma_commit(&k_empty[st]);
       };
@@ -550,14 +605,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn2_kernel(const __grid_con
         attn_trace(p, i, 9);
         mbar_wait(&v_full[st], (i >> 1) & 1);
         tc_fence_after();
-        const uint32_t pa = smem_u32(sP), va = smem_u32(sKV + st * kStageBytes + kKBytes);
-        const bool fresh = i == 0 || i == n_self;   // first tile of a segment overwrites O
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t da = umma_desc_kmajor(pa + k * 32, 128);
-          const uint64_t db = umma_desc_kmajor(va + k * 32, 128);
-          umma_f16(tmem_O, da, db, idesc_o, (k != 0 || !fresh) ? 1u : 0u);
-        }
+        const uint64_t dv = dv0 + (uint64_t)(st * (kStageBytes >> 4));
+        const uint32_t fresh = (i == 0 || i == n_self) ? 0u : 1u;   // first tile of a segment overwrites O
+        umma_f16(tmem_O, dp0, dv, idesc_o, fresh);
+        umma_f16(tmem_O, dp0 + 2, dv + 2, idesc_o, 1u);
+        umma_f16(tmem_O, dp0 + 4, dv + 4, idesc_o, 1u);
+        umma_f16(tmem_O, dp0 + 6, dv + 6, idesc_o, 1u);
         umma_commit(o_full);
         umma_commit(&v_empty[st]);
         attn_trace(p, i, 10);
@@ -568,15 +621,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn2_kernel(const __grid_con
         }
       }
     }
-  } else if (warp < n_active) {
-    const int row = warp * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  } else if ((warp & 3) < n_active) {
+    const int qw = warp & 3, half = warp >> 2;      // TMEM lane quarter; which 32 keys of a tile / which O columns
+    const int row = qw * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(qw * 32) << 16;
     const uint32_t tO = tmem_O + lane_base;
     const bool bf16 = p.dtype == MA3_BF16;
     uint8_t* prow = sP + row * 128;
-    uint32_t stash[HD / 2];
+    uint32_t stash[NSTASH];
 #pragma unroll
-    for (int e = 0; e < HD / 2; ++e) stash[e] = 0u;
+    for (int e = 0; e < NSTASH; ++e) stash[e] = 0u;
     uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + ((long long)ns * p.T + q0 + row) * p.D + (long long)h * HD;
     const bool row_ok = q0 + row < p.T;
     int it = 0;
@@ -591,50 +645,56 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn2_kernel(const __grid_con
         mbar_wait(&s_full[it & 1], (it >> 1) & 1);
         if (tr) attn_trace(p, it, 1);
         tc_fence_after();
-        const uint32_t tS = tmem_S + (it & 1) * BKV + lane_base;
-        uint32_t s[64];
-        tmem_ld_n<32>(tS, s);
-        tmem_ld_n<32>(tS + 32, s + 32);
+        uint32_t s[32];
+        tmem_ld_n<32>(tmem_S + (it & 1) * BKV + half * 32 + lane_base, s);
         tmem_ld_wait();
-        const int valid = kvlen - j * BKV;
-        if (valid < BKV) {   // ragged last tile of a segment: keys beyond the sequence get -inf
+        const int valid = kvlen - j * BKV - half * 32;   // keys of this thread's half that exist
+        if (valid < 32) {   // ragged last tile of a segment: keys beyond the sequence get -inf
 #pragma unroll
-          for (int e = 0; e < 64; ++e)
+          for (int e = 0; e < 32; ++e)
             if (e >= valid) s[e] = 0xff800000u;
         }
         float mx4[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 4]));
 #pragma unroll
-        for (int e = 8; e < 64; e += 8) {
+        for (int e = 8; e < 32; e += 8) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) mx4[c] = fmax3(mx4[c], __uint_as_float(s[e + c]), __uint_as_float(s[e + c + 4]));
         }
-        const float mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]);
+        float mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]);
+        // row maximum over both halves: exchange with the partner thread (warp ^ 4) through shared memory
+        float* xs = xch + (it & 1) * 256;
+        xs[half * 128 + row] = mx;
+        named_bar_sync(1 + qw, 64);
+        mx = fmaxf(mx, xs[(half ^ 1) * 128 + row]);
         if (tr) attn_trace(p, it, 2);
         bool waited = false;
         if (j == 0) {
           m = mx;
-        } else if (__any_sync(0xffffffffu, mx > m + 8.f)) {
+        } else if (__any_sync(0xffffffffu, mx > m + 8.f)) {   // identical decision in both warps of the pair
           mbar_wait(o_full, (it - 1) & 1);   // PV(it-1) complete: O may be modified
           tc_fence_after();
           waited = true;
           const float m_new = fmaxf(m, mx);
-          rescale_o<HDO>(tO, ex2_approx(m - m_new));
+          const float alpha = ex2_approx(m - m_new);
+          if (half == 0) rescale_cols<0, HSPLIT>(tO, alpha);
+          else rescale_cols<HSPLIT, HDO>(tO, alpha);
+          tmem_st_wait();
           m = m_new;
         }
         if (tr) attn_trace(p, it, 3);
-        uint32_t pk[32];
+        uint32_t pk[16];
         const float2 nm = make_float2(-m, -m);
         if (bf16) {
 #pragma unroll
-          for (int e = 0; e < 64; e += 2) {
+          for (int e = 0; e < 32; e += 2) {
             const float2 d = fadd2(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), nm);
             pk[e >> 1] = pack_bf16(ex2_approx(d.x), ex2_approx(d.y));
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 64; e += 2) {
+          for (int e = 0; e < 32; e += 2) {
             const float2 d = fadd2(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), nm);
             pk[e >> 1] = pack_f16(ex2_approx(d.x), ex2_approx(d.y));
           }
@@ -643,29 +703,37 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn2_kernel(const __grid_con
         if (it > 0 && !waited) mbar_wait(o_full, (it - 1) & 1);   // PV(it-1) has finished reading P
         if (tr) attn_trace(p, it, 5);
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          *reinterpret_cast<uint4*>(prow + ((u ^ (row & 7)) * 16)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(prow + (((half * 4 + u) ^ (row & 7)) * 16)) =
+              make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
         tc_fence_before();
         fence_proxy_async_smem();
-        mbar_arrive(p_full);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
         if (tr) attn_trace(p, it, 6);
       }
       mbar_wait(o_full, (it - 1) & 1);
       tc_fence_after();
-      uint32_t rl[16];
-      tmem_ld16(tO + HDO - 16, rl);
+      uint32_t rl[8];
+      tmem_ld8(tO + (HD / 8) * 8, rl);
       tmem_ld_wait();
-      const float l = __uint_as_float(rl[HD - (HDO - 16)]);
+      const float l = __uint_as_float(rl[HD % 8]);
       const float f = __fdividef(seg ? tanhf(p.gate[h]) : 1.f, l);
-      if (seg == 0 && n_cross > 0) drain_o<HD, false>(tO, f, stash, orow, bf16, row_ok);
-      else drain_o<HD, true>(tO, f, stash, orow, bf16, row_ok);
+      const bool park = seg == 0 && n_cross > 0;
+      if (half == 0) {
+        if (park) drain_cols<0, HSPLIT, false, NSTASH>(tO, f, stash, orow, bf16, row_ok);
+        else drain_cols<0, HSPLIT, true, NSTASH>(tO, f, stash, orow, bf16, row_ok);
+      } else {
+        if (park) drain_cols<HSPLIT, HD, false, NSTASH>(tO, f, stash, orow, bf16, row_ok);
+        else drain_cols<HSPLIT, HD, true, NSTASH>(tO, f, stash, orow, bf16, row_ok);
+      }
       tc_fence_before();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -673,7 +741,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn2_kernel(const __grid_con
 
 template <int HDP, int HD, int BKV>
 static int launch_attn2(const AttnParams& p, int NS, cudaStream_t st) {
-  constexpr size_t smem = 128 * HDP * 2 + 2 * (2 * BKV * HDP * 2) + 128 * BKV * 2 + 256;
+  constexpr int HDO = (HD + 1 + 15) / 16 * 16;
+  constexpr size_t smem = 128 * HDP * 2 + 2 * (BKV * HDP * 2 + HDO * 128) + 128 * BKV * 2 + 128 + 2048;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn2_kernel<HDP, HD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -681,7 +750,7 @@ static int launch_attn2(const AttnParams& p, int NS, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((unsigned)((p.T + 127) / 128), (unsigned)p.H, (unsigned)NS);
-  cudaError_t le = launch_pdl(attn2_kernel<HDP, HD, BKV>, grid, dim3(kAttnThreads), smem, st, 1, p);
+  cudaError_t le = launch_pdl(attn2_kernel<HDP, HD, BKV>, grid, dim3(kAttn2Threads), smem, st, 1, p);
   if (le != cudaSuccess) MA3_FAIL((int)le, "attention launch: %s", cudaGetErrorString(le));
   MA3_LAUNCH_CHECK("attention");
   return 0;
@@ -725,6 +794,12 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
   const int BKV = 64;
   const uint64_t nbh = (uint64_t)NS * H;
   int rc;
+  // v2 (O resident in TMEM, row sums through the ones row of V^T) whenever the padded head has a spare row;
+  // MA3_ATTN_V1=1 forces the first-generation kernel (diagnostics)
+  static const bool force_v1 = getenv("MA3_ATTN_V1") != nullptr && getenv("MA3_ATTN_V1")[0] == '1';
+  const bool v2 = !force_v1 && ((hdp == 64 && (hd == 16 || hd == 24 || hd == 32 || hd == 48)) ||
+                                (hdp == 128 && (hd == 72 || hd == 96)));
+  const uint32_t vrows = v2 ? (uint32_t)((hd + 1 + 15) / 16 * 16) : (uint32_t)hdp;   // V^T rows staged per tile
   {
     uint64_t dims[3] = {(uint64_t)hdp, (uint64_t)T, nbh};
     uint64_t str[2] = {(uint64_t)hdp * 2, (uint64_t)T * hdp * 2};
@@ -735,7 +810,7 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
   {
     uint64_t dims[3] = {(uint64_t)T, (uint64_t)hdp, nbh};
     uint64_t str[2] = {(uint64_t)Tp * 2, (uint64_t)hdp * Tp * 2};
-    uint32_t box[3] = {64, (uint32_t)hdp, 1};
+    uint32_t box[3] = {64, vrows, 1};
     if ((rc = encode_tmap(&p.tmVt, vt, 2, 3, dims, str, box, 128))) return rc;
   }
   if (L > 0) {
@@ -745,17 +820,14 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
     if ((rc = encode_tmap(&p.tmKy, ky, 2, 3, dims, str, boxk, 128))) return rc;
     uint64_t dimv[3] = {(uint64_t)L, (uint64_t)hdp, nbh};
     uint64_t strv[2] = {(uint64_t)Lp * 2, (uint64_t)hdp * Lp * 2};
-    uint32_t boxv[3] = {64, (uint32_t)hdp, 1};
+    uint32_t boxv[3] = {64, vrows, 1};
     if ((rc = encode_tmap(&p.tmVyt, vyt, 2, 3, dimv, strv, boxv, 128))) return rc;
   } else {
     p.tmKy = p.tmK;
     p.tmVyt = p.tmVt;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // v2 (O resident in TMEM, row sums through the ones row of V^T) whenever the padded head has a spare row;
-  // MA3_ATTN_V1=1 forces the first-generation kernel (diagnostics)
-  static const bool force_v1 = getenv("MA3_ATTN_V1") != nullptr && getenv("MA3_ATTN_V1")[0] == '1';
-  if (!force_v1) {
+  if (v2) {
     if (hdp == 64 && hd == 16) return launch_attn2<64, 16, 64>(p, NS, st);
     if (hdp == 64 && hd == 24) return launch_attn2<64, 24, 64>(p, NS, st);
     if (hdp == 64 && hd == 32) return launch_attn2<64, 32, 64>(p, NS, st);

@@ -150,6 +150,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- CTA pair (cta_group::2) variants
@@ -287,16 +292,10 @@ __host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int fmt) {
 // ---------------------------------------------------------------- packed fp32x2 math (Blackwell FFMA2 / FMUL2)
 __device__ __forceinline__ unsigned long long f2_as_u64(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
 __device__ __forceinline__ float2 u64_as_f2(unsigned long long v) { return *reinterpret_cast<float2*>(&v); }
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)), "l"(f2_as_u64(c)));
-  return u64_as_f2(d);
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
-  return u64_as_f2(d);
-}
+// Compiler intrinsics rather than inline PTX: ptxas can then feed coefficients straight from uniform registers
+// (FFMA2 R, R.F32x2, UR.F32, R.F32x2 -- a scalar constant broadcast to both lanes costs no vector register or MOV).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 
 // ---------------------------------------------------------------- misc math
 __device__ __forceinline__ float ex2_approx(float x) {

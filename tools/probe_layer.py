@@ -1,5 +1,6 @@
 """GPU probe: per-kernel timing of one XL DiT block at the bench shapes (N=16, T=312, L=154)."""
 import sys, os, math
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ma3_b200 import ops, lib as L
@@ -23,38 +24,8 @@ gate = torch.randn(H, device=dev); att = torch.empty(M, D, device=dev, dtype=bf)
 ang = torch.outer(torch.arange(1000, device=dev).float(), 1.0 / (10000 ** (torch.arange(0, hd, 2, device=dev).float() / hd)))
 rope = torch.stack([ang.cos(), ang.sin()], -1).contiguous()
 qs = math.log2(math.e) / math.sqrt(hd)
-flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
-def bench(name, fn, flops=0, bytes_=0, n=10):
-    """Two timings per kernel: `cold` = one launch after an L2 flush (CUDA events; includes any CPU launch gap when
-    the host has not run ahead), `graph` = 10 launches captured in a CUDA graph and replayed (no host in the loop,
-    operands L2-warm as in the sampler loop)."""
-    for _ in range(2): fn()
-    torch.cuda.synchronize()
-    tot = 0.0
-    for _ in range(n):
-        flush.sum()   # evict L2 with clean lines
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    ms = tot / n
-    g = torch.cuda.CUDAGraph()
-    st = torch.cuda.Stream()
-    with torch.cuda.stream(st):
-        fn(); torch.cuda.synchronize()
-        with torch.cuda.graph(g, stream=st):
-            for _ in range(10): fn()
-    torch.cuda.synchronize()
-    g.replay(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    e0.record()
-    for _ in range(3): g.replay()
-    e1.record(); torch.cuda.synchronize()
-    mg = e0.elapsed_time(e1) / 30
-    s = f"{name:44s} cold {ms*1e3:7.1f} us  graph {mg*1e3:7.1f} us"
-    if flops: s += f"  {flops/mg/1e9:7.1f} TFLOP/s"
-    if bytes_: s += f"  {bytes_/mg/1e6:7.1f} GB/s"
-    print(s, flush=True)
+from _bench import bench
 
 bench("rmsnorm_modulate", lambda: ops.rmsnorm_modulate(h, wn, u, mod=mod, shift_off=0, scale_off=D, rows_per_sample=T), bytes_=M * D * 6)
 bench("qkv gemm + rope", lambda: ops.gemm(u, wqkv, M=M, N=3 * D, K=D, epi=L.EPI_QKV_ROPE, q_out=q, k_out=k, vt_out=vt, rope=rope, model_dim=D, head_dim=hd, head_dim_pad=hdp, tokens=T, tokens_pad=Tp, q_scale=qs), flops=2.0 * M * 3 * D * D)

@@ -4,19 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ma3_b200 import ops, lib as L
 dev = "cuda"
-flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-def bench(name, fn, flops=0, bytes_=0, n=6):
-    for _ in range(2): fn()
-    torch.cuda.synchronize(); tot = 0.0
-    for _ in range(n):
-        flush.sum()
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); tot += e0.elapsed_time(e1)
-    ms = tot / n
-    s = f"{name:28s} {ms*1e3:8.1f} us"
-    if flops: s += f"  {flops/ms/1e9:7.1f} TFLOP/s"
-    if bytes_: s += f"  {bytes_/ms/1e6:7.1f} GB/s"
-    print(s, flush=True)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _bench import bench
 B = 8
 only_act = len(sys.argv) > 1 and sys.argv[1] == "act"
 for (C, Tt, kk) in [(768, 2496, 11), (384, 9984, 7), (192, 19968, 7), (96, 39936, 7), (48, 79872, 7), (32, 159744, 7)]:
