@@ -521,6 +521,18 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
   const int n_self = (p.T + BKV - 1) / BKV, n_cross = (p.L + BKV - 1) / BKV;
   const int n_tiles = n_self + n_cross;
   const int n_active = min(4, (p.T - q0 + 31) / 32);   // 32-row groups owning at least one query row < T
+  // diagnostics: per-CTA (SM id, start, end) in nanoseconds of the global timer (tools/probe_trace_attn.py)
+  long long* cta_rec = nullptr;
+  if (p.trace && threadIdx.x == 0) {
+    cta_rec = p.trace + 256 + 4 * ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+    unsigned smid;
+    unsigned long long t0;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    cta_rec[0] = smid;
+    cta_rec[1] = (long long)t0;
+    cta_rec[3] = clock64();
+  }
 
   if (warp == 8) {
     if (lane == 0) {
@@ -733,6 +745,12 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
+  if (cta_rec) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    cta_rec[2] = (long long)t1;
+    cta_rec[3] = clock64() - cta_rec[3];
+  }
   if (warp == 8) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);

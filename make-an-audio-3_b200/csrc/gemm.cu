@@ -473,12 +473,97 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
   __syncwarp();
 }
 
+// STORE epilogue for narrow tiles (BN <= 64): thread <-> output row, all BN columns of the row straight from the
+// TMEM registers to global memory in 8-column (16-byte) pieces.  For the channels-last conv outputs this path serves
+// (rows of 2 * BN contiguous bytes) the warp's stores cover a contiguous span, no shared-memory transpose or warp
+// synchronisation sits in the chain, and the residual pieces are requested before the accumulator is even ready.
+template <int kMaxGroups>
+struct RowRes {
+  uint4 v[kMaxGroups];
+};
+
+__device__ __forceinline__ void unpack16(uint4 u, int dtype, float (&v)[8]) {
+  if (dtype == MA3_BF16) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+  } else {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+  }
+}
+
+// whether the 16-bit residual of this launch can be prefetched as one uint4 per 8-column group
+__device__ __forceinline__ bool rowdirect_res16(const GemmKParams& p) {
+  return p.res != nullptr && p.vec_ok && p.res_dtype != MA3_F32;
+}
+
+__device__ __forceinline__ void rowdirect_prefetch(const GemmKParams& p, int z, int m, int n0, int bn, RowRes<8>& rr) {
+  if (!rowdirect_res16(p) || m >= p.M) return;
+  const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
+  const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res) + (long long)z * p.res_batch_stride + orow * p.res_ld + n0;
+#pragma unroll
+  for (int gq = 0; gq < 8; ++gq)
+    if (gq * 8 < bn && n0 + gq * 8 + 8 <= p.N) rr.v[gq] = *reinterpret_cast<const uint4*>(rp + gq * 8);
+}
+
+__device__ __forceinline__ void rowdirect_group(const GemmKParams& p, int z, int m, int col, const uint32_t* r,
+                                                bool has_pre, uint4 pre, float brow) {
+  // 8 columns [col, col + 8) of row m
+  const int n = min(8, p.N - col);
+  if (n <= 0 || m >= p.M) return;
+  const bool vec = p.vec_ok != 0;
+  const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
+  const long long ooff = (long long)z * p.out_batch_stride + orow * p.out_ld + col;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[e]);
+  if (p.bias) {
+    if (p.bias_per_row) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += brow;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) if (e < n) v[e] += p.bias[col + e];
+    }
+  }
+  if (p.res) {
+    float rv[8];
+    if (has_pre && n == 8) unpack16(pre, p.res_dtype, rv);
+    else load8(p.res, p.res_dtype, (long long)z * p.res_batch_stride + orow * p.res_ld + col, vec, n, rv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += rv[e];
+  }
+  if (p.alpha != 1.f) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+  } else if (p.act == 2) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.5f * v[e] * (1.f + erff(v[e] * 0.70710678118654752f));
+  } else if (p.act == 3) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = tanhf(v[e]);
+  }
+  if (p.accumulate) {
+    float ov[8];
+    load8(p.out, p.out_dtype, ooff, vec, n, ov);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += ov[e];
+  }
+  store8(p.out, p.out_dtype, ooff, vec, n, v);
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile: each
 // CTA stages its own 128 rows of A and HALF of the B tile, the leader issues one M=256 MMA that reads both CTAs' shared
 // memory, and each CTA drains its own 128 accumulator rows from its own TMEM.  Halving the B bytes every SM has to pull
 // through L2 is what lifts the L2-feed bound of the large GEMMs.
-template <int EPI, int CG>
+template <int EPI, int CG, bool kNarrow = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -509,7 +594,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull[i], 1);
-        mbar_init(&tempty[i], kEpiWarps * CG);   // CG = 2: the leader's copy collects both CTAs' epilogue warps
+        // CG = 2: the leader's copy collects both CTAs' epilogue warps; row-direct STORE: one warp set per stage
+        mbar_init(&tempty[i], (kNarrow ? kEpiWarps / 2 : kEpiWarps) * CG);
       }
       fence_barrier_init();
     }
@@ -529,7 +615,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
   // work items: CG = 1 -> 128-row tiles over all CTAs; CG = 2 -> 256-row tiles over CTA pairs
   const int total_tiles = p.tiles_m * p.tiles_n * p.batch;
   const int worker = blockIdx.x / CG, n_workers = gridDim.x / CG;
-  const int kchunks = p.K / p.BK;
+  const int kchunks = (p.K + p.BK - 1) / p.BK;   // a ragged last chunk is zero-filled by TMA (box beyond the tensor)
   const int iters = p.taps * kchunks;
 
   // The producer and the MMA issuer are single threads running dependent instruction chains (~5 clk per instruction):
@@ -642,6 +728,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       const int m0 = (m_t * CG + (int)rank) * kBM + q * 32;
+      if constexpr (kNarrow) {
+        // narrow tiles: the two warp sets take alternate tiles (set = accumulator stage), thread <-> row
+        if (as != half) continue;
+        const int m = m0 + lane, n0 = n_t * p.BN;
+        RowRes<8> rr;
+        rowdirect_prefetch(p, z, m, n0, p.BN, rr);
+        const float brow = (p.bias && p.bias_per_row && m < p.M) ? p.bias[m] : 0.f;
+        const bool pre = rowdirect_res16(p);
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.tmem_stage_cols;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          if (c0 < p.BN) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            rowdirect_group(p, z, m, n0 + c0, r, pre, rr.v[c0 >> 3], brow);
+            if (c0 + 8 < p.BN) rowdirect_group(p, z, m, n0 + c0 + 8, r + 8, pre, rr.v[(c0 >> 3) + 1], brow);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_leader(&tempty[as]);
+          else mbar_arrive(&tempty[as]);
+        }
+        continue;
+      }
       float* stg = staging + ew * (32 * kStagePitch);
       RowCtx rc;
       make_row_ctx<EPI>(p, z, m0, lane, rc);
@@ -695,15 +810,16 @@ static uint32_t pow2_cols(int n) {
   return c;
 }
 
-template <int EPI, int CG>
+template <int EPI, int CG, bool kNarrow>
 static int launch_cg(const GemmKParams& kp, size_t smem, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e =
+        cudaFuncSetAttribute(tap_gemm_kernel<EPI, CG, kNarrow>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(tap_gemm): %s", cudaGetErrorString(e));
     configured = true;
   }
-  cudaError_t e = launch_pdl(tap_gemm_kernel<EPI, CG>, dim3((unsigned)grid), dim3(kGemmThreads), smem, st, CG, kp);
+  cudaError_t e = launch_pdl(tap_gemm_kernel<EPI, CG, kNarrow>, dim3((unsigned)grid), dim3(kGemmThreads), smem, st, CG, kp);
   if (e != cudaSuccess) MA3_FAIL((int)e, "tap_gemm launch: %s", cudaGetErrorString(e));
   MA3_LAUNCH_CHECK("tap_gemm");
   return 0;
@@ -711,7 +827,11 @@ static int launch_cg(const GemmKParams& kp, size_t smem, int grid, cudaStream_t 
 
 template <int EPI>
 static int launch(const GemmKParams& kp, size_t smem, int grid, int cta_group, cudaStream_t st) {
-  return cta_group == 2 ? launch_cg<EPI, 2>(kp, smem, grid, st) : launch_cg<EPI, 1>(kp, smem, grid, st);
+  if constexpr (EPI == MA3_EPI_STORE) {
+    if (kp.BN <= 64)   // narrow tiles: row-direct epilogue
+      return cta_group == 2 ? launch_cg<EPI, 2, true>(kp, smem, grid, st) : launch_cg<EPI, 1, true>(kp, smem, grid, st);
+  }
+  return cta_group == 2 ? launch_cg<EPI, 2, false>(kp, smem, grid, st) : launch_cg<EPI, 1, false>(kp, smem, grid, st);
 }
 
 // Modelled critical path (SM clocks) of one launch for a tile shape.  Per 64-wide k-iteration the tensor pipe needs
@@ -723,7 +843,7 @@ static double tile_cost(const ma3_gemm_t* g, int BN, int CG, int BK) {
   const int workers = num_sms() / CG;
   const long tiles_m = (g->M + kBM * CG - 1) / (kBM * CG), tiles_n = (g->N + BN - 1) / BN;
   const long tiles = tiles_m * tiles_n * g->batch;
-  const long iters = (long)g->taps * (g->K / BK);
+  const long iters = (long)g->taps * ((g->K + BK - 1) / BK);
   const double ks = BK / 64.0;
   const double mma = fmax(2.0 * BN * ks, 95.0 * (BK / 16));
   const double feed = CG == 1 ? 120.0 + 1.5 * BN * ks : 200.0 + 0.6 * BN * ks;
@@ -758,7 +878,9 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
 
   GemmKParams kp;
   memset(&kp, 0, sizeof(kp));
-  const int BK = g->K % 64 == 0 ? 64 : (g->K % 32 == 0 ? 32 : 16);
+  // 64-wide k-chunks whenever K > 32: a ragged last chunk (K = 48, 96, ...) is zero-filled by TMA, which costs idle
+  // tensor-pipe work but a third of the k-iterations (and their fixed pipeline cost) of 16- or 32-wide chunks
+  const int BK = g->K > 32 ? 64 : (g->K > 16 ? 32 : 16);
   int BN = g->tile_n;
   int CG = g->cta_group;
   MA3_REQUIRE(CG >= 0 && CG <= 2, "gemm: cta_group must be 0 (auto), 1 or 2");

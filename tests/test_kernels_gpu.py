@@ -93,6 +93,35 @@ def test_gemm_as_conv1d(ops, k, dil):
     assert rel(y, ref.transpose(1, 2)) < 8e-3
 
 
+@pytest.mark.parametrize("C,k,dil,T", [(48, 7, 5, 1000), (32, 11, 3, 300), (96, 7, 1, 513), (16, 3, 1, 129), (64, 7, 3, 2048)])
+def test_gemm_narrow_conv_epilogue(ops, C, k, dil, T):
+    """Narrow conv layers of the vocoder (C <= 96): ragged 64-wide k-chunks (TMA zero fill beyond K) and, for
+    N <= 64, the row-direct STORE epilogue with prefetched residual, scaling and accumulation (fp16)."""
+    B = 2
+    pad = (k * dil - dil) // 2
+    x = (torch.randn(B, T, C, generator=g(60))).half().cuda()
+    w = (torch.randn(C, C, k, generator=g(61)) / (C * k) ** .5).half().cuda()
+    wp = w.permute(2, 0, 1).contiguous().view(k * C, C)
+    bias = torch.randn(C, generator=g(62)).cuda()
+    res = torch.randn(B, T, C, generator=g(63)).half().cuda()
+    old = torch.randn(B, T, C, generator=g(64)).half().cuda()
+    taps = [(j * dil - pad, j * C) for j in range(k)]
+    ref = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.float(), bias, padding=pad, dilation=dil).transpose(1, 2)
+    y = torch.empty(B, T, C, device="cuda", dtype=torch.float16)
+    ops.gemm(x, wp, M=T, N=C, K=C, batch=B, a_rows=T, a_batch_stride=T * C, b_rows=k * C, taps=taps, out=y,
+             out_batch_stride=T * C, bias=bias)
+    assert rel(y, ref) < 2e-3
+    y2 = old.clone()
+    ops.gemm(x, wp, M=T, N=C, K=C, batch=B, a_rows=T, a_batch_stride=T * C, b_rows=k * C, taps=taps, out=y2,
+             out_batch_stride=T * C, bias=bias, res=res, res_batch_stride=T * C, alpha=1 / 3, accumulate=True)
+    assert rel(y2, (ref + res.float()) / 3 + old.float()) < 2e-3
+    o32 = torch.empty(B, T, 1, device="cuda", dtype=torch.float32)   # conv_post: one output channel, tanh, fp32
+    w1 = wp.view(k, C, C)[:, :1].contiguous().view(k, C)
+    ops.gemm(x, w1, M=T, N=1, K=C, batch=B, a_rows=T, a_batch_stride=T * C, b_rows=k, taps=[(j * dil - pad, j) for j in range(k)],
+             out=o32, out_ld=1, out_batch_stride=T, bias=bias[:1].contiguous(), act=3)
+    assert rel(o32, torch.tanh(ref[..., :1])) < 1e-3
+
+
 def test_gemm_gate_residual_and_swiglu(ops):
     from ma3_b200 import lib as L
     M, N, K, T = 624, 768, 768, 312
