@@ -263,16 +263,24 @@ def main():
                 acc[i] += ev[i].elapsed_time(ev[i + 1]) / reps
         stage_ms = {"sample_cfg_24_steps": round(acc[0], 3), "vae_decode": round(acc[1], 3), "bigvgan": round(acc[2], 3)}
 
-    # live roofline of the dominant kernel: one eager (no graph) pass over the same workload with CUDA events around
-    # every launch on the launching stream
+    # live roofline of the dominant kernel: CUDA events around every launch on the launching stream.  With graphs the
+    # plans are re-captured with the events as graph nodes and replayed once, so each interval is device time of one
+    # kernel with nothing from the host in it; --no-graph brackets the eager launches instead.
     roofline, breakdown = None, None
     if rank == 0:
-        pipe.sampler.use_graph = False
         ops.PROFILE = []
-        torch.cuda.synchronize()
-        pipe.generate(cond, unc, x0, scale=GUIDANCE, timesteps=N_POINTS)
+        if args.no_graph:
+            torch.cuda.synchronize()
+            pipe.generate(cond, unc, x0, scale=GUIDANCE, timesteps=N_POINTS)
+        else:
+            ops.PROFILE_CAPTURED_ONLY = True
+            pipe.sampler._graphs, pipe._tail = {}, {}
+            pipe.generate(cond, unc, x0, scale=GUIDANCE, timesteps=N_POINTS)   # eager pass + capture (events -> nodes)
+            torch.cuda.synchronize()
+            pipe.generate(cond, unc, x0, scale=GUIDANCE, timesteps=N_POINTS)   # replay: the events get their times
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
+        ops.PROFILE_CAPTURED_ONLY = False
         agg = {}
         for tag, a, b, work in prof:
             fam = tag.split("/")[0]

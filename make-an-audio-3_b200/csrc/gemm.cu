@@ -752,8 +752,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (CG == 2) mbar_arrive_leader(&tempty[as]);
-          else mbar_arrive(&tempty[as]);
+          if constexpr (CG == 2) mbar_arrive_leader_relaxed(&tempty[as]);
+          else mbar_arrive_relaxed(&tempty[as]);
         }
         continue;
       }
@@ -787,8 +787,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_leader(&tempty[as]);
-        else mbar_arrive(&tempty[as]);
+        if constexpr (CG == 2) mbar_arrive_leader_relaxed(&tempty[as]);
+        else mbar_arrive_relaxed(&tempty[as]);
       }
     }
   }

@@ -205,6 +205,17 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
       "h"(mask)
       : "memory");
 }
+// Relaxed arrivals for barriers that only hand back a TMEM accumulator stage: the tcgen05.ld reads were already
+// completed by tcgen05.wait::ld and ordered by tcgen05.fence::before_thread_sync, so no memory release is needed -- the
+// default .release form makes the warp wait for all of its outstanding global stores (MEMBAR + ERRBAR, ~10% of the
+// samples of the QKV GEMM).
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+               : "memory");
+}
 // arrive on the leader CTA's copy of a barrier (from either CTA of the pair)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)

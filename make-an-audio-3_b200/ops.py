@@ -11,21 +11,27 @@ from . import lib as L
 # (kernel tag, start event, end event, algorithmic work: FLOPs for GEMM/attention, bytes for HBM-bound kernels).
 # bench.py uses this for the live roofline measurement; None (default) adds no overhead.
 PROFILE = None
+# With PROFILE_CAPTURED_ONLY only launches issued while the stream is being captured are bracketed: the events become
+# event-record nodes of the CUDA graph (`external=True`), so a later replay times every kernel on the device with no
+# host launch latency between the two records (eager bracketing over-reports short kernels when the host falls behind).
+PROFILE_CAPTURED_ONLY = False
 
 
 class _Span:
     def __init__(self, tag, work):
         self.tag, self.work = tag, work
+        self.on = False
 
     def __enter__(self):
-        if PROFILE is not None:
-            self.e0 = torch.cuda.Event(enable_timing=True)
-            self.e1 = torch.cuda.Event(enable_timing=True)
+        self.on = PROFILE is not None and (not PROFILE_CAPTURED_ONLY or torch.cuda.is_current_stream_capturing())
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True, external=True)
+            self.e1 = torch.cuda.Event(enable_timing=True, external=True)
             self.e0.record()
         return self
 
     def __exit__(self, *exc):
-        if PROFILE is not None and exc[0] is None:
+        if self.on and exc[0] is None:
             self.e1.record()
             PROFILE.append((self.tag, self.e0, self.e1, self.work))
         return False

@@ -9,6 +9,7 @@ only collective (one NCCL all-gather of the finished waveforms).
 import torch
 
 from . import lib as L
+from . import sampler as _sampler
 from .dit import TxtFlagLargeImprovedDiTV2, VideoFlagLargeDiT
 from .sampler import CFMSampler
 from .vae import AutoencoderKL
@@ -34,6 +35,8 @@ class Txt2AudioPipeline:
         self.scale_factor = float(scale_factor)
         self.mel_dim, self.mel_length, self.channels = mel_dim, mel_length, 0
         self.sampler = CFMSampler(self, use_graph=use_graph)
+        self.use_graph = use_graph
+        self._tail = {}
 
     # CFMSampler looks the DiT up as model.model.diffusion_model (the reference's nesting, ddpm.py:1402)
     @property
@@ -62,8 +65,31 @@ class Txt2AudioPipeline:
         """cond/uncond [B, L, Cd], x0 [B, 20, T] (device tensors) -> waveforms [B, 2T*hop] on the device."""
         B = x0.shape[0]
         z, _ = self.sample_cfg(cond, scale, uncond, B, timesteps=timesteps, x_latent=x0)
-        mel = self.decode_first_stage(z)
-        return self.vocoder.vocode_tensor(mel)
+        return self.decode_and_vocode(z)
+
+    @torch.no_grad()
+    def decode_and_vocode(self, z):
+        """decode_first_stage + vocode of latents z [B, 20, T] -> waveforms [B, 2T*hop].  With use_graph the ~450
+        launches of the two stages are captured once per latent shape and replayed (as the sampler does for its step
+        loop), so no host launch latency sits between the short kernels of the VAE and of the early vocoder stages."""
+        if not self.use_graph:
+            return self.vocoder.vocode_tensor(self.decode_first_stage(z))
+        key = (tuple(z.shape), id(self.first_stage_model), id(self.vocoder))
+        st = self._tail.get(key)
+        if st is None:
+            zin = z.clone()
+            self.vocoder.vocode_tensor(self.decode_first_stage(zin))   # eager pass: packs weights, allocates buffers
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(g):
+                wav = self.vocoder.vocode_tensor(self.decode_first_stage(zin))
+            st = {"zin": zin, "wav": wav, "graph": g, "launches": L.launch_count() - n0}
+            self._tail = {key: st}             # keep one plan: the vocoder buffers are large
+        st["zin"].copy_(z)
+        st["graph"].replay()
+        _sampler.GRAPH_REPLAY_LAUNCHES += st["launches"]
+        return st["wav"].clone()
 
 
 def build_random_pipeline(model="M", vocoder_h=None, seed=0, device="cuda", use_graph=True, state_dicts=None):
