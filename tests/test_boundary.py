@@ -92,11 +92,12 @@ def test_euler_schedule_matches_oracle_and_golden(golden):
 
 def test_packed_conv_transpose_phases():
     from ma3_b200.convs import PackedConvTranspose
-    w = torch.randn(4, 6, 8)
+    gen = torch.Generator().manual_seed(7)
+    w = torch.randn(4, 6, 8, generator=gen).bfloat16().float()   # bf16-exact weights: the packed copy is bf16
     p = PackedConvTranspose(w, torch.zeros(6), stride=4, padding=2, device="cpu")
     assert p.out_len(10) == 40 and len(p.phases) == 4 and all(len(t) == 2 for t in p.phases)
     # emulate the tap-GEMM on CPU with the packed weights and compare with conv_transpose1d
-    x = torch.randn(1, 10, 16)
+    x = torch.randn(1, 10, 16, generator=gen)
     x[..., 4:] = 0
     out = torch.zeros(1, 40, 6)
     W_ = p.w.float().view(8, 6, 16)
@@ -107,7 +108,7 @@ def test_packed_conv_transpose_phases():
                 if 0 <= i < 10:
                     out[0, 4 * q + r] += W_[brow // 6] @ x[0, i]
     ref = torch.nn.functional.conv_transpose1d(x[..., :4].transpose(1, 2), w, None, stride=4, padding=2)
-    assert torch.allclose(out.transpose(1, 2), ref, atol=2e-2)   # packed weights are bf16
+    assert torch.allclose(out.transpose(1, 2), ref, atol=1e-4)
 
 
 def test_shard_prompts():
