@@ -174,6 +174,123 @@ __device__ __forceinline__ void final_row(const float* __restrict__ hrow, const 
   result = mine;
 }
 
+// Fast path for D = 128 * kV4: one warp takes TWO rows at a time (the uncond / cond pair in CFG mode), keeps both
+// normalised rows in registers as float4 pieces and walks W once for both: 2 * Cout independent accumulators per lane
+// (instruction-level parallelism instead of one dependent FMA chain per channel), then one "transposing" butterfly per
+// row that leaves lane c holding output channel c (31 shuffles for up to 32 channels instead of 5 per channel).
+template <int kV4>
+__device__ __forceinline__ void norm_row4(const float* __restrict__ hrow, const float* __restrict__ sc,
+                                          const float* __restrict__ sh, int D, float eps, int lane, float4 (&xn)[kV4]) {
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    xn[i] = reinterpret_cast<const float4*>(hrow)[i * 32 + lane];
+    s += (xn[i].x + xn[i].y) + (xn[i].z + xn[i].w);
+    s2 += (xn[i].x * xn[i].x + xn[i].y * xn[i].y) + (xn[i].z * xn[i].z + xn[i].w * xn[i].w);
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  const float mean = s / (float)D;
+  const float rstd = rsqrtf(fmaxf(s2 / (float)D - mean * mean, 0.f) + eps);
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const float4 a = reinterpret_cast<const float4*>(sc)[i * 32 + lane];
+    const float4 b = reinterpret_cast<const float4*>(sh)[i * 32 + lane];
+    xn[i].x = (xn[i].x - mean) * rstd * (1.f + a.x) + b.x;
+    xn[i].y = (xn[i].y - mean) * rstd * (1.f + a.y) + b.y;
+    xn[i].z = (xn[i].z - mean) * rstd * (1.f + a.z) + b.z;
+    xn[i].w = (xn[i].w - mean) * rstd * (1.f + a.w) + b.w;
+  }
+}
+
+// v[0..32) per lane -> lane l returns sum over the warp of v[l]
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = up ? v[k] : v[k + off];
+      const float keep = up ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int kV4>
+__device__ __forceinline__ void final_pair(const float* __restrict__ h0, const float* __restrict__ h1,
+                                           const float* __restrict__ mod0, const float* __restrict__ mod1, int shift_off,
+                                           int scale_off, const float* __restrict__ sW, const float* __restrict__ bias,
+                                           int D, int Cout, float eps, int lane, float& r0, float& r1) {
+  float4 x0[kV4], x1[kV4];
+  norm_row4<kV4>(h0, mod0 + scale_off, mod0 + shift_off, D, eps, lane, x0);
+  norm_row4<kV4>(h1, mod1 + scale_off, mod1 + shift_off, D, eps, lane, x1);
+  float a0[32], a1[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
+#pragma unroll
+  for (int c = 0; c < kMaxCout; ++c) {
+    if (c < Cout) {
+      const float4* wr = reinterpret_cast<const float4*>(sW + (long long)c * D);
+#pragma unroll
+      for (int i = 0; i < kV4; ++i) {
+        const float4 w = wr[i * 32 + lane];
+        a0[c] = fmaf(x0[i].x, w.x, fmaf(x0[i].y, w.y, fmaf(x0[i].z, w.z, fmaf(x0[i].w, w.w, a0[c]))));
+        a1[c] = fmaf(x1[i].x, w.x, fmaf(x1[i].y, w.y, fmaf(x1[i].z, w.z, fmaf(x1[i].w, w.w, a1[c]))));
+      }
+    }
+  }
+  const float b = lane < Cout ? bias[lane] : 0.f;
+  r0 = warp_transpose_sum32(a0, lane) + b;
+  r1 = warp_transpose_sum32(a1, lane) + b;
+}
+
+template <bool kCfg, int kV4>
+__global__ void __launch_bounds__(256) final_layer_fast_kernel(const float* __restrict__ h, const float* __restrict__ mod,
+                                                               long long mod_ld, int shift_off, int scale_off,
+                                                               const float* __restrict__ W, const float* __restrict__ bias,
+                                                               int N, int T, int D, int Cout, float eps,
+                                                               float* __restrict__ v_out, const float* __restrict__ x_in,
+                                                               float* __restrict__ x_out, float dt, float guidance) {
+  extern __shared__ __align__(16) float sW[];  // [Cout, D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int i = threadIdx.x; i < (Cout * D) >> 2; i += blockDim.x)
+    reinterpret_cast<float4*>(sW)[i] = reinterpret_cast<const float4*>(W)[i];
+  __syncthreads();
+  if constexpr (!kCfg) {
+    const int pairs = (N * T + 1) >> 1;
+    for (int pid = blockIdx.x * nwarp + warp; pid < pairs; pid += gridDim.x * nwarp) {
+      const int w0 = 2 * pid, w1 = min(2 * pid + 1, N * T - 1);
+      const int n0 = w0 / T, n1 = w1 / T;
+      float r0, r1;
+      final_pair<kV4>(h + (long long)w0 * D, h + (long long)w1 * D, mod + (long long)n0 * mod_ld, mod + (long long)n1 * mod_ld,
+                      shift_off, scale_off, sW, bias, D, Cout, eps, lane, r0, r1);
+      if (lane < Cout) {
+        v_out[((long long)n0 * Cout + lane) * T + (w0 - n0 * T)] = r0;
+        if (2 * pid + 1 < N * T) v_out[((long long)n1 * Cout + lane) * T + (w1 - n1 * T)] = r1;
+      }
+    }
+  } else {
+    const int B = N >> 1;
+    for (int wid = blockIdx.x * nwarp + warp; wid < B * T; wid += gridDim.x * nwarp) {
+      const int b = wid / T, t = wid - b * T;
+      const int nc = b + B;
+      float ru, rc;
+      final_pair<kV4>(h + (long long)wid * D, h + ((long long)nc * T + t) * D, mod + (long long)b * mod_ld,
+                      mod + (long long)nc * mod_ld, shift_off, scale_off, sW, bias, D, Cout, eps, lane, ru, rc);
+      if (lane < Cout) {
+        const float vg = ru + guidance * (rc - ru);
+        const long long idx = ((long long)b * Cout + lane) * T + t;
+        if (v_out) v_out[idx] = vg;
+        if (x_out) x_out[idx] = x_in[idx] + dt * vg;
+      }
+    }
+  }
+}
+
 template <bool kCfg>
 __global__ void __launch_bounds__(256) final_layer_kernel(const float* __restrict__ h, const float* __restrict__ mod,
                                                           long long mod_ld, int shift_off, int scale_off,
@@ -478,9 +595,25 @@ int ma3_final_layer(const float* h, const float* mod, int64_t mod_ld, int shift_
   }
   MA3_REQUIRE(smem <= 200 * 1024, "final_layer: Cout * D too large for shared memory");
   const unsigned fgrid = (unsigned)min((long long)num_sms(), ((long long)N * T + 7) / 8);
+#define FL_FAST(KV4)                                                                                                   \
+  do {                                                                                                                 \
+    static bool cfgd = false;                                                                                          \
+    if (!cfgd) {                                                                                                       \
+      cudaFuncSetAttribute(final_layer_fast_kernel<false, KV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      cfgd = true;                                                                                                     \
+    }                                                                                                                  \
+    launch_pdl(final_layer_fast_kernel<false, KV4>, dim3(fgrid), dim3(256), smem, ST(stream), 1, h, mod, (long long)mod_ld, \
+               shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, (const float*)nullptr, (float*)nullptr, 0.f, 0.f); \
+  } while (0)
+  const bool fast = aligned16(h) && aligned16(mod) && mod_ld % 4 == 0 && shift_off % 4 == 0 && scale_off % 4 == 0;
+  if (fast && D == 768) FL_FAST(6);
+  else if (fast && D == 1152) FL_FAST(9);
+  else if (fast && D == 1536) FL_FAST(12);
+  else
   launch_pdl(final_layer_kernel<false>, dim3(fgrid), dim3(256), smem, ST(stream), 1, h, mod,
              (long long)mod_ld, shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, (const float*)nullptr,
              (float*)nullptr, 0.f, 0.f);
+#undef FL_FAST
   MA3_LAUNCH_CHECK("final_layer");
   return 0;
 }
@@ -502,8 +635,24 @@ int ma3_final_layer_cfg_euler(const float* h, const float* mod, int64_t mod_ld, 
   }
   MA3_REQUIRE(smem <= 200 * 1024, "final_layer_cfg_euler: Cout * D too large for shared memory");
   const unsigned fgrid = (unsigned)min((long long)num_sms(), ((long long)(N / 2) * T + 7) / 8);
+#define FL_FAST(KV4)                                                                                                   \
+  do {                                                                                                                 \
+    static bool cfgd = false;                                                                                          \
+    if (!cfgd) {                                                                                                       \
+      cudaFuncSetAttribute(final_layer_fast_kernel<true, KV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      cfgd = true;                                                                                                     \
+    }                                                                                                                  \
+    launch_pdl(final_layer_fast_kernel<true, KV4>, dim3(fgrid), dim3(256), smem, ST(stream), 1, h, mod, (long long)mod_ld, \
+               shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, x_in, x_out, dt, guidance);                   \
+  } while (0)
+  const bool fast = aligned16(h) && aligned16(mod) && mod_ld % 4 == 0 && shift_off % 4 == 0 && scale_off % 4 == 0;
+  if (fast && D == 768) FL_FAST(6);
+  else if (fast && D == 1152) FL_FAST(9);
+  else if (fast && D == 1536) FL_FAST(12);
+  else
   launch_pdl(final_layer_kernel<true>, dim3(fgrid), dim3(256), smem, ST(stream), 1, h, mod,
              (long long)mod_ld, shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, x_in, x_out, dt, guidance);
+#undef FL_FAST
   MA3_LAUNCH_CHECK("final_layer_cfg_euler");
   return 0;
 }

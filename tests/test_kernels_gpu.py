@@ -259,8 +259,9 @@ def test_rmsnorm_modulate(ops):
     assert rel(out32, O.rmsnorm(x, torch.ones(D))) < 1e-5
 
 
-def test_final_layer_and_cfg_euler(ops):
-    B, T, D, Cc = 3, 50, 768, 20
+@pytest.mark.parametrize("D,T", [(768, 50), (1152, 51), (1536, 8), (256, 33)])   # fast row-pair kernels + the generic one (odd N*T)
+def test_final_layer_and_cfg_euler(ops, D, T):
+    B, Cc = 3, 20
     N = 2 * B
     h = torch.randn(N * T, D, generator=g(33)) * 2 + 0.3
     mod = torch.randn(N, 2 * D, generator=g(34)) * 0.3
