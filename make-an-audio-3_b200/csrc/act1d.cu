@@ -314,6 +314,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __ha
   const int rows = TB + 16;
   const int pitch = CT * 2 + 16;             // bytes; +16 keeps the 8 rows of an ldmatrix / stmatrix on distinct banks
   const int vpr = CT >> 3;                   // 16-byte vectors per row
+  const int vshift = 31 - __clz(vpr);
   const size_t in_bytes = (size_t)rows * pitch;
   uint8_t* os = smem_raw + 2 * in_bytes;     // output tile [TB][pitch]
   const int total = tiles_c * tiles_t * B;
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __ha
     const __half* xb = x + (long long)b * T * C + c0;
     uint8_t* tile = smem_raw + buf * in_bytes;
     for (int idx = threadIdx.x; idx < rows * vpr; idx += kMmaWarps * 32) {
-      const int r = idx / vpr, v = idx - r * vpr;
+      const int r = idx >> vshift, v = idx & (vpr - 1);   // vpr is 2, 4 or 8
       int gr = tb0 - 6 + r;
       gr = gr < 0 ? 0 : (gr > T - 1 ? T - 1 : gr);
       cp_async16(tile + (size_t)r * pitch + v * 16, xb + (long long)gr * C + v * 8);
@@ -392,11 +393,14 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __ha
         // snake: [0], [1] -> channel g; [2], [3] -> channel g + 8
         float sl[4], sh[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 4; ++e) {   // (low, high) sample of one channel as a packed fp32 pair around the two MUFU.SIN
           const float a = e < 2 ? a0 : a1, ib = e < 2 ? ib0 : ib1;
-          const float s0 = __sinf(ul[e] * a), s1 = __sinf(uh[e] * a);
-          sl[e] = fmaf(ib * s0, s0, ul[e]);
-          sh[e] = fmaf(ib * s1, s1, uh[e]);
+          const float2 u = make_float2(ul[e], uh[e]);
+          const float2 arg = fmul2(u, make_float2(a, a));
+          const float2 sn = make_float2(__sinf(arg.x), __sinf(arg.y));
+          const float2 r = ffma2(fmul2(make_float2(ib, ib), sn), sn, u);
+          sl[e] = r.x;
+          sh[e] = r.y;
         }
         // replicate padding of the activated signal: samples m < 0 take s[0], samples m > 2T-1 take s[2T-1]
         const int mb = 2 * tw0 - 6 + 16 * j;
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __ha
       __half* ob = out + ((long long)b * T + tb0) * C + c0;
       const int nrows = min(TB, T - tb0);
       for (int idx = threadIdx.x; idx < nrows * vpr; idx += kMmaWarps * 32) {
-        const int r = idx / vpr, v = idx - r * vpr;
+        const int r = idx >> vshift, v = idx & (vpr - 1);
         *reinterpret_cast<uint4*>(ob + (long long)r * C + v * 8) = *reinterpret_cast<const uint4*>(os + (size_t)r * pitch + v * 16);
       }
     }

@@ -547,6 +547,23 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
       mbar_init(p_full, 2 * n_active);   // one arrival per active softmax warp
       mbar_init(o_full, 1);
       fence_barrier_init();
+      // the first loads (Q, K/V tiles 0 and 1) go out before the TMEM allocation and the CTA-wide sync, so their
+      // L2 / HBM latency overlaps the rest of the prologue
+      pdl_wait();
+      mbar_arrive_expect_tx(q_full, kQBytes);
+#pragma unroll
+      for (int c = 0; c < HDC; ++c) tma_load_3d(sQ + c * (128 * 128), &p.tmQ, q_full, c * 64, q0, bh);
+      for (int i = 0; i < 2 && i < n_tiles; ++i) {
+        const bool cross = i >= n_self;
+        const int kv0 = (cross ? i - n_self : i) * BKV;
+        uint8_t* dK = sKV + i * kStageBytes;
+        mbar_arrive_expect_tx(&k_full[i], kKBytes);
+#pragma unroll
+        for (int c = 0; c < HDC; ++c)
+          tma_load_3d(dK + c * (BKV * 128), cross ? &p.tmKy : &p.tmK, &k_full[i], c * 64, kv0, bh);
+        mbar_arrive_expect_tx(&v_full[i], kVBytes);
+        tma_load_3d(dK + kKBytes, cross ? &p.tmVyt : &p.tmVt, &v_full[i], kv0, 0, bh);
+      }
     }
     __syncwarp();
     tmem_alloc(tmem_slot, kTmemCols);
@@ -597,13 +614,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
         umma_commit(&k_empty[st]);
       };
 
-      mbar_arrive_expect_tx(q_full, kQBytes);
-#pragma unroll
-      for (int c = 0; c < HDC; ++c) tma_load_3d(sQ + c * (128 * 128), &p.tmQ, q_full, c * 64, q0, bh);
-      load_k(0);
-      load_v(0);
-      if (n_tiles > 1) { load_k(1); load_v(1); }
-      mbar_wait(q_full, 0);
+      mbar_wait(q_full, 0);   // Q and the first two K / V tiles were requested in the prologue
       issue_s(0);
       if (n_tiles > 1) issue_s(1);
       for (int i = 0; i < n_tiles; ++i) {
