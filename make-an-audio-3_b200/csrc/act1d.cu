@@ -382,15 +382,14 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __ha
                               (uint32_t)((cgi * 16 + ((lane >> 3) & 1) * 8) * 2);
       const uint32_t oaddr0 = smem_u32(os) + (uint32_t)((seg * kMmaTS + (lane & 7)) * pitch) +
                               (uint32_t)((cgi * 16 + ((lane >> 3) & 1) * 8) * 2);
-      uint32_t sp[4] = {0u, 0u, 0u, 0u};
-#pragma unroll 3
-      for (int j = 0; j <= ngroups; ++j) {
+      // one sample block: stage-1 MMAs, Snake on the accumulator fragments, replicate padding of the activated signal
+      // at the sequence ends, packed to the fp16 A fragment stage 2 consumes
+      auto sample_block = [&](int j, uint32_t (&sc)[4]) {
         uint32_t xa[4];
         ldmatrix_x4_trans(xa, xaddr0 + (uint32_t)(j * 8 * pitch));
         float ul[4] = {0.f, 0.f, 0.f, 0.f}, uh[4] = {0.f, 0.f, 0.f, 0.f};
         mma_f16(ul, xa, bu[0][0], bu[0][1]);
         mma_f16(uh, xa, bu[1][0], bu[1][1]);
-        // snake: [0], [1] -> channel g; [2], [3] -> channel g + 8
         float sl[4], sh[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {   // (low, high) sample of one channel as a packed fp32 pair around the two MUFU.SIN
@@ -402,7 +401,6 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __ha
           sl[e] = r.x;
           sh[e] = r.y;
         }
-        // replicate padding of the activated signal: samples m < 0 take s[0], samples m > 2T-1 take s[2T-1]
         const int mb = 2 * tw0 - 6 + 16 * j;
         if (mb < 0) {             // only block 0 of a sequence: m = 0 is local sample 6 (lane tq = 3, low half, e = 0)
           const float v0 = __shfl_sync(0xffffffffu, sl[0], (lane & ~3) | 3);
@@ -415,15 +413,32 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __ha
           if (tq == 3) { sl[0] = v0; sl[1] = v0; sl[2] = v1; sl[3] = v1; }
           sh[0] = v0; sh[1] = v0; sh[2] = v1; sh[3] = v1;
         }
-        uint32_t sc[4] = {pack_f16(sl[0], sl[1]), pack_f16(sl[2], sl[3]), pack_f16(sh[0], sh[1]), pack_f16(sh[2], sh[3])};
-        if (j > 0) {
-          float o[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_f16(o, sp, bd[0][0], bd[0][1]);
-          mma_f16(o, sc, bd[1][0], bd[1][1]);
-          stmatrix_x2_trans(oaddr0 + (uint32_t)((j - 1) * 8 * pitch), pack_f16(o[0], o[1]), pack_f16(o[2], o[3]));
-        }
+        sc[0] = pack_f16(sl[0], sl[1]); sc[1] = pack_f16(sl[2], sl[3]);
+        sc[2] = pack_f16(sh[0], sh[1]); sc[3] = pack_f16(sh[2], sh[3]);
+      };
+      // output group g (8 outputs from tw0 + 8 g) = low-pass over sample blocks g (window samples 0-15) and g + 1 (16-31)
+      auto out_group = [&](int gidx, const uint32_t (&lo)[4], const uint32_t (&hi)[4]) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(o, lo, bd[0][0], bd[0][1]);
+        mma_f16(o, hi, bd[1][0], bd[1][1]);
+        stmatrix_x2_trans(oaddr0 + (uint32_t)(gidx * 8 * pitch), pack_f16(o[0], o[1]), pack_f16(o[2], o[3]));
+      };
+      uint32_t sp[4];
+      sample_block(0, sp);
+      int j = 1;
+      for (; j + 1 <= ngroups; j += 2) {   // two blocks per trip: their chains are independent (instruction-level parallelism)
+        uint32_t c1[4], c2[4];
+        sample_block(j, c1);
+        sample_block(j + 1, c2);
+        out_group(j - 1, sp, c1);
+        out_group(j, c1, c2);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) sp[e] = sc[e];
+        for (int e = 0; e < 4; ++e) sp[e] = c2[e];
+      }
+      if (j <= ngroups) {
+        uint32_t c1[4];
+        sample_block(j, c1);
+        out_group(j - 1, sp, c1);
       }
     }
     __syncthreads();
