@@ -105,6 +105,23 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, flo
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Explicit shared-space accesses for the epilogue staging patch: the patch pointer is derived by pointer arithmetic
+// from the dynamic shared-memory base and ptxas otherwise falls back to generic LD / ST (slower address path, and the
+// loads then sit on the long scoreboard next to the global ones).
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ float lds_f1(const float* p) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(float* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ epilogues
 __device__ __forceinline__ void load8(const void* base, int dtype, long long idx, bool vec, int n, float (&v)[8]) {
   if (dtype == MA3_F32) {
@@ -277,7 +294,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
 #pragma unroll
   for (int e = 0; e < 32; e += 4)
     if (e < w)
-      *reinterpret_cast<uint4*>(stg + lane * kStagePitch + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+      sts_u4(stg + lane * kStagePitch + e, r[e], r[e + 1], r[e + 2], r[e + 3]);
   __syncwarp();
 
   if constexpr (EPI == MA3_EPI_GATE_RES) {
@@ -297,7 +314,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
 #pragma unroll
       for (int pass = 0; pass < 8; ++pass) {
         if (rc.off[pass] >= 0) {
-          const float4 a = *reinterpret_cast<const float4*>(sp);
+          const float4 a = lds_f4(sp);
           red_add_f32x4(out + rc.off[pass] + col, gv[pass].x * a.x, gv[pass].y * a.y, gv[pass].z * a.z, gv[pass].w * a.w);
         }
         sp += 4 * kStagePitch;
@@ -315,7 +332,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
           float v[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float4 a = *reinterpret_cast<const float4*>(sp + 4 * e);
+            const float4 a = lds_f4(sp + 4 * e);
             v[2 * e] = silu_f(a.x) * a.y;
             v[2 * e + 1] = silu_f(a.z) * a.w;
           }
@@ -352,7 +369,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
         if (rc.off[pass] >= 0) {
           float v[8];
           {
-            const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+            const float4 a = lds_f4(sp), b = lds_f4(sp + 4);
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
           }
           if (p.bias) {
@@ -409,7 +426,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
           if (rc.off[4 + gq] >= 0) {
             float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = sp[(gq * 8 + e) * kStagePitch];
+            for (int e = 0; e < 8; ++e) v[e] = lds_f1(sp + (gq * 8 + e) * kStagePitch);
             uint4 u;
             if (p.op_dtype == MA3_BF16)
               u = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -452,7 +469,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const float4 f = cs[pass][e];  // (cos, sin) of two consecutive pairs
-              const float4 xv = *reinterpret_cast<const float4*>(sp + 4 * e);
+              const float4 xv = lds_f4(sp + 4 * e);
               const float x0 = xv.x, x1 = xv.y, x2 = xv.z, x3 = xv.w;
               v[4 * e] = (x0 * f.x - x1 * f.y) * sc;
               v[4 * e + 1] = (x0 * f.y + x1 * f.x) * sc;
@@ -460,7 +477,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
               v[4 * e + 3] = (x2 * f.w + x3 * f.z) * sc;
             }
           } else {
-            const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+            const float4 a = lds_f4(sp), b = lds_f4(sp + 4);
             v[0] = a.x * sc; v[1] = a.y * sc; v[2] = a.z * sc; v[3] = a.w * sc;
             v[4] = b.x * sc; v[5] = b.y * sc; v[6] = b.z * sc; v[7] = b.w * sc;
           }
