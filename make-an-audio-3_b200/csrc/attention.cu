@@ -362,7 +362,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------ v2 kernel
 // Same contract and CTA shape as attn_kernel above, restructured to cut the softmax warps' instruction count ~3x
 // (they, not the tensor core, bound the kernel at these head dims):
-//  * S is read from TMEM once (64 registers per row) instead of once for the max and once for the exponentials;
+//  * S is read from TMEM once instead of once for the max and once for the exponentials, and P is written back into
+//    tensor memory over the consumed S columns (tcgen05.st) and fed to the PV MMA as a TMEM A operand: no shared-memory
+//    P tile, no async-proxy fence.  The tensor pipe does NOT order those A reads against a later MMA that overwrites
+//    the same columns, so S(i+2) is issued only after PV(i) has completed;
 //  * O stays in TMEM and the PV MMAs accumulate into it.  The running maximum is only raised when a tile exceeds it
 //    by more than 2^8 (lazy rescaling: p <= 256 is harmless for bf16 P and the fp32 accumulator, and the result is
 //    exact because numerator and denominator share the stale reference); the rare correction multiplies O in place;
@@ -430,8 +433,16 @@ __device__ __forceinline__ void drain_o(uint32_t tO, float f, uint32_t (&stash)[
 
 constexpr int kAttn2Threads = 288;   // warps 0-7: softmax, two threads per query row (32 keys each); warp 8: TMA + MMA
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// Named barrier of one softmax warp pair.  The id must be an immediate: with a register operand ptxas cannot see which
+// barriers the kernel uses, reports "used 1 barriers", the hardware then reserves a single barrier per CTA and ids
+// 1-4 alias the barriers of the co-resident CTA (observed as intermittent wrong rows in the second CTA of an SM).
+__device__ __forceinline__ void pair_bar_sync(int qw) {
+  switch (qw) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
 }
 
 // Segment epilogue over this thread's O columns [C0, C1) in pieces of 8: kFinal = false parks O * f as packed bf16
@@ -495,24 +506,22 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
   constexpr uint32_t kKBytes = BKV * HDP * 2;
   constexpr uint32_t kVBytes = HDO * 128;        // only the HDO rows of V^T the PV MMA reads are staged
   constexpr uint32_t kStageBytes = kKBytes + kVBytes;
-  constexpr uint32_t kPBytes = 128 * BKV * 2;
   constexpr uint32_t kTmemCols = 256;            // S0: [0, 64)  S1: [64, 128)  O: [128, 128 + HDO)
   static_assert(2 * BKV + HDO <= 256, "TMEM budget");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sQ = smem_raw;
   uint8_t* sKV = sQ + kQBytes;
-  uint8_t* sP = sKV + 2 * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 2 * kStageBytes);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* k_empty = bars + 3;
   uint64_t* v_full = bars + 5;
   uint64_t* v_empty = bars + 7;
   uint64_t* s_full = bars + 9;
-  uint64_t* p_full = bars + 11;
-  uint64_t* o_full = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* p_full = bars + 11;     // 2, by tile parity
+  uint64_t* o_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   float* xch = reinterpret_cast<float*>(bars + 16);   // [tile parity][column half][row]: per-tile row maxima
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -544,7 +553,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
         mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         mbar_init(&s_full[i], 1);
       }
-      mbar_init(p_full, 2 * n_active);   // one arrival per active softmax warp
+      mbar_init(&p_full[0], 2 * n_active);   // one arrival per active softmax warp
+      mbar_init(&p_full[1], 2 * n_active);
       mbar_init(o_full, 1);
       fence_barrier_init();
       // the first loads (Q, K/V tiles 0 and 1) go out before the TMEM allocation and the CTA-wide sync, so their
@@ -598,18 +608,20 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
       };
       const uint32_t idesc_s = umma_idesc(128, BKV, p.dtype == MA3_BF16 ? 1 : 0);
       const uint32_t idesc_o = umma_idesc(128, HDO, p.dtype == MA3_BF16 ? 1 : 0);
+      // descriptors as (lo, shared hi) 32-bit halves: only the start-address field of lo changes between MMAs, so the
+      // single issuing thread spends one integer add per operand per MMA (see the tap-GEMM issue loop)
       const uint64_t dq0 = umma_desc_kmajor(smem_u32(sQ), 128);
-      const uint64_t dp0 = umma_desc_kmajor(smem_u32(sP), 128);
-      const uint64_t dk0 = umma_desc_kmajor(smem_u32(sKV), 128);
-      const uint64_t dv0 = umma_desc_kmajor(smem_u32(sKV + kKBytes), 128);
+      const uint32_t dhi = (uint32_t)(dq0 >> 32), q_lo = (uint32_t)dq0;
+      const uint32_t k_lo = (uint32_t)umma_desc_kmajor(smem_u32(sKV), 128);
+      const uint32_t v_lo = (uint32_t)umma_desc_kmajor(smem_u32(sKV + kKBytes), 128);
       auto issue_s = [&](int i) {
         const int st = i & 1;
         mbar_wait(&k_full[st], (i >> 1) & 1);
-        const uint64_t db = dk0 + (uint64_t)(st * (kStageBytes >> 4));
+        const uint32_t b_lo = k_lo + (uint32_t)st * (kStageBytes >> 4);
 #pragma unroll
         for (int k = 0; k < KS; ++k)
-          umma_f16(tmem_S + st * BKV, dq0 + (uint64_t)((k / 4) * (128 * 128 / 16) + (k % 4) * 2),
-                   db + (uint64_t)((k / 4) * (BKV * 128 / 16) + (k % 4) * 2), idesc_s, k != 0 ? 1u : 0u);
+          umma_f16_lohi<1>(tmem_S + st * BKV, q_lo + (uint32_t)((k / 4) * (128 * 128 / 16) + (k % 4) * 2),
+                           b_lo + (uint32_t)((k / 4) * (BKV * 128 / 16) + (k % 4) * 2), dhi, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[st]);
         umma_commit(&k_empty[st]);
       };
@@ -624,23 +636,26 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
           load_k(i + 2);
         }
         attn_trace(p, i, 8);
-        mbar_wait(p_full, i & 1);     // P(i) in smem, S buffer st drained, O rescaled / consumed as needed
+        mbar_wait(&p_full[st], (i >> 1) & 1);   // P(i) in TMEM, S buffer st drained, O rescaled / consumed as needed
         attn_trace(p, i, 9);
         mbar_wait(&v_full[st], (i >> 1) & 1);
         tc_fence_after();
-        const uint64_t dv = dv0 + (uint64_t)(st * (kStageBytes >> 4));
+        const uint32_t dv = v_lo + (uint32_t)st * (kStageBytes >> 4);
         const uint32_t fresh = (i == 0 || i == n_self) ? 0u : 1u;   // first tile of a segment overwrites O
-        umma_f16(tmem_O, dp0, dv, idesc_o, fresh);
-        umma_f16(tmem_O, dp0 + 2, dv + 2, idesc_o, 1u);
-        umma_f16(tmem_O, dp0 + 4, dv + 4, idesc_o, 1u);
-        umma_f16(tmem_O, dp0 + 6, dv + 6, idesc_o, 1u);
+        // P(i) lives in tensor memory, packed two keys per column over the first 32 columns of S buffer st
+        const uint32_t tP = tmem_S + st * BKV;
+        umma_f16_ts(tmem_O, tP, dv, dhi, idesc_o, fresh);
+        umma_f16_ts(tmem_O, tP + 8, dv + 2, dhi, idesc_o, 1u);
+        umma_f16_ts(tmem_O, tP + 16, dv + 4, dhi, idesc_o, 1u);
+        umma_f16_ts(tmem_O, tP + 24, dv + 6, dhi, idesc_o, 1u);
         umma_commit(o_full);
         umma_commit(&v_empty[st]);
         attn_trace(p, i, 10);
         if (i + 2 < n_tiles) {
-          issue_s(i + 2);
+          // S(i+2) overwrites the TMEM buffer PV(i) reads P from: issue it only once PV(i) has completed
           mbar_wait(&v_empty[st], (i >> 1) & 1);
           load_v(i + 2);
+          issue_s(i + 2);
         }
       }
     }
@@ -650,7 +665,6 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
     const uint32_t lane_base = (uint32_t)(qw * 32) << 16;
     const uint32_t tO = tmem_O + lane_base;
     const bool bf16 = p.dtype == MA3_BF16;
-    uint8_t* prow = sP + row * 128;
     uint32_t stash[NSTASH];
 #pragma unroll
     for (int e = 0; e < NSTASH; ++e) stash[e] = 0u;
@@ -689,16 +703,14 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
         // row maximum over both halves: exchange with the partner thread (warp ^ 4) through shared memory
         float* xs = xch + (it & 1) * 256;
         xs[half * 128 + row] = mx;
-        named_bar_sync(1 + qw, 64);
+        pair_bar_sync(qw);
         mx = fmaxf(mx, xs[(half ^ 1) * 128 + row]);
         if (tr) attn_trace(p, it, 2);
-        bool waited = false;
         if (j == 0) {
           m = mx;
         } else if (__any_sync(0xffffffffu, mx > m + 8.f)) {   // identical decision in both warps of the pair
           mbar_wait(o_full, (it - 1) & 1);   // PV(it-1) complete: O may be modified
           tc_fence_after();
-          waited = true;
           const float m_new = fmaxf(m, mx);
           const float alpha = ex2_approx(m - m_new);
           if (half == 0) rescale_cols<0, HSPLIT>(tO, alpha);
@@ -723,16 +735,21 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
           }
         }
         if (tr) attn_trace(p, it, 4);
-        if (it > 0 && !waited) mbar_wait(o_full, (it - 1) & 1);   // PV(it-1) has finished reading P
+        // P goes back into tensor memory over the S columns both threads of the row have already consumed (the named
+        // barrier above orders the partner's S load before this store): 16 packed columns per thread, read by the PV
+        // MMA as its A operand.  No shared-memory tile, no async-proxy fence; S(it+2), which overwrites this buffer,
+        // is issued after PV(it) and the tensor pipe executes in issue order.
+        tmem_st16(tmem_S + (it & 1) * BKV + half * 16 + lane_base, pk);
+        tmem_st_wait();
+        // Every warp observes every phase of o_full, in order, before it arrives for the next tile: a parity wait is
+        // only meaningful when the waiter is at most one phase behind, and the waits of the correction path and of the
+        // segment end would otherwise see a barrier two phases back and fall through (measured: intermittent wrong
+        // rows).  PV(it-1) was issued a whole tile ago, so this wait is normally already satisfied.
+        if (it > 0) mbar_wait(o_full, (it - 1) & 1);
         if (tr) attn_trace(p, it, 5);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(prow + (((half * 4 + u) ^ (row & 7)) * 16)) =
-              make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
         tc_fence_before();
-        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) mbar_arrive(&p_full[it & 1]);
         if (tr) attn_trace(p, it, 6);
       }
       mbar_wait(o_full, (it - 1) & 1);
@@ -771,7 +788,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
 template <int HDP, int HD, int BKV>
 static int launch_attn2(const AttnParams& p, int NS, cudaStream_t st) {
   constexpr int HDO = (HD + 1 + 15) / 16 * 16;
-  constexpr size_t smem = 128 * HDP * 2 + 2 * (BKV * HDP * 2 + HDO * 128) + 128 * BKV * 2 + 128 + 2048;
+  constexpr size_t smem = 128 * HDP * 2 + 2 * (BKV * HDP * 2 + HDO * 128) + 128 + 2048;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn2_kernel<HDP, HD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -269,6 +269,18 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, ui
         : "memory");
   }
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand is read from tensor memory (lane = row, each 32-bit column holds two
+// consecutive K elements), which lets a softmax write P with tcgen05.st and skip shared memory and its proxy fence.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 template <int CG>
 __device__ __forceinline__ void umma_commit_u32(uint32_t bar) {
   if constexpr (CG == 2) {

@@ -217,10 +217,14 @@ def test_qkv_rope_attention(ops, D, H, T, L, Ns):
     assert _qkv_attention_case(ops, D, H, T, L, Ns, seed=20) < 2e-2
 
 
-def test_attention_lazy_rescale_large_logits(ops):
+@pytest.mark.parametrize("Ns,H,hd,hdp,reps", [(2, 4, 72, 128, 1), (2, 32, 24, 64, 25)])
+def test_attention_lazy_rescale_large_logits(ops, Ns, H, hd, hdp, reps):
     """Logits with a large, growing spread across KV tiles force the in-TMEM rescale of O (running maximum raised by
-    more than 2^8) on most tiles; compared with an fp32 softmax of the same bf16 operands."""
-    Ns, H, T, L, hd, hdp = 2, 4, 312, 154, 72, 128
+    more than 2^8) on most tiles; compared with an fp32 softmax of the same bf16 operands.  The second case fills the
+    GPU with two CTAs per SM and repeats the launch back to back: every run must be bit-identical (this is the shape
+    that exposed an under-declared named-barrier count and out-of-order mbarrier phase waits as intermittent wrong rows
+    in the second CTA of an SM)."""
+    T, L = 312, 154
     dev = "cuda"
     gg = g(21)
     q = torch.zeros(Ns, H, T, hdp); k = torch.zeros(Ns, H, T, hdp); ky = torch.zeros(Ns, H, L, hdp)
@@ -233,8 +237,13 @@ def test_attention_lazy_rescale_large_logits(ops):
     Tp, Lp = T, (L + 7) // 8 * 8
     vt = ops.alloc_vt(Ns, H, hd=hd, hdp=hdp, tokens_pad=Tp, device=dev); vt[:, :, :hd, :T] = b(v).transpose(2, 3).to(dev)
     vyt = ops.alloc_vt(Ns, H, hd=hd, hdp=hdp, tokens_pad=Lp, device=dev); vyt[:, :, :hd, :L] = b(vy).transpose(2, 3).to(dev)
-    out = torch.empty(Ns, T, H * hd, device=dev, dtype=torch.bfloat16)
-    ops.attention(b(q).to(dev), b(k).to(dev), vt, b(ky).to(dev), vyt, gate.to(dev), out, hd=hd)
+    qd, kd, kyd, gd = b(q).to(dev), b(k).to(dev), b(ky).to(dev), gate.to(dev)
+    outs = [torch.empty(Ns, T, H * hd, device=dev, dtype=torch.bfloat16) for _ in range(reps)]
+    for o in outs:
+        ops.attention(qd, kd, vt, kyd, vyt, gd, o, hd=hd)
+    torch.cuda.synchronize()
+    out = outs[0]
+    assert all(torch.equal(o, out) for o in outs[1:])
     ln2 = math.log(2.0)
     qf, kf, kyf = b(q).float()[..., :hd], b(k).float()[..., :hd], b(ky).float()[..., :hd]
     ps = torch.softmax(qf @ kf.transpose(2, 3) * ln2, -1) @ b(v).float()
