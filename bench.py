@@ -241,7 +241,7 @@ def main():
     value = audio_s / (ms_step / 1e3)
     e2e_value = audio_s / (ms_e2e / 1e3)
     h2d = cond_h.numel() * 4 + unc_h.numel() * 4 + x0_h.numel() * 4
-    d2h = B * samples * 4
+    d2h = B * world * samples * 4   # rank 0 copies the gathered waveforms of all ranks to the host
 
     # per-stage device time (sampler graph / VAE decode / vocoder), same inputs, CUDA events
     stage_ms = None
