@@ -312,6 +312,14 @@ def main():
                         "frac": ach / peak, "traffic": None,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
                         "launches": n, "avg_launch_us": 1e3 * ms / n, "bytes_per_launch": work / n}
+        # DRAM traffic per launch of that family from the committed ncu --set full capture, when there is one
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+            if tr:
+                roofline["traffic"] = tr["bytes_per_launch"]
+                roofline["traffic_source"] = tr["source"]
+        except Exception:
+            pass
         # secondary: the HBM-bound vocoder activation kernel the north_star singles out
         if "act1d" in agg:
             ms, work, n = agg["act1d"]
