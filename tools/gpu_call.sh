@@ -1,5 +1,2 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err; tail -3 gpurun_out/bench_2gpu.err; python -c "
-import json; d=json.loads([l for l in open('gpurun_out/bench_2gpu.json').read().strip().splitlines() if l.startswith('{')][-1]); print('2 GPUs', round(d['value'],1), round(d['ms_per_step'],2), d['n_gpus'], d['e2e'], d['clocks'])"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 2>/dev/null | tail -1 | cut -c1-300
+timeout 900 python -m pytest tests/test_modules_gpu.py -x -q -m gpu -k "full_size_properties" 2>&1 | tail -12
