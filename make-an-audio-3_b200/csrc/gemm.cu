@@ -8,6 +8,7 @@
 #include "ptx.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace ma3 {
 
@@ -49,6 +50,8 @@ struct GemmKParams {
   int op_dtype;
   float inv_rows_per_sample, inv_tokens, inv_head_dim;  // exact-division helpers (see fast_div)
   int debug_mode;    // diagnostics: 1 = no TMA loads, 2 = no MMAs
+  // narrow-conv kernel (conv_narrow_kernel): rows of the staged A tile, smallest tap shift, padded N, A stages
+  int cn_rows_a, cn_min_shift, cn_bnp, cn_stages;
   int stream_k;      // GATE_RES only: workers take equal contiguous ranges of (tile, k-iteration) instead of whole tiles
   long long* trace;  // diagnostics: when non-null, CTA 0 records clock64() at pipeline events (tools/probe_trace.py)
 };
@@ -526,7 +529,7 @@ __device__ __forceinline__ void rowdirect_prefetch(const GemmKParams& p, int z, 
 }
 
 __device__ __forceinline__ void rowdirect_group(const GemmKParams& p, int z, int m, int col, const uint32_t* r,
-                                                bool has_pre, uint4 pre, float brow) {
+                                                bool has_pre, uint4 pre, float brow, const float* sbias = nullptr) {
   // 8 columns [col, col + 8) of row m
   const int n = min(8, p.N - col);
   if (n <= 0 || m >= p.M) return;
@@ -540,6 +543,9 @@ __device__ __forceinline__ void rowdirect_group(const GemmKParams& p, int z, int
     if (p.bias_per_row) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] += brow;
+    } else if (sbias != nullptr) {   // per-column bias staged in shared memory (zero beyond N): two broadcast loads
+      const float4 b0 = lds_f4(sbias + col), b1 = lds_f4(sbias + col + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) if (e < n) v[e] += p.bias[col + e];
@@ -821,6 +827,206 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ narrow conv kernel
+// Conv1d / ConvTranspose1d phases with K <= 64 input channels and N <= 64 output channels (the 48- and 24-channel
+// stages of BigVGAN and conv_post).  The tap-GEMM above re-fetches the 128-row input tile once per tap and pays a
+// pipeline round trip per (tap, k-chunk); with so few channels that fixed cost is the whole run time.  Here
+//   * the weights of all taps stay resident in shared memory for the life of the persistent CTA,
+//   * the input tile is staged ONCE per output tile as (128 + halo) rows, and a tap is nothing but a row offset of the
+//     UMMA A descriptor inside that tile: the 128B swizzle is a function of the absolute shared-memory address, so a
+//     K-major operand may start at any row of a swizzled tile with base-offset 0 (measured exact for every shift,
+//     tools/probe note in DESIGN.md section 7),
+//   * four TMEM accumulator stages and two alternating sets of row-direct epilogue warps keep two tile epilogues in
+//     flight.
+constexpr int kCnAcc = 4;   // accumulator stages of 64 columns
+
+__global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __grid_constant__ GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t w_tap_bytes = (uint32_t)p.cn_bnp * 128u;
+  const uint32_t w_bytes = (uint32_t)p.taps * w_tap_bytes;
+  const uint32_t a_bytes = (uint32_t)p.cn_rows_a * 128u;
+  const uint32_t a_stage = (a_bytes + 1023u) & ~1023u;
+  uint8_t* sW = base;
+  uint8_t* sA = base + ((w_bytes + 1023u) & ~1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)p.cn_stages * a_stage);
+  uint64_t* w_full = bars;
+  uint64_t* a_full = bars + 1;
+  uint64_t* a_empty = a_full + kMaxStages;
+  uint64_t* t_full = a_empty + kMaxStages;
+  uint64_t* t_empty = t_full + kCnAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + kCnAcc);
+  float* sbias = reinterpret_cast<float*>(bars + 32);       // 64 floats at byte 256 of the barrier block
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA);
+    prefetch_tmap(&p.tmB);
+  }
+  const bool col_bias = p.bias != nullptr && !p.bias_per_row;
+  if (warp >= 2 && threadIdx.x - 64 < 64) {
+    const int c = threadIdx.x - 64;
+    sbias[c] = (col_bias && c < p.N) ? p.bias[c] : 0.f;
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(w_full, 1);
+      for (int i = 0; i < p.cn_stages; ++i) {
+        mbar_init(&a_full[i], 1);
+        mbar_init(&a_empty[i], 1);
+      }
+      for (int i = 0; i < kCnAcc; ++i) {
+        mbar_init(&t_full[i], 1);
+        mbar_init(&t_empty[i], kEpiWarps / 2);   // one warp set (4 warps) drains a stage
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kCnAcc * 64);
+  }
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int total_tiles = p.tiles_m * p.batch;
+  const int ksteps = (p.K + 15) >> 4;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_full, w_bytes);
+      for (int tap = 0; tap < p.taps; ++tap) tma_load_3d(sW + (size_t)tap * w_tap_bytes, &p.tmB, w_full, 0, p.b_row[tap], 0);
+      int s = 0;
+      uint32_t ph = 1;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_t = tile % p.tiles_m, z = tile / p.tiles_m;
+        mbar_wait(&a_empty[s], ph);
+        mbar_arrive_expect_tx(&a_full[s], a_bytes);
+        tma_load_3d(sA + (size_t)s * a_stage, &p.tmA, &a_full[s], 0, m_t * kBM + p.cn_min_shift, p.a_batched ? z : 0);
+        if (++s == p.cn_stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc(kBM, p.cn_bnp, p.op_dtype == MA3_BF16 ? 1 : 0);
+      const uint64_t d0 = umma_desc_kmajor(smem_u32(sA), 128);
+      const uint32_t dhi = (uint32_t)(d0 >> 32), a_lo0 = (uint32_t)d0;
+      const uint32_t w_lo0 = (uint32_t)umma_desc_kmajor(smem_u32(sW), 128);
+      const uint32_t a_stage16 = a_stage >> 4, w_tap16 = w_tap_bytes >> 4;
+      mbar_wait(w_full, 0);
+      int s = 0, lt = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int as = lt & (kCnAcc - 1);
+        mbar_wait(&t_empty[as], ((lt / kCnAcc) & 1) ^ 1);
+        mbar_wait(&a_full[s], ph);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 64;
+        const uint32_t a_lo = a_lo0 + (uint32_t)s * a_stage16;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const uint32_t at = a_lo + (uint32_t)(p.a_shift[tap] - p.cn_min_shift) * 8u;   // 128-byte rows = 8 x 16 B
+          const uint32_t wt = w_lo0 + (uint32_t)tap * w_tap16;
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_f16_lohi<1>(d_tmem, at + 2 * ks, wt + 2 * ks, dhi, idesc, (tap | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(&a_empty[s]);
+        umma_commit(&t_full[as]);
+        if (++s == p.cn_stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3, ew = warp - 2, set = ew >> 2;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      if ((lt & 1) != set) continue;
+      const int m_t = tile % p.tiles_m, z = tile / p.tiles_m;
+      const int as = lt & (kCnAcc - 1);
+      const int m = m_t * kBM + q * 32 + lane;
+      RowRes<8> rr;
+      rowdirect_prefetch(p, z, m, 0, p.cn_bnp, rr);
+      const float brow = (p.bias && p.bias_per_row && m < p.M) ? p.bias[m] : 0.f;
+      const bool pre = rowdirect_res16(p);
+      mbar_wait(&t_full[as], (lt / kCnAcc) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 64;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        if (c0 < p.cn_bnp) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          rowdirect_group(p, z, m, c0, r, pre, rr.v[c0 >> 3], brow, col_bias ? sbias : nullptr);
+          rowdirect_group(p, z, m, c0 + 8, r + 8, pre, rr.v[(c0 >> 3) + 1], brow, col_bias ? sbias : nullptr);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(&t_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kCnAcc * 64);
+  }
+}
+
+// host side of the narrow-conv path; returns 1 when the problem is not eligible (caller falls back to the tap-GEMM)
+static int try_conv_narrow(const ma3_gemm_t* g, GemmKParams& kp, cudaStream_t st) {
+  static const bool off = getenv("MA3_CONV_NARROW") != nullptr && getenv("MA3_CONV_NARROW")[0] == '0';
+  if (off || g->epi != MA3_EPI_STORE || g->K > 64 || g->N > 64 || g->taps < 2 || g->cta_group == 2 || g->tile_n > 0 ||
+      g_gemm_debug_mode != 0 || g_trace != nullptr || g->b_batch_stride != 0)
+    return 1;
+  int lo = g->a_shift[0], hi = g->a_shift[0];
+  for (int i = 1; i < g->taps; ++i) { lo = g->a_shift[i] < lo ? g->a_shift[i] : lo; hi = g->a_shift[i] > hi ? g->a_shift[i] : hi; }
+  const int rows_a = kBM + (hi - lo);
+  const int bnp = (g->N + 15) / 16 * 16;
+  if (rows_a > 256) return 1;
+  const size_t w_bytes = ((size_t)g->taps * bnp * 128 + 1023) & ~(size_t)1023;
+  const size_t a_stage = ((size_t)rows_a * 128 + 1023) & ~(size_t)1023;
+  const size_t tail = 512;
+  int stages = (int)((200 * 1024 - w_bytes - tail) / a_stage);
+  if (stages < 2) return 1;
+  if (stages > 4) stages = 4;
+  kp.cn_rows_a = rows_a; kp.cn_min_shift = lo; kp.cn_bnp = bnp; kp.cn_stages = stages;
+  kp.BN = bnp; kp.BK = 64;
+  kp.tiles_m = (g->M + kBM - 1) / kBM; kp.tiles_n = 1;
+  const bool a_batched = g->a_batch_stride != 0;
+  {
+    uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->a_rows, (uint64_t)(a_batched ? g->batch : 1)};
+    uint64_t str[2] = {(uint64_t)g->a_ld * 2, (uint64_t)(a_batched ? g->a_batch_stride : g->a_rows * g->a_ld) * 2};
+    uint32_t box[3] = {64, (uint32_t)rows_a, 1};
+    int rc = encode_tmap(&kp.tmA, g->a, 2, 3, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->b_rows, 1};
+    uint64_t str[2] = {(uint64_t)g->b_ld * 2, (uint64_t)g->b_rows * g->b_ld * 2};
+    uint32_t box[3] = {64, (uint32_t)bnp, 1};
+    int rc = encode_tmap(&kp.tmB, g->b, 2, 3, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + w_bytes + stages * a_stage + tail;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(conv_narrow): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int total_tiles = kp.tiles_m * g->batch;
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  // at least half of the SM's shared memory so that one CTA (and its 256 TMEM columns) lives per SM
+  cudaError_t e = launch_pdl(conv_narrow_kernel, dim3((unsigned)grid), dim3(kGemmThreads), smem < 120 * 1024 ? 120 * 1024 : smem,
+                             st, 1, kp);
+  if (e != cudaSuccess) MA3_FAIL((int)e, "conv_narrow launch: %s", cudaGetErrorString(e));
+  MA3_LAUNCH_CHECK("conv_narrow");
+  return 0;
+}
+
 static uint32_t pow2_cols(int n) {
   uint32_t c = 32;
   while ((int)c < n) c <<= 1;
@@ -998,6 +1204,10 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
       }
       kp.vec_ok = vec ? 1 : 0;
       if (kp.alpha == 0.f) kp.alpha = 1.f;
+      {
+        const int rc = try_conv_narrow(g, kp, st);   // narrow multi-tap layers: input tile staged once (see above)
+        if (rc != 1) return rc;
+      }
       return launch<MA3_EPI_STORE>(kp, smem, grid, CG, st);
     }
     case MA3_EPI_GATE_RES:
