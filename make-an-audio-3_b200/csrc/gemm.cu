@@ -260,9 +260,26 @@ __device__ __forceinline__ void make_row_ctx(const GemmKParams& p, int z, int m0
 // different row).  The chunk is therefore transposed through a per-warp shared-memory patch (pitch 33 floats, conflict
 // free both ways) and processed row-wise: a group of lanes covers contiguous columns of one row, so loads of the
 // residual / RoPE table and the stores are coalesced.  All global loads of a chunk are issued before its first store.
+__device__ __forceinline__ void unpack16(uint4 u, int dtype, float (&v)[8]);
+
+// 16-bit residual pieces of one chunk in the STORE epilogue's row-wise layout (4 passes x 8 columns per lane), requested
+// before the accumulator chunk is loaded and staged so that their global-memory latency overlaps that work.
+struct ResPre {
+  uint4 v[4];
+  bool on;
+};
+__device__ __forceinline__ void res_pre_issue(const GemmKParams& p, int n0, int w, int lane, const RowCtx& rc, ResPre& rp) {
+  const int cg = (lane & 3) * 8, col = n0 + cg;
+  rp.on = p.res != nullptr && p.vec_ok && p.res_dtype != MA3_F32 && cg < w && col + 8 <= p.N;
+  if (!rp.on) return;
+  const uint16_t* res = reinterpret_cast<const uint16_t*>(p.res);
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass)
+    if (rc.off[pass] >= 0) rp.v[pass] = *reinterpret_cast<const uint4*>(res + rc.aux[pass] + col);
+}
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int n0, int w, const uint32_t* r,
-                                               float* stg, int lane, const RowCtx& rc) {
+                                               float* stg, int lane, const RowCtx& rc, const ResPre* rp = nullptr) {
   // V^T: with tokens % 8 == 0 the chunk is transposed through the staging patch below (16-byte stores along the token
   // axis); otherwise it is scattered straight from registers (lanes = consecutive tokens, 2-byte stores per column).
   const bool vt_fast = EPI == MA3_EPI_QKV_ROPE && (p.tokens & 7) == 0;
@@ -358,8 +375,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
       }
       if (p.res) {
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass)
-          if (rc.off[pass] >= 0) load8(p.res, p.res_dtype, rc.aux[pass] + col, vec, n, rv[pass]);
+        for (int pass = 0; pass < 4; ++pass) {
+          if (rc.off[pass] < 0) continue;
+          if (rp != nullptr && rp->on) unpack16(rp->v[pass], p.res_dtype, rv[pass]);
+          else load8(p.res, p.res_dtype, rc.aux[pass] + col, vec, n, rv[pass]);
+        }
       }
       if (p.accumulate) {
 #pragma unroll
@@ -793,6 +813,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
         const int w = min(32, p.BN - c0);
         const bool tr0 = ew == 0 && lane == 0 && c0 == 0;
         if (tr0) trace_evt(p, lt, 8);
+        ResPre rp;
+        // (the same trick for the accumulate operand was measured slower: 16 more live registers spill)
+        if constexpr (EPI == MA3_EPI_STORE) res_pre_issue(p, n_t * p.BN + c0, w, lane, rc, rp);
         if (w == 32) {
           tmem_ld32(taddr + c0, r);
         } else {
@@ -803,7 +826,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
         }
         tmem_ld_wait();
         if (tr0) trace_evt(p, lt, 9);
-        epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc);
+        if constexpr (EPI == MA3_EPI_STORE) epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc, &rp);
+        else epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc);
         if (tr0) trace_evt(p, lt, 10);
       }
       if (ew == 0 && lane == 0) trace_evt(p, lt, 6);

@@ -16,4 +16,5 @@ for (C, Tt, kk) in [(768, 2496, 11), (384, 9984, 7), (192, 19968, 7), (96, 39936
     w = (torch.randn(kk * C, C, device=dev) / (C * kk) ** .5).half(); bias = torch.zeros(C, device=dev)
     taps = [(j - kk // 2, j * C) for j in range(kk)]
     bench(f"conv k{kk} C{C} T{Tt} +res", lambda: ops.gemm(x, w, M=Tt, N=C, K=C, batch=B, a_rows=Tt, a_batch_stride=Tt * C, b_rows=kk * C, taps=taps, out=y, out_batch_stride=Tt * C, bias=bias, res=x), flops=2.0 * B * Tt * C * C * kk, bytes_=B * Tt * C * 2 * 3)
+    bench(f"conv k{kk} C{C} T{Tt} +res+acc", lambda: ops.gemm(x, w, M=Tt, N=C, K=C, batch=B, a_rows=Tt, a_batch_stride=Tt * C, b_rows=kk * C, taps=taps, out=y, out_batch_stride=Tt * C, bias=bias, res=x, alpha=1 / 3, accumulate=True), flops=2.0 * B * Tt * C * C * kk, bytes_=B * Tt * C * 2 * 4)
     bench(f"conv k{kk} C{C} T{Tt}", lambda: ops.gemm(x, w, M=Tt, N=C, K=C, batch=B, a_rows=Tt, a_batch_stride=Tt * C, b_rows=kk * C, taps=taps, out=y, out_batch_stride=Tt * C, bias=bias), flops=2.0 * B * Tt * C * C * kk, bytes_=B * Tt * C * 2 * 2)
