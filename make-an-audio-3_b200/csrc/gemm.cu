@@ -548,8 +548,22 @@ __device__ __forceinline__ void rowdirect_prefetch(const GemmKParams& p, int z, 
     if (gq * 8 < bn && n0 + gq * 8 + 8 <= p.N) rr.v[gq] = *reinterpret_cast<const uint4*>(rp + gq * 8);
 }
 
+// previous output values of a row (16-bit out, accumulate), requested together with the residual
+__device__ __forceinline__ bool rowdirect_acc16(const GemmKParams& p) {
+  return p.accumulate && p.vec_ok && p.out_dtype != MA3_F32;
+}
+__device__ __forceinline__ void rowdirect_prefetch_acc(const GemmKParams& p, int z, int m, int n0, int bn, RowRes<8>& ro) {
+  if (!rowdirect_acc16(p) || m >= p.M) return;
+  const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
+  const uint16_t* op = reinterpret_cast<const uint16_t*>(p.out) + (long long)z * p.out_batch_stride + orow * p.out_ld + n0;
+#pragma unroll
+  for (int gq = 0; gq < 8; ++gq)
+    if (gq * 8 < bn && n0 + gq * 8 + 8 <= p.N) ro.v[gq] = *reinterpret_cast<const uint4*>(op + gq * 8);
+}
+
 __device__ __forceinline__ void rowdirect_group(const GemmKParams& p, int z, int m, int col, const uint32_t* r,
-                                                bool has_pre, uint4 pre, float brow, const float* sbias = nullptr) {
+                                                bool has_pre, uint4 pre, float brow, const float* sbias = nullptr,
+                                                bool has_acc = false, uint4 acc = make_uint4(0u, 0u, 0u, 0u)) {
   // 8 columns [col, col + 8) of row m
   const int n = min(8, p.N - col);
   if (n <= 0 || m >= p.M) return;
@@ -594,7 +608,8 @@ __device__ __forceinline__ void rowdirect_group(const GemmKParams& p, int z, int
   }
   if (p.accumulate) {
     float ov[8];
-    load8(p.out, p.out_dtype, ooff, vec, n, ov);
+    if (has_acc && n == 8) unpack16(acc, p.out_dtype, ov);
+    else load8(p.out, p.out_dtype, ooff, vec, n, ov);
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] += ov[e];
   }
@@ -970,8 +985,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
       const int m = m_t * kBM + q * 32 + lane;
       RowRes<8> rr;
       rowdirect_prefetch(p, z, m, 0, p.cn_bnp, rr);
+      RowRes<8> ro;
+      rowdirect_prefetch_acc(p, z, m, 0, p.cn_bnp, ro);
       const float brow = (p.bias && p.bias_per_row && m < p.M) ? p.bias[m] : 0.f;
-      const bool pre = rowdirect_res16(p);
+      const bool pre = rowdirect_res16(p), pacc = rowdirect_acc16(p);
       mbar_wait(&t_full[as], (lt / kCnAcc) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 64;
@@ -981,8 +998,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
           uint32_t r[16];
           tmem_ld16(taddr + c0, r);
           tmem_ld_wait();
-          rowdirect_group(p, z, m, c0, r, pre, rr.v[c0 >> 3], brow, col_bias ? sbias : nullptr);
-          rowdirect_group(p, z, m, c0 + 8, r + 8, pre, rr.v[(c0 >> 3) + 1], brow, col_bias ? sbias : nullptr);
+          rowdirect_group(p, z, m, c0, r, pre, rr.v[c0 >> 3], brow, col_bias ? sbias : nullptr, pacc, ro.v[c0 >> 3]);
+          rowdirect_group(p, z, m, c0 + 8, r + 8, pre, rr.v[(c0 >> 3) + 1], brow, col_bias ? sbias : nullptr, pacc,
+                          ro.v[(c0 >> 3) + 1]);
         }
       }
       tc_fence_before();
