@@ -638,8 +638,8 @@ int ma3_rmsnorm_modulate(const float* x, const float* w, const float* mod, int64
   const int rps = mod ? rows_per_sample : M;   // without modulation all rows form one "sample"
   MA3_REQUIRE(!mod || M % rows_per_sample == 0, "rmsnorm_modulate: M must be samples * rows_per_sample");
   {
-    // bulk-staged variant when a block's rows fit shared memory twice per SM (MA3_RMS_BULK=0: register-staged kernel)
-    static const bool no_bulk = getenv("MA3_RMS_BULK") != nullptr && getenv("MA3_RMS_BULK")[0] == '0';
+    // bulk-staged variant when a block's rows fit shared memory twice per SM (MA3_RMS_BULK=1 selects it)
+    static const bool no_bulk = !(getenv("MA3_RMS_BULK") != nullptr && getenv("MA3_RMS_BULK")[0] == '1');   // opt-in until measured
     int R = (int)((110 * 1024 - 16) / ((size_t)D * sizeof(float))) - 2;
     if (R > kBulkRows) R = kBulkRows;
     const size_t bsmem = ((size_t)R + 2) * D * sizeof(float) + 16;
