@@ -129,84 +129,6 @@ __global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(const float* __re
   }
 }
 
-// Bulk-staged variant for the DiT's [samples x rows_per_sample, D] fp32 streams: a block takes kBulkRows consecutive
-// rows of one sample, ONE thread requests all of them with a single bulk async copy (the rows are contiguous in memory,
-// so the whole block's traffic is in flight at once and nothing is parked in registers), and the eight warps then make
-// two passes over shared memory (sum of squares, normalise + modulate).  With 24 rows per block the 16 x 312-row
-// residual stream is 208 blocks = a single wave at two blocks per SM, where the register-staged kernel above needs
-// 320 blocks = 1.08 waves.
-constexpr int kBulkRows = 24;   // upper bound; the host picks the largest count whose staging fits twice per SM
-
-template <typename TOut>
-__global__ void __launch_bounds__(256) rmsnorm_bulk_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                           const float* __restrict__ mod, long long mod_ld, int shift_off,
-                                                           int scale_off, int rows_per_sample, TOut* __restrict__ out,
-                                                           int D, float eps, int R) {
-  extern __shared__ __align__(128) uint8_t bulk_smem[];
-  float* rows = reinterpret_cast<float*>(bulk_smem);                       // [R][D]
-  float* sa = rows + (size_t)R * D;
-  float* sb = sa + D;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + D);
-  pdl_launch_dependents();
-  pdl_wait();
-  const int sample = blockIdx.y;
-  const int r_lo = blockIdx.x * R;
-  const int nrows = min(R, rows_per_sample - r_lo);
-  const long long row0 = (long long)sample * rows_per_sample + r_lo;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nvec = D >> 2;
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    fence_barrier_init();
-    const uint32_t bytes = (uint32_t)nrows * D * 4u;
-    mbar_arrive_expect_tx(bar, bytes);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(rows)),
-                 "l"(x + row0 * D), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-  }
-  const float* sc = mod ? mod + (long long)sample * mod_ld + scale_off : nullptr;
-  const float* sh = mod ? mod + (long long)sample * mod_ld + shift_off : nullptr;
-  for (int j = threadIdx.x; j < nvec; j += blockDim.x) {
-    float4 a = w ? reinterpret_cast<const float4*>(w)[j] : make_float4(1.f, 1.f, 1.f, 1.f);
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mod) {
-      const float4 s1 = reinterpret_cast<const float4*>(sc)[j];
-      b = reinterpret_cast<const float4*>(sh)[j];
-      a.x *= 1.f + s1.x; a.y *= 1.f + s1.y; a.z *= 1.f + s1.z; a.w *= 1.f + s1.w;
-    }
-    reinterpret_cast<float4*>(sa)[j] = a;
-    reinterpret_cast<float4*>(sb)[j] = b;
-  }
-  __syncthreads();          // barrier initialised and a / b staged
-  mbar_wait(bar, 0);
-  for (int r = warp; r < nrows; r += 8) {
-    const float4* xr = reinterpret_cast<const float4*>(rows + (size_t)r * D);
-    float ss = 0.f;
-    for (int j = lane; j < nvec; j += 32) {
-      const float4 v = xr[j];
-      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    }
-    ss = warp_sum(ss);
-    const float q = rsqrtf(ss / (float)D + eps);
-    TOut* op = out + (row0 + r) * D;
-    for (int j = lane; j < nvec; j += 32) {
-      const float4 v = xr[j];
-      const float4 a = reinterpret_cast<const float4*>(sa)[j];
-      const float4 b = reinterpret_cast<const float4*>(sb)[j];
-      const float o0 = fmaf(v.x * q, a.x, b.x), o1 = fmaf(v.y * q, a.y, b.y);
-      const float o2 = fmaf(v.z * q, a.z, b.z), o3 = fmaf(v.w * q, a.w, b.w);
-      if constexpr (sizeof(TOut) == 2) {
-        uint2 u;
-        if constexpr (std::is_same<TOut, __nv_bfloat16>::value) { u.x = pack_bf16(o0, o1); u.y = pack_bf16(o2, o3); }
-        else { u.x = pack_f16(o0, o1); u.y = pack_f16(o2, o3); }
-        *reinterpret_cast<uint2*>(op + j * 4) = u;
-      } else {
-        *reinterpret_cast<float4*>(op + j * 4) = make_float4(o0, o1, o2, o3);
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------- final layer
 // LayerNorm(no affine, eps) -> modulate -> Linear(D -> Cout) ; output transposed to [N, Cout, T].
 // kCfg: rows come in (uncond n, cond n+B) pairs; the guided velocity v = vu + s (vc - vu) is formed in-kernel and
@@ -637,32 +559,6 @@ int ma3_rmsnorm_modulate(const float* x, const float* w, const float* mod, int64
               "rmsnorm_modulate: pointers must be 16-byte aligned");
   const int rps = mod ? rows_per_sample : M;   // without modulation all rows form one "sample"
   MA3_REQUIRE(!mod || M % rows_per_sample == 0, "rmsnorm_modulate: M must be samples * rows_per_sample");
-  {
-    // bulk-staged variant when a block's rows fit shared memory twice per SM (MA3_RMS_BULK=1 selects it)
-    static const bool no_bulk = !(getenv("MA3_RMS_BULK") != nullptr && getenv("MA3_RMS_BULK")[0] == '1');   // opt-in until measured
-    int R = (int)((110 * 1024 - 16) / ((size_t)D * sizeof(float))) - 2;
-    if (R > kBulkRows) R = kBulkRows;
-    const size_t bsmem = ((size_t)R + 2) * D * sizeof(float) + 16;
-    if (!no_bulk && R >= 8 && rps >= R) {
-      const dim3 bgrid((unsigned)((rps + R - 1) / R), (unsigned)(M / rps));
-#define RMS_BULK(TO)                                                                                                  \
-  do {                                                                                                                \
-    static bool cfgd = false;                                                                                         \
-    if (!cfgd) {                                                                                                      \
-      cudaFuncSetAttribute(rmsnorm_bulk_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);         \
-      cfgd = true;                                                                                                    \
-    }                                                                                                                 \
-    launch_pdl(rmsnorm_bulk_kernel<TO>, bgrid, dim3(256), bsmem, ST(stream), 1, x, w, mod, (long long)mod_ld, shift_off, \
-               scale_off, rps, (TO*)out, D, eps, R);                                                                 \
-  } while (0)
-      if (out_dtype == MA3_BF16) RMS_BULK(__nv_bfloat16);
-      else if (out_dtype == MA3_F16) RMS_BULK(__half);
-      else RMS_BULK(float);
-#undef RMS_BULK
-      MA3_LAUNCH_CHECK("rmsnorm_modulate");
-      return 0;
-    }
-  }
   const dim3 grid((unsigned)((rps + kRmsRows - 1) / kRmsRows), (unsigned)(M / rps));
   const size_t smem = 2 * (size_t)D * sizeof(float);
   const int nv = (D / 4 + 31) / 32;  // float4 per lane
