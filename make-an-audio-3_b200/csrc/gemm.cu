@@ -639,6 +639,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   if (threadIdx.x == 0) trace_evt(p, 15, 0);   // kernel entry
+  if (p.trace && threadIdx.x == 0) {            // launch span over all CTAs (ns): first entry, last exit
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(reinterpret_cast<unsigned long long*>(p.trace) + 250, t);
+  }
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA);
@@ -859,6 +864,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
   if constexpr (CG == 2) cluster_sync_all();
   else __syncthreads();
   if (threadIdx.x == 0) trace_evt(p, 15, 2);   // all roles done
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(reinterpret_cast<unsigned long long*>(p.trace) + 251, t);
+  }
   if (warp == 1) {
     __syncwarp();
     if constexpr (CG == 2) tmem_dealloc2(tmem_base, p.tmem_cols);
@@ -1148,6 +1158,26 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   const int BK = g->K > 32 ? 64 : (g->K > 16 ? 32 : 16);
   int BN = g->tile_n;
   int CG = g->cta_group;
+  {
+    // experiment hook: MA3_TILE_<epilogue id>="tile_n,cta_group" overrides the automatic choice for large problems
+    // (in-step A/B runs of bench.py; the isolated probes see L2-warm operands and a different clock)
+    static int ov[5][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}};   // [4]: GATE_RES with K > 2048
+    static bool parsed = false;
+    if (!parsed) {
+      for (int e = 0; e < 5; ++e) {
+        char name[32];
+        snprintf(name, sizeof(name), "MA3_TILE_%d", e);
+        const char* v = getenv(name);
+        if (v) sscanf(v, "%d,%d", &ov[e][0], &ov[e][1]);
+      }
+      parsed = true;
+    }
+    const int oi = (g->epi == MA3_EPI_GATE_RES && g->K > 2048) ? 4 : g->epi;
+    if (oi >= 0 && oi < 5 && ov[oi][0] > 0 && BN <= 0 && CG == 0 && g->M >= 2048 && g->N >= 512) {
+      BN = ov[oi][0];
+      CG = ov[oi][1];
+    }
+  }
   MA3_REQUIRE(CG >= 0 && CG <= 2, "gemm: cta_group must be 0 (auto), 1 or 2");
   if (BN <= 0 || CG == 0) {
     // pick (tile_n, cta_group) by the modelled critical path in SM clocks (constants measured with tools/probe_trace.py)

@@ -162,6 +162,29 @@ def test_gemm_gate_residual_stream_k(ops, M, N, K, cg):
     assert rel(outs[0], outs[1]) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K,T,tn,cg,ld", [(200, 176, 64, 40, 48, 1, 176), (333, 100, 96, 37, 0, 1, 104),
+                                              (520, 304, 128, 65, 80, 1, 320), (777, 224, 256, 111, 96, 2, 224)])
+def test_gemm_gate_residual_ragged(ops, M, N, K, T, tn, cg, ld):
+    """The tensor reduce-add epilogue on ragged shapes: row and column tails (clipped by the tensor map), 16-wide last
+    chunks (tile_n % 32 == 16), a padded output pitch, several samples per 32-row chunk; untouched columns stay put."""
+    from ma3_b200 import lib as L
+    ns = (M + T - 1) // T
+    Mp = ns * T
+    a = torch.randn(Mp, K, generator=g(70)).bfloat16().cuda()
+    b = (torch.randn(N, K, generator=g(71)) / K ** .5).bfloat16().cuda()
+    h0 = torch.randn(Mp, ld, generator=g(72)).cuda()
+    gate = torch.randn(ns, N, generator=g(73)).cuda()
+    h = h0.clone()
+    ops.gemm(a, b, M=M, N=N, K=K, epi=L.EPI_GATE_RES, out=h, out_ld=ld, gate=gate, rows_per_sample=T, tile_n=tn, cta_group=cg)
+    ref = h0.clone()
+    ref[:M, :N] += (gate.repeat_interleave(T, 0) * (a.float() @ b.float().t()))[:M]
+    assert rel(h[:M, :N], ref[:M, :N]) < 1e-4
+    assert torch.equal(h[M:], h0[M:]) and torch.equal(h[:, N:], h0[:, N:])
+    h2 = h0.clone()
+    ops.gemm(a, b, M=M, N=N, K=K, epi=L.EPI_GATE_RES, out=h2, out_ld=ld, gate=gate, rows_per_sample=T, tile_n=tn, cta_group=cg)
+    assert torch.equal(h, h2)
+
+
 # ------------------------------------------------------------------------------------------------ QKV+RoPE, attention
 def _qkv_attention_case(ops, D, H, T, L, Ns, seed):
     """QKV GEMM with RoPE scatter followed by the fused self+cross attention, against oracle.attention pieces."""

@@ -1,9 +1,12 @@
 import sys, os, ctypes
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tools")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ma3_b200 import ops, lib as L
 lib = L.require_device()
 lib.ma3_debug_set_gemm_trace.argtypes = [ctypes.c_void_p]
+lib.ma3_debug_set_gemm_mode.argtypes = [ctypes.c_int]
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+lib.ma3_debug_set_gemm_mode(mode); print('debug mode', mode)
 dev = "cuda"; bf = torch.bfloat16
 Ns, T, D, F = 16, 312, 1152, 3072
 M = Ns * T
@@ -13,7 +16,7 @@ h = torch.randn(M, D, device=dev); mod = torch.randn(Ns, D, device=dev) * 0.1
 cases = {"wo": lambda **kw: ops.gemm(u, wo, M=M, N=D, K=D, epi=L.EPI_GATE_RES, out=h, gate=mod, rows_per_sample=T, **kw),
          "w2": lambda **kw: ops.gemm(mid, w2, M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=h, gate=mod, rows_per_sample=T, **kw)}
 for name, fn in cases.items():
-    for kw in (dict(cta_group=1, tile_n=192, stream_k=-1), dict(cta_group=1, tile_n=192, stream_k=1), dict(cta_group=1, tile_n=256, stream_k=1)):
+    for kw in (dict(cta_group=1, tile_n=192, stream_k=-1), dict(cta_group=2, tile_n=192, stream_k=-1), dict(cta_group=1, tile_n=192, stream_k=1)):
         for _ in range(3): fn(**kw)
         torch.cuda.synchronize()
         tr = torch.zeros(256, dtype=torch.int64, device=dev)
