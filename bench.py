@@ -266,7 +266,7 @@ def main():
     # live roofline of the dominant kernel: CUDA events around every launch on the launching stream.  With graphs the
     # plans are re-captured with the events as graph nodes and replayed once, so each interval is device time of one
     # kernel with nothing from the host in it; --no-graph brackets the eager launches instead.
-    roofline, breakdown = None, None
+    roofline, breakdown, gemm_shapes = None, None, None
     if rank == 0:
         ops.PROFILE = []
         if args.no_graph:
@@ -289,6 +289,17 @@ def main():
             d[1] += work
             d[2] += 1
         tot_ms = sum(d[0] for d in agg.values())
+        # the GEMM family by problem shape (in-step device time, launches, achieved TFLOP/s), largest first
+        shapes = {}
+        for tag, a, b, work in prof:
+            if tag.startswith("tap_gemm/"):
+                d = shapes.setdefault(tag[len("tap_gemm/"):], [0.0, 0.0, 0])
+                d[0] += a.elapsed_time(b)
+                d[1] += work
+                d[2] += 1
+        gemm_shapes = {k: {"ms": round(v[0], 3), "launches": v[2], "us_per_launch": round(1e3 * v[0] / v[2], 1),
+                           "TFLOPs": round(v[1] / (v[0] * 1e-3) / 1e12, 1)}
+                       for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:24]}
         breakdown = {k: {"ms": round(v[0], 3), "launches": v[2], "share": round(v[0] / tot_ms, 4)} for k, v in
                      sorted(agg.items(), key=lambda kv: -kv[1][0])}
         peaks = {}
@@ -346,7 +357,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stage_ms,
-                "kernel_breakdown": breakdown}
+                "kernel_breakdown": breakdown, "gemm_shapes": gemm_shapes}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -124,7 +124,7 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
     d.tile_n = tile_n
     d.cta_group = cta_group
     d.stream_k = stream_k
-    with _Span("tap_gemm/" + _EPI_NAMES[epi], 2.0 * M * N * K * len(taps) * batch):
+    with _Span(f"tap_gemm/{_EPI_NAMES[epi]}/M{M} N{N} K{K} taps{len(taps)} batch{batch}", 2.0 * M * N * K * len(taps) * batch):
         L.check(lib.ma3_gemm(C.byref(d), L.stream_ptr()), "ma3_gemm")
     return out
 
