@@ -47,6 +47,7 @@ struct GemmKParams {
   int model_dim, head_dim, head_dim_pad, heads, tokens, tokens_pad;
   float q_scale;
   int first_section;
+  int qkv_fast;      // QKV_ROPE: lean chunk code for full, single-section chunks (MA3_QKV_FAST=0 switches it off)
   int op_dtype;
   float inv_rows_per_sample, inv_tokens, inv_head_dim;  // exact-division helpers (see fast_div)
   int debug_mode;    // diagnostics: 1 = no TMA loads, 2 = no MMAs
@@ -513,6 +514,91 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
   __syncwarp();
 }
 
+// QKV_ROPE fast path for a full 32 x 32 chunk that lies in one section (q, k or v) with all 32 rows inside M and
+// tokens % 8 == 0: the same arithmetic, memory accesses and layouts as epilogue_chunk<QKV_ROPE>, with every row / dtype
+// / section test hoisted out of the pass loops.  The epilogue warps (two per scheduler, dependent chains) are
+// instruction-latency bound -- ncu: ~350 warp-instructions per chunk of which 140 are loads, math and stores -- so the
+// instruction count is the epilogue time, and this epilogue is longer than its tile's mainloop.
+template <bool kBf16>
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  if constexpr (kBf16) return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  else return make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
+}
+
+template <bool kBf16, bool kScale, bool kRope>
+__device__ __forceinline__ void qk_rows_fast(uint16_t* dst, const RowCtx& rc, const float* sp, const float* rope_d, float sc) {
+  float4 cs[4][2];
+  if constexpr (kRope) {
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const float4* c4 = reinterpret_cast<const float4*>(rope_d + rc.aux[pass]);
+      cs[pass][0] = __ldg(c4);
+      cs[pass][1] = __ldg(c4 + 1);
+    }
+  }
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const float4 xa = lds_f4(sp), xb = lds_f4(sp + 4);
+    float v[8];
+    if constexpr (kRope) {
+      const float4 ca = cs[pass][0], cb = cs[pass][1];
+      v[0] = xa.x * ca.x - xa.y * ca.y; v[1] = xa.x * ca.y + xa.y * ca.x;
+      v[2] = xa.z * ca.z - xa.w * ca.w; v[3] = xa.z * ca.w + xa.w * ca.z;
+      v[4] = xb.x * cb.x - xb.y * cb.y; v[5] = xb.x * cb.y + xb.y * cb.x;
+      v[6] = xb.z * cb.z - xb.w * cb.w; v[7] = xb.z * cb.w + xb.w * cb.z;
+    } else {
+      v[0] = xa.x; v[1] = xa.y; v[2] = xa.z; v[3] = xa.w; v[4] = xb.x; v[5] = xb.y; v[6] = xb.z; v[7] = xb.w;
+    }
+    if constexpr (kScale) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= sc;
+    }
+    *reinterpret_cast<uint4*>(dst + rc.off[pass]) = pack8<kBf16>(v);
+    sp += 8 * kStagePitch;
+  }
+}
+
+template <bool kBf16>
+__device__ __forceinline__ void qkv_chunk_fast(const GemmKParams& p, int n0, int which, int sec, const uint32_t* r,
+                                               float* stg, int lane, const RowCtx& rc) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) sts_u4(stg + lane * kStagePitch + e, r[e], r[e + 1], r[e + 2], r[e + 3]);
+  __syncwarp();
+  const int hd = p.head_dim;
+  if (which == 2) {
+    // lane <-> column (one head dimension); 4 groups of 8 consecutive tokens, one 16-byte store each
+    const int within = n0 + lane - sec * p.model_dim;
+    const int head = fast_div(within, p.inv_head_dim);
+    const int d = within - head * hd;
+    uint16_t* vt = reinterpret_cast<uint16_t*>(p.vt_out) + ((long long)head * p.head_dim_pad + d) * p.tokens_pad;
+    const float* sp = stg + lane;
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = lds_f1(sp + (gq * 8 + e) * kStagePitch);
+      *reinterpret_cast<uint4*>(vt + rc.off[4 + gq]) = pack8<kBf16>(v);
+    }
+  } else {
+    // 4 lanes x 8 columns per row, 8 rows per pass; the 8 columns never straddle a head (head_dim % 8 == 0)
+    const int cg = (lane & 3) * 8;
+    const int within = n0 + cg - sec * p.model_dim;
+    const int head = fast_div(within, p.inv_head_dim);
+    const int d = within - head * hd;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(which == 0 ? p.q_out : p.k_out) + (long long)head * p.tokens * p.head_dim_pad + d;
+    const float* sp = stg + (lane >> 2) * kStagePitch + cg;
+    const bool scale = which == 0 && p.q_scale != 1.0f;
+    if (p.rope) {
+      if (scale) qk_rows_fast<kBf16, true, true>(dst, rc, sp, p.rope + d, p.q_scale);
+      else qk_rows_fast<kBf16, false, true>(dst, rc, sp, p.rope + d, 1.0f);
+    } else {
+      if (scale) qk_rows_fast<kBf16, true, false>(dst, rc, sp, nullptr, p.q_scale);
+      else qk_rows_fast<kBf16, false, false>(dst, rc, sp, nullptr, 1.0f);
+    }
+  }
+  __syncwarp();
+}
+
 // STORE epilogue for narrow tiles (BN <= 64): thread <-> output row, all BN columns of the row straight from the
 // TMEM registers to global memory in 8-column (16-byte) pieces.  For the channels-last conv outputs this path serves
 // (rows of 2 * BN contiguous bytes) the warp's stores cover a contiguous span, no shared-memory transpose or warp
@@ -828,6 +914,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       if (ew == 0 && lane == 0) trace_evt(p, lt, 5);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.tmem_stage_cols;
+      // QKV_ROPE: all 32 rows of this warp inside M and 16-byte V^T stores possible -> lean chunk code
+      const bool qkv_fast = EPI == MA3_EPI_QKV_ROPE && p.qkv_fast && (p.tokens & 7) == 0 && m0 + 32 <= p.M;
       for (int c0 = half * 32; c0 < p.BN; c0 += 32 * (kEpiWarps / 4)) {
         uint32_t r[32];
         const int w = min(32, p.BN - c0);
@@ -846,8 +934,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
         }
         tmem_ld_wait();
         if (tr0) trace_evt(p, lt, 9);
-        if constexpr (EPI == MA3_EPI_STORE) epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc, &rp);
-        else epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc);
+        if constexpr (EPI == MA3_EPI_STORE) {
+          epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc, &rp);
+        } else if constexpr (EPI == MA3_EPI_QKV_ROPE) {
+          const int n0 = n_t * p.BN + c0;
+          const int sec = (n0 >= p.model_dim) + (n0 >= 2 * p.model_dim);
+          const int sec_last = (n0 + 31 >= p.model_dim) + (n0 + 31 >= 2 * p.model_dim);
+          if (qkv_fast && w == 32 && sec == sec_last && n0 + 32 <= p.N) {
+            if (p.op_dtype == MA3_BF16) qkv_chunk_fast<true>(p, n0, sec + p.first_section, sec, r, stg, lane, rc);
+            else qkv_chunk_fast<false>(p, n0, sec + p.first_section, sec, r, stg, lane, rc);
+          } else {
+            epilogue_chunk<EPI>(p, m0, n0, w, r, stg, lane, rc);
+          }
+        } else {
+          epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc);
+        }
         if (tr0) trace_evt(p, lt, 10);
       }
       if (ew == 0 && lane == 0) trace_evt(p, lt, 6);
@@ -1249,6 +1350,10 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   kp.inv_rows_per_sample = g->rows_per_sample > 0 ? 1.0f / (float)g->rows_per_sample : 0.f;
   kp.inv_tokens = g->tokens > 0 ? 1.0f / (float)g->tokens : 0.f;
   kp.inv_head_dim = g->head_dim > 0 ? 1.0f / (float)g->head_dim : 0.f;
+  {
+    static const bool qf = !(getenv("MA3_QKV_FAST") && getenv("MA3_QKV_FAST")[0] == '0');
+    kp.qkv_fast = qf ? 1 : 0;
+  }
   kp.trace = g_trace;
   kp.debug_mode = g_gemm_debug_mode;
 
