@@ -1,13 +1,12 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -4 > gpurun_out/tests_gpu_r01f.log; cat gpurun_out/tests_gpu_r01f.log
-timeout 900 python bench.py > gpurun_out/bench_default_r01f.json 2> gpurun_out/bench_default_r01f.err; python -c "
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "qkv or attention" 2>&1 | tail -2
+run() { timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_$1.json 2> gpurun_out/bench_ab_$1.err; python -c "
 import json
-d=json.loads(open('gpurun_out/bench_default_r01f.json').read().strip().splitlines()[-1])
-print(round(d['value'],1), round(d['ms_per_step'],2), d['clocks'], d['roofline']['frac'], d['e2e']['value'], d['cpu_baseline']['value'])
-for k,v in list(d['gemm_shapes'].items())[:4]: print(k, v)
-"
-for m in "M 1" "M 16" "XXL 1" "MOE 1"; do set -- $m; timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --model $1 --prompts $2 > gpurun_out/bench_r01f_$1_$2.json 2>/dev/null; python -c "
-import json
-d=json.loads(open('gpurun_out/bench_r01f_$1_$2.json').read().strip().splitlines()[-1])
-print('$1 $2', round(d['value'],1), round(d['ms_per_step'],2), d['stage_ms'])
-"; done
+d=json.loads(open('gpurun_out/bench_ab_$1.json').read().strip().splitlines()[-1])
+q=[v for k,v in d['gemm_shapes'].items() if k.startswith('qkv')][0]
+print('$1', round(d['value'],1), round(d['ms_per_step'],2), d['clocks']['sm_mhz'], 'tap_gemm', d['kernel_breakdown']['tap_gemm']['ms'], 'qkv', q)
+"; }
+MA3_LIB=$PWD/make-an-audio-3_b200/csrc/libma3b200_lean.so run lean1
+run pre1
+MA3_LIB=$PWD/make-an-audio-3_b200/csrc/libma3b200_lean.so run lean2
+run pre2
