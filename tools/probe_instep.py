@@ -15,6 +15,7 @@ pipe = build_random_pipeline("XL", vocoder_h=dict(Bn.BIGVGAN_H), seed=0, device=
 B, T, Lc, Cd = 8, Bn.T_LATENT, Bn.L_CTX, cfg["context_dim"]
 cond = torch.randn(B, Lc, Cd, device=dev); unc = torch.randn(B, Lc, Cd, device=dev); x0 = torch.randn(B, 20, T, device=dev)
 which = {"qkv": L.EPI_QKV_ROPE, "swiglu": L.EPI_SWIGLU, "gate": L.EPI_GATE_RES}
+if len(sys.argv) > 1: which = {k: v for k, v in which.items() if k in sys.argv[1:]}
 target_n = 300   # the 300th launch of that epilogue in the captured step (a mid-step DiT block)
 real_gemm = ops.gemm
 for name, epi in which.items():
