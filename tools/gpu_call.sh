@@ -1,12 +1,7 @@
+set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py -x -q -m gpu -k "swiglu or dit or sampler or pipeline" 2>&1 | tail -2
-run() { timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_$1.json 2> gpurun_out/bench_ab_$1.err; python -c "
-import json
-d=json.loads(open('gpurun_out/bench_ab_$1.json').read().strip().splitlines()[-1])
-q=[v for k,v in d['gemm_shapes'].items() if k.startswith('swiglu')][0]
-print('$1', round(d['value'],1), round(d['ms_per_step'],2), d['clocks']['sm_mhz'], 'tap_gemm', d['kernel_breakdown']['tap_gemm']['ms'], 'w13', q)
-"; }
-MA3_LIB=$PWD/make-an-audio-3_b200/csrc/libma3b200_lean.so run old1
-run new1
-MA3_LIB=$PWD/make-an-audio-3_b200/csrc/libma3b200_lean.so run old2
-run new2
+CMD="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline"
+$CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain.log; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -s 15267 -c 5089 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tap_gemm -s 400 -c 4 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
+ls -la gpurun_out/ | tail -5

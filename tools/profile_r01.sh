@@ -6,7 +6,7 @@ CMD="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain.log; exit 1; }
 tail -c 600 gpurun_out/plain.log
 # (1) launch list of one full step: skip the launches of the 3 warm-up steps (5089 launches per step, eager)
-ncu --metrics gpu__time_duration.sum --clock-control none -s 15300 -c 5100 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 15267 -c 5089 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 # (2) full-set captures: the four DiT GEMMs of one block, attention, the tensor-core Activation1d, rmsnorm, narrow conv
 ncu --set full --clock-control none --import-source on -k regex:tap_gemm -s 400 -c 4 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
