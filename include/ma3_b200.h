@@ -37,6 +37,9 @@ int ma3_version(void);
 int ma3_check_device(void);
 /* number of kernel launches enqueued by this library in this process so far (bench.py reports the delta). */
 int64_t ma3_launch_count(void);
+/* L2 access-policy window for launches on `stream` (persisting hits on [ptr, ptr+bytes), streaming elsewhere); NULL
+ * removes it.  Used for the DiT's fp32 residual stream, which every block reads twice and reduces into twice. */
+int ma3_l2_persist(const void* ptr, size_t bytes, void* stream);
 const char* ma3_last_error(void);
 
 /* ------------------------------------------------------------------------------------------------------------------

@@ -101,4 +101,31 @@ int ma3_check_device(void) {
   return 0;
 }
 
+/* Mark [ptr, ptr + bytes) as L2-persisting for kernels launched (or captured) on `stream` from now on: hits keep the
+ * lines resident, other addresses are treated as streaming.  ptr == NULL removes the window.  The set-aside is sized
+ * to the window (capped by the device limit). */
+int ma3_l2_persist(const void* ptr, size_t bytes, void* stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int max_persist = 0, max_window = 0;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof(v));
+  if (ptr != nullptr && bytes > 0) {
+    size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+    size_t keep = win < (size_t)max_persist ? win : (size_t)max_persist;
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, keep);
+    if (e != cudaSuccess) MA3_FAIL((int)e, "cudaDeviceSetLimit(persisting L2): %s", cudaGetErrorString(e));
+    v.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+    v.accessPolicyWindow.num_bytes = win;
+    v.accessPolicyWindow.hitRatio = win > 0 ? (float)keep / (float)win : 0.f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  }
+  cudaError_t e = cudaStreamSetAttribute(reinterpret_cast<cudaStream_t>(stream), cudaStreamAttributeAccessPolicyWindow, &v);
+  if (e != cudaSuccess) MA3_FAIL((int)e, "cudaStreamSetAttribute(access policy window): %s", cudaGetErrorString(e));
+  return 0;
+}
+
 }  // extern "C"

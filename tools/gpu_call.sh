@@ -1,12 +1,13 @@
 mkdir -p gpurun_out
-run() { timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_$1.json 2> gpurun_out/bench_ab_$1.err; python -c "
+timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -4 > gpurun_out/tests_gpu_r01g.log; cat gpurun_out/tests_gpu_r01g.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/bench_default_r01g.json 2> gpurun_out/bench_default_r01g.err; python -c "
 import json
-d=json.loads(open('gpurun_out/bench_ab_$1.json').read().strip().splitlines()[-1])
-g=[(k.split('/')[1][:22],v['us_per_launch']) for k,v in d['gemm_shapes'].items() if k.startswith('gate_res')]
-print('$1', round(d['value'],1), round(d['ms_per_step'],2), d['clocks']['sm_mhz'], 'tap_gemm', d['kernel_breakdown']['tap_gemm']['ms'], g)
-"; }
-run base1
-MA3_TILE_1=176,1 run wo176
-MA3_TILE_4=176,1 run w2_176
-MA3_TILE_1=176,1 MA3_TILE_4=176,1 run both176
-run base2
+d=json.loads(open('gpurun_out/bench_default_r01g.json').read().strip().splitlines()[-1])
+print(round(d['value'],1), round(d['ms_per_step'],2), d['clocks'], round(d['roofline']['frac'],4), round(d['e2e']['value'],1), d['cpu_baseline']['value'], d['stage_ms'])
+"
+for m in "M 16" "XXL 1"; do set -- $m; timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --model $1 --prompts $2 > gpurun_out/bench_r01g_$1_$2.json 2>/dev/null; python -c "
+import json
+d=json.loads(open('gpurun_out/bench_r01g_$1_$2.json').read().strip().splitlines()[-1])
+print('$1 $2', round(d['value'],1), round(d['ms_per_step'],2), d['stage_ms'])
+"; done
