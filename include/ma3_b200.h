@@ -38,8 +38,12 @@ int ma3_check_device(void);
 /* number of kernel launches enqueued by this library in this process so far (bench.py reports the delta). */
 int64_t ma3_launch_count(void);
 /* L2 access-policy window for launches on `stream` (persisting hits on [ptr, ptr+bytes), streaming elsewhere); NULL
- * removes it.  Used for the DiT's fp32 residual stream, which every block reads twice and reduces into twice. */
+ * removes the stream's window.  Used for the DiT's fp32 residual stream, which every block reads twice and reduces
+ * into twice.  NOTE: this is the one entry point with a device-wide side effect: it sizes the device's persisting-L2
+ * set-aside (cudaLimitPersistingL2CacheSize) to the window, and kernels captured while the window was set keep using
+ * it on replay.  ma3_l2_persist_release() gives the set-aside back (limit 0 + cudaCtxResetPersistingL2Cache). */
 int ma3_l2_persist(const void* ptr, size_t bytes, void* stream);
+int ma3_l2_persist_release(void);
 const char* ma3_last_error(void);
 
 /* ------------------------------------------------------------------------------------------------------------------

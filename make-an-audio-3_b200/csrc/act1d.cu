@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __ha
   }
 }
 
-static bool g_filter_set = false;
+static DeviceOnce g_filter_set;   // the taps live in __constant__ memory: one copy per device
 
 }  // namespace ma3
 
@@ -474,14 +474,14 @@ int ma3_act1d_set_filter(const float* taps12, void* stream) {
                                 reinterpret_cast<cudaStream_t>(stream));
   if (e == cudaSuccess) e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) MA3_FAIL((int)e, "act1d_set_filter: %s", cudaGetErrorString(e));
-  g_filter_set = true;
+  g_filter_set.mark();
   return 0;
 }
 
 // x [B, T, C] (f32 / f16 / bf16) -> out [B, T, C] (f16 / bf16); alpha, beta [C] fp32 (beta NULL = Snake).
 int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float* alpha, const float* beta, int B,
               int T, int C, int logscale, void* stream) {
-  MA3_REQUIRE(g_filter_set, "act1d: call ma3_act1d_set_filter first");
+  MA3_REQUIRE(!g_filter_set.pending(), "act1d: call ma3_act1d_set_filter first (once per device)");
   MA3_REQUIRE(x && out && alpha && B > 0 && T > 0, "act1d: null pointer or empty");
   MA3_REQUIRE(C % 16 == 0, "act1d: C=%d must be a multiple of 16 (pad channels)", C);
   MA3_REQUIRE(aligned16(x) && aligned16(out), "act1d: pointers must be 16-byte aligned");
@@ -495,10 +495,10 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
     const long long total = (long long)tiles_c * tiles_t * B;
     const int pitch = CT * 2 + 16;
     const size_t smem = 2 * (size_t)(TB + 16) * pitch + (size_t)TB * pitch;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.pending()) {
       cudaFuncSetAttribute(act1d_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      configured = true;
+      configured.mark();
     }
     long long gridl = 3LL * num_sms();
     if (gridl > total) gridl = total;
@@ -521,10 +521,10 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
   cudaError_t le = cudaSuccess;
 #define ACT_CASE(TI, TO)                                                                                            \
   do {                                                                                                              \
-    static bool configured = false;                                                                                 \
-    if (!configured) {                                                                                              \
+    static DeviceOnce configured;                                                                                 \
+    if (configured.pending()) {                                                                                              \
       cudaFuncSetAttribute(act1d_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);          \
-      configured = true;                                                                                            \
+      configured.mark();                                                                                            \
     }                                                                                                               \
     le = launch_pdl(act1d_kernel<TI, TO>, grid, dim3(kActThreads), smem, st, 1, (const TI*)x, (TO*)out, alpha, beta, \
                     B, T, C, CT, tiles_c, tiles_t, logscale);                                                       \

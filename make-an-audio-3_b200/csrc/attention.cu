@@ -789,11 +789,11 @@ template <int HDP, int HD, int BKV>
 static int launch_attn2(const AttnParams& p, int NS, cudaStream_t st) {
   constexpr int HDO = (HD + 1 + 15) / 16 * 16;
   constexpr size_t smem = 128 * HDP * 2 + 2 * (BKV * HDP * 2 + HDO * 128) + 128 + 2048;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn2_kernel<HDP, HD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(attn2): %s", cudaGetErrorString(e));
-    configured = true;
+    configured.mark();
   }
   dim3 grid((unsigned)((p.T + 127) / 128), (unsigned)p.H, (unsigned)NS);
   cudaError_t le = launch_pdl(attn2_kernel<HDP, HD, BKV>, grid, dim3(kAttn2Threads), smem, st, 1, p);
@@ -805,11 +805,11 @@ static int launch_attn2(const AttnParams& p, int NS, cudaStream_t st) {
 template <int HDP, int HD, int BKV>
 static int launch_attn(const AttnParams& p, int NS, cudaStream_t st) {
   constexpr size_t smem = 128 * HDP * 2 + 2 * (2 * BKV * HDP * 2) + 128 * BKV * 2 + 256;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<HDP, HD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
-    configured = true;
+    configured.mark();
   }
   dim3 grid((unsigned)((p.T + 127) / 128), (unsigned)p.H, (unsigned)NS);
   cudaError_t le = launch_pdl(attn_kernel<HDP, HD, BKV>, grid, dim3(kAttnThreads), smem, st, 1, p);

@@ -588,20 +588,20 @@ int ma3_final_layer(const float* h, const float* mod, int64_t mod_ld, int shift_
   MA3_REQUIRE((Cout * D) % 4 == 0 && aligned16(W), "final_layer: W must be 16-byte aligned");
   const size_t smem = (size_t)Cout * D * sizeof(float);
   {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.pending()) {
       cudaFuncSetAttribute(final_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      configured = true;
+      configured.mark();
     }
   }
   MA3_REQUIRE(smem <= 200 * 1024, "final_layer: Cout * D too large for shared memory");
   const unsigned fgrid = (unsigned)min((long long)num_sms(), ((long long)N * T + 7) / 8);
 #define FL_FAST(KV4)                                                                                                   \
   do {                                                                                                                 \
-    static bool cfgd = false;                                                                                          \
-    if (!cfgd) {                                                                                                       \
+    static DeviceOnce cfgd;                                                                                                \
+    if (cfgd.pending()) {                                                                                                       \
       cudaFuncSetAttribute(final_layer_fast_kernel<false, KV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-      cfgd = true;                                                                                                     \
+      cfgd.mark();                                                                                                     \
     }                                                                                                                  \
     launch_pdl(final_layer_fast_kernel<false, KV4>, dim3(fgrid), dim3(256), smem, ST(stream), 1, h, mod, (long long)mod_ld, \
                shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, (const float*)nullptr, (float*)nullptr, 0.f, 0.f); \
@@ -628,20 +628,20 @@ int ma3_final_layer_cfg_euler(const float* h, const float* mod, int64_t mod_ld, 
   MA3_REQUIRE((Cout * D) % 4 == 0 && aligned16(W), "final_layer_cfg_euler: W must be 16-byte aligned");
   const size_t smem = (size_t)Cout * D * sizeof(float);
   {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.pending()) {
       cudaFuncSetAttribute(final_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      configured = true;
+      configured.mark();
     }
   }
   MA3_REQUIRE(smem <= 200 * 1024, "final_layer_cfg_euler: Cout * D too large for shared memory");
   const unsigned fgrid = (unsigned)min((long long)num_sms(), ((long long)(N / 2) * T + 7) / 8);
 #define FL_FAST(KV4)                                                                                                   \
   do {                                                                                                                 \
-    static bool cfgd = false;                                                                                          \
-    if (!cfgd) {                                                                                                       \
+    static DeviceOnce cfgd;                                                                                                \
+    if (cfgd.pending()) {                                                                                                       \
       cudaFuncSetAttribute(final_layer_fast_kernel<true, KV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-      cfgd = true;                                                                                                     \
+      cfgd.mark();                                                                                                     \
     }                                                                                                                  \
     launch_pdl(final_layer_fast_kernel<true, KV4>, dim3(fgrid), dim3(256), smem, ST(stream), 1, h, mod, (long long)mod_ld, \
                shift_off, scale_off, W, bias, N, T, D, Cout, eps, v_out, x_in, x_out, dt, guidance);                   \

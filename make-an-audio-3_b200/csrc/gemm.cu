@@ -1164,11 +1164,11 @@ static int try_conv_narrow(const ma3_gemm_t* g, GemmKParams& kp, cudaStream_t st
     if (rc) return rc;
   }
   const size_t smem = 1024 + w_bytes + stages * a_stage + tail;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     cudaError_t e = cudaFuncSetAttribute(conv_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(conv_narrow): %s", cudaGetErrorString(e));
-    configured = true;
+    configured.mark();
   }
   const int total_tiles = kp.tiles_m * g->batch;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
@@ -1188,12 +1188,12 @@ static uint32_t pow2_cols(int n) {
 
 template <int EPI, int CG, bool kNarrow>
 static int launch_cg(const GemmKParams& kp, size_t smem, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     cudaError_t e =
         cudaFuncSetAttribute(tap_gemm_kernel<EPI, CG, kNarrow>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(tap_gemm): %s", cudaGetErrorString(e));
-    configured = true;
+    configured.mark();
   }
   cudaError_t e = launch_pdl(tap_gemm_kernel<EPI, CG, kNarrow>, dim3((unsigned)grid), dim3(kGemmThreads), smem, st, CG, kp);
   if (e != cudaSuccess) MA3_FAIL((int)e, "tap_gemm launch: %s", cudaGetErrorString(e));

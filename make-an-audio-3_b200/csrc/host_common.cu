@@ -23,14 +23,15 @@ bool pdl_enabled() {
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = n[dev & 63];
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
   }
-  return n;
+  return v;
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -64,7 +65,9 @@ int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, co
   if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
   if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
   if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  // 16-bit operands are bf16 or fp16 depending on the caller: the maps only ever copy (no OOB NaN fill, no
+  // arithmetic), so they are typed as plain 16-bit words rather than mislabelled as one of the two.
+  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -125,6 +128,13 @@ int ma3_l2_persist(const void* ptr, size_t bytes, void* stream) {
   }
   cudaError_t e = cudaStreamSetAttribute(reinterpret_cast<cudaStream_t>(stream), cudaStreamAttributeAccessPolicyWindow, &v);
   if (e != cudaSuccess) MA3_FAIL((int)e, "cudaStreamSetAttribute(access policy window): %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int ma3_l2_persist_release(void) {
+  cudaError_t e = cudaCtxResetPersistingL2Cache();
+  if (e == cudaSuccess) e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+  if (e != cudaSuccess) MA3_FAIL((int)e, "ma3_l2_persist_release: %s", cudaGetErrorString(e));
   return 0;
 }
 

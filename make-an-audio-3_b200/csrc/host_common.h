@@ -37,6 +37,15 @@ extern long long* g_trace;  // diagnostics buffer (ma3_debug_set_gemm_trace); nu
 
 int num_sms();
 
+// "Done once" flag for state that lives on the device (function attributes, __constant__ uploads): one bit per device
+// ordinal, so a second GPU used from the same process configures its own copy instead of inheriting the first one's.
+struct DeviceOnce {
+  std::atomic<uint64_t> done{0};
+  static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+  bool pending() const { return !((done.load(std::memory_order_relaxed) >> dev()) & 1ull); }
+  void mark() { done.fetch_or(1ull << dev(), std::memory_order_relaxed); }
+};
+
 // elem_bytes = 2 (bf16/f16) or 4 (f32).  dims/strides innermost first; strides[i] = byte pitch of dim i+1.
 // swizzle_bytes in {0, 32, 64, 128}.  Returns 0 or an error code (message in g_err).
 int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,

@@ -147,6 +147,9 @@ class TxtFlagLargeDiT(nn.Module):
         self._rope_src = None
         self._work = {}
         self._ctx = None
+        # bumped whenever a device buffer a captured CUDA graph may point at is re-allocated (packed weights, RoPE
+        # table, context buffers, workspaces): CFMSampler keys its plans on it
+        self.generation = 0
         self.register_load_state_dict_post_hook(lambda m, k: m.invalidate())
 
     # ---------------------------------------------------------------- reference surface
@@ -163,6 +166,9 @@ class TxtFlagLargeDiT(nn.Module):
     def invalidate(self):
         self._packed = None
         self._ctx = None
+        self._work = {}
+        self._rope_src = None
+        self.generation += 1
 
     def _apply(self, fn, *a, **k):
         self.invalidate()
@@ -249,7 +255,13 @@ class TxtFlagLargeDiT(nn.Module):
         fc = self.freqs_cis
         if self._rope_src is not fc:  # callers overwrite the table on the live module (NTK scaling)
             dev = self.proj_in.weight.device
-            self._packed["rope"] = torch.view_as_real(fc.to("cpu")).float().contiguous().to(dev)
+            tab = torch.view_as_real(fc.to("cpu")).float().contiguous().to(dev)
+            old = self._packed.get("rope")
+            if old is not None and old.shape == tab.shape:
+                old.copy_(tab)             # same storage: captured graphs keep pointing at a live, updated table
+            else:
+                self._packed["rope"] = tab
+                self.generation += 1
             self._rope_src = fc
         return self._packed
 
@@ -277,6 +289,7 @@ class TxtFlagLargeDiT(nn.Module):
             if self.num_experts:
                 w.y1 = torch.empty(N * T, D, device=dev, dtype=bf)
             self._work[key] = w
+            self.generation += 1
         return w
 
     # ---------------------------------------------------------------- step-invariant work
@@ -306,6 +319,7 @@ class TxtFlagLargeDiT(nn.Module):
                 c["y"] = torch.empty(N * Lc, D, device=dev, dtype=torch.float32)
                 c["ctx16"] = torch.empty(N * Lc, Cd, device=dev, dtype=bf)
             self._ctx = c
+            self.generation += 1
         if self._video:
             # c = LayerNorm(W2 gelu(W1 ctx + b1) + b2)   (flag_large_dit_moe.py:151-162, 680)
             ops.cast(context.view(N * Lc, Cd), c["ctx16"])

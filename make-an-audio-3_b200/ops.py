@@ -58,6 +58,7 @@ def declare(lib):
         "ma3_act1d_set_filter": [vp, vp],
         "ma3_act1d": [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, vp],
         "ma3_attention": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+        "ma3_l2_persist": [vp, C.c_size_t, vp],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -230,16 +231,16 @@ def cast(x, out):
     return out
 
 
-_filter_set = False
+_filter_set = set()   # device ordinals whose __constant__ taps have been uploaded
 
 
 def act1d(x, out, alpha, beta, logscale=True):
     """Fused Activation1d on channels-last x [B, T, C]."""
-    global _filter_set
-    if not _filter_set:
+    if x.device.index not in _filter_set:
         taps = (C.c_float * 12)(*kaiser_sinc_taps())
-        _call("ma3_act1d_set_filter", taps)
-        _filter_set = True
+        with torch.cuda.device(x.device):
+            _call("ma3_act1d_set_filter", taps)
+        _filter_set.add(x.device.index)
     B, T, Cc = x.shape
     _call("ma3_act1d", L.ptr(x), L.dt(x), L.ptr(out), L.dt(out), L.ptr(alpha), L.ptr(beta), B, T, Cc, int(logscale),
           work=float(B) * T * Cc * (x.element_size() + out.element_size()))

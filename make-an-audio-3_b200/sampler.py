@@ -118,13 +118,18 @@ class CFMSampler:
         S = len(ints)
 
         cbuf = dit.prepare_context(ctx)
-        # the plan (buffers + captured graph) is valid for these shapes, this schedule and these context buffers
-        key = (cfg, B, C, T, tuple(ctx.shape), tuple(ints), scale, cbuf["ky"].data_ptr(), id(dit._packed))
+        work = dit._workspace(N, T)
+        # The plan (buffers + captured graph) is valid for these shapes and this schedule, and only as long as none of
+        # the device buffers the captured launches point at has been re-allocated: dit.generation counts those
+        # (load_state_dict / .to() / a freqs_cis table of another shape / a new context or workspace shape), and the
+        # plan holds a reference to every captured buffer so that nothing is freed while the graph is alive.
+        key = (cfg, B, C, T, tuple(ctx.shape), tuple(ints), scale, dit.generation)
         st = self._graphs.get(key)
         if st is None:
             st = {"traj": torch.empty(S + 1, B, C, T, device=dev, dtype=torch.float32),
                   "mod": torch.empty(S, N, dit._ensure()["mod_cols"], device=dev, dtype=torch.float32),
-                  "v": torch.empty(N, C, T, device=dev, dtype=torch.float32), "graph": None}
+                  "v": torch.empty(N, C, T, device=dev, dtype=torch.float32), "graph": None,
+                  "keep": (dit._packed, cbuf, work)}
             self._graphs = {key: st}          # keep one plan: buffers are large
         st["mod"].copy_(dit.prepare_timesteps(torch.tensor(ints, dtype=torch.int64)))
         st["traj"][0].copy_(x0)
@@ -148,14 +153,10 @@ class CFMSampler:
             # =<workspace buffer name> moves it.
             which = os.environ.get("MA3_L2_PERSIST", "h")
             if which not in ("", "0"):
-                w0 = dit._workspace(N, T)
-                buf = getattr(w0, "h" if which == "1" else which)
-                lib_ = L.load()
-                lib_.ma3_l2_persist.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-                L.check(lib_.ma3_l2_persist(ctypes.c_void_p(buf.data_ptr()), buf.numel() * buf.element_size(),
-                                            ctypes.c_void_p(cap.cuda_stream)), "ma3_l2_persist")
+                self._l2_window(work, "h" if which == "1" else which, cap)
             with torch.cuda.graph(g, stream=cap):
                 loop()
+            self._l2_window(None, None, cap)   # the window is baked into the captured kernel nodes; clear the stream's
             st["graph_launches"] = L.launch_count() - n0
             st["graph"] = g                    # the eager pass above already produced this call's trajectory
         else:
@@ -164,6 +165,36 @@ class CFMSampler:
             GRAPH_REPLAY_LAUNCHES += st["graph_launches"]
         traj = st["traj"].clone()
         return traj[-1], traj
+
+    def close(self):
+        """Drop the captured plan and give the persisting-L2 set-aside back to the device."""
+        self._graphs = {}
+        try:
+            L.load().ma3_l2_persist_release()
+        except Exception:  # noqa: BLE001
+            pass
+
+    @staticmethod
+    def _l2_window(work, name, stream):
+        """Best effort (a ~1 % optimisation must never abort sampling): put an L2 access-policy window on `stream` over
+        workspace buffer `name`, or clear it when work is None.  The persisting set-aside it needs is a device-wide
+        limit and stays sized to the window while the plan lives (include/ma3_b200.h, ma3_l2_persist)."""
+        import warnings
+        try:
+            buf = None
+            if work is not None:
+                buf = getattr(work, name, None)
+                if not torch.is_tensor(buf):
+                    warnings.warn(f"MA3_L2_PERSIST={name!r} is not a workspace buffer; L2 window not set")
+                    return
+            rc = L.load().ma3_l2_persist(ctypes.c_void_p(buf.data_ptr() if buf is not None else 0),
+                                         buf.numel() * buf.element_size() if buf is not None else 0,
+                                         ctypes.c_void_p(stream.cuda_stream))
+            if rc != 0:
+                warnings.warn("ma3_l2_persist failed (continuing without the L2 window): "
+                              + L.load().ma3_last_error().decode("utf-8", "replace"))
+        except Exception as e:  # noqa: BLE001
+            warnings.warn(f"L2 window not set: {e!r}")
 
     def _step(self, st, k, t_int, dt, scale, cfg, N, T):
         dit = self.dit

@@ -15,13 +15,14 @@ import torch.nn.functional as Fn
 
 
 # ------------------------------------------------------------------------------------------------ DiT pieces
-def rope_table(head_dim, end, theta=10000.0, rope_scaling_factor=1.0, ntk_factor=1.0):
-    """flag_large_dit.py:212-251 (precompute_freqs_cis) -> (cos, sin), each [end, head_dim/2]."""
+def rope_table(head_dim, end, theta=10000.0, rope_scaling_factor=1.0, ntk_factor=1.0, device=None):
+    """flag_large_dit.py:212-251 (precompute_freqs_cis) -> (cos, sin), each [end, head_dim/2].  The table is always
+    computed on the CPU (as the GPU tests' reference of record) and moved to `device` afterwards."""
     theta = theta * ntk_factor
     inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2)[: head_dim // 2].float() / head_dim))
     pos = torch.arange(end, dtype=torch.float32) / rope_scaling_factor
     ang = torch.outer(pos, inv).float()
-    return torch.cos(ang), torch.sin(ang)
+    return torch.cos(ang).to(device), torch.sin(ang).to(device)
 
 
 def apply_rope(x, cos, sin):
@@ -45,7 +46,7 @@ def rmsnorm(x, w, eps=1e-5):
 def timestep_embedding(t, dim=256, max_period=10000):
     """flag_large_dit_moe.py:110-127."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -103,7 +104,7 @@ def dit_forward(sd, x, t, context, *, heads, video=False, num_experts=0, rope=No
     D = sd["proj_in.weight"].shape[0]
     depth = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
     hd = D // heads
-    cos, sin = rope if rope is not None else rope_table(hd, max_len)
+    cos, sin = rope if rope is not None else rope_table(hd, max_len, device=x.device)
     h = x.transpose(1, 2) @ sd["proj_in.weight"].t() + sd["proj_in.bias"]
     te = timestep_embedding(t)
     te = Fn.silu(te @ sd["t_embedder.mlp.0.weight"].t() + sd["t_embedder.mlp.0.bias"])
@@ -166,7 +167,7 @@ def sample_cfg(velocity, x0, cond, uncond, scale, n_points=25, t_start=None):
     traj, vels = [x], []
     B = x.shape[0]
     for ti, dt in zip(ints, dts):
-        t = torch.full((2 * B,), ti, dtype=torch.long)
+        t = torch.full((2 * B,), ti, dtype=torch.long, device=x.device)
         v = velocity(torch.cat([x, x]), t, torch.cat([uncond, cond]))
         vu, vc = v[:B], v[B:]
         vg = vu + scale * (vc - vu)
@@ -182,7 +183,7 @@ def sample_plain(velocity, x0, cond, n_points=25, t_start=None):
     x = x0
     traj = [x]
     for ti, dt in zip(ints, dts):
-        t = torch.full((x.shape[0],), ti, dtype=torch.long)
+        t = torch.full((x.shape[0],), ti, dtype=torch.long, device=x.device)
         x = x + dt * velocity(x, t, cond)
         traj.append(x)
     return x, torch.stack(traj)
@@ -306,7 +307,7 @@ def snake(x, alpha, logscale=True):
 
 def activation1d(x, sd, name, h, f=None):
     """Activation1d.forward (alias_free_torch/act.py:23-28): up x2 -> snake(beta) -> down x2."""
-    f = kaiser_sinc_filter() if f is None else f
+    f = (kaiser_sinc_filter() if f is None else f).to(x.device)
     u = up2(x, f)
     if h["activation"] == "snakebeta":
         u = snakebeta(u, sd[name + ".act.alpha"], sd[name + ".act.beta"], h["snake_logscale"])
@@ -338,7 +339,7 @@ def _amp2(x, sd, p, h, k, dils, f):
 def bigvgan_forward(sd, mel, h):
     """BigVGAN.forward (vocoder/bigvgan/models.py:183-205) on weight-norm-folded weights.  mel [B,80,T] ->
     [B,1,T*hop]."""
-    f = kaiser_sinc_filter()
+    f = kaiser_sinc_filter().to(mel.device)
     nk = len(h["resblock_kernel_sizes"])
     amp = _amp1 if h["resblock"] == "1" else _amp2
     x = _c1d(mel, sd, "conv_pre", padding=3)
@@ -368,6 +369,20 @@ def fold_weight_norm(sd):
         else:
             out[k] = v
     return out
+
+
+# ------------------------------------------------------------------------------------------------ device
+def strict_fp32():
+    """The oracle is fp32 arithmetic.  On a CUDA device torch would otherwise run convolutions (cuDNN) in TF32;
+    callers that put the oracle on `cuda` (the full-size parity tests, bench.py's library baseline in fp32 mode)
+    call this first."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+
+
+def to_device(sd, device):
+    return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in sd.items()}
 
 
 # ------------------------------------------------------------------------------------------------ metrics

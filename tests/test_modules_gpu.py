@@ -112,10 +112,19 @@ def test_sampler_golden(golden):
     for use_graph in (False, True):
         s = CFMSampler(m, use_graph=use_graph)
         for rep in range(2):  # second call with graphs replays the captured loop
+            for st in s._graphs.values():      # a replay that did nothing must not pass on the first call's result
+                st["traj"].fill_(float("nan"))
+                st["mod"].fill_(float("nan"))
             xf, traj = s.sample_cfg(c.cuda(), 3.0, uc.cuda(), 2, timesteps=6, x_latent=x0.cuda())
             assert traj.shape == golden["cfm_cfg_traj"].shape
             assert O.cosine(xf.cpu(), golden["cfm_cfg_final"]) > 0.999
             assert O.max_rel_err(traj.cpu(), golden["cfm_cfg_traj"]) < 2e-2
+    # replay with other prompts / noise of the same shapes == the graph-free path on those inputs, bit for bit
+    g = Cs.gen(99)
+    c2, uc2, x2 = torch.randn(c.shape, generator=g).cuda(), torch.randn(uc.shape, generator=g).cuda(), torch.randn(x0.shape, generator=g).cuda()
+    _, tr_g = s.sample_cfg(c2, 3.0, uc2, 2, timesteps=6, x_latent=x2)
+    _, tr_e = CFMSampler(m, use_graph=False).sample_cfg(c2, 3.0, uc2, 2, timesteps=6, x_latent=x2)
+    assert torch.equal(tr_g, tr_e) and not torch.equal(tr_g, traj)
     xp, _ = s.sample(c.cuda(), 2, timesteps=6, x_latent=x0.cuda())
     assert O.cosine(xp.cpu(), golden["cfm_plain_final"]) > 0.999
     xs, trs = s.sample_cfg(c.cuda(), 3.0, uc.cuda(), 2, timesteps=6, x_latent=x0.cuda(), t_start=2)
@@ -266,6 +275,10 @@ def test_pipeline_full_size_properties():
     unc = torch.randn(1, L, Cd, generator=g).expand(B, L, Cd).contiguous().cuda()
     x0 = torch.randn(B, 20, T, generator=g).cuda()
     w_eager = pipe.generate(cond, unc, x0, scale=3.0, timesteps=25).clone()     # first call: eager pass + capture
+    for st in list(pipe.sampler._graphs.values()) + list(pipe._tail.values()):  # a no-op replay must not pass
+        for k in ("traj", "mod", "wav", "zin"):
+            if k in st:
+                st[k].fill_(float("nan"))
     w_graph = pipe.generate(cond, unc, x0, scale=3.0, timesteps=25).clone()     # second call: graph replay
     assert w_graph.shape == (B, 2 * T * 256)
     assert torch.equal(w_eager, w_graph)

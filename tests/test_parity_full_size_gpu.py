@@ -1,0 +1,227 @@
+"""Parity at the BENCHMARKED sizes (BASELINE.json configs, SURVEY.md section 8(d) gates) against the fp32 oracle.
+
+The oracle (oracle/restated.py, pinned to the reference's own outputs by tests/test_oracle_golden.py) is put on the
+GPU in strict fp32 (no TF32) so that full-depth models finish in seconds; it is the checker, never the thing measured.
+
+Gates (north_star):
+  * per-step guided velocity, the CUDA path fed the ORACLE's x_k at every one of the 24 Euler steps:
+        max|v - v_ref| / max|v_ref| <= 1e-2          (bf16 operands vs the fp32 reference, cfm1_audio.py:145-161)
+  * final latent of the path's own 24-step trajectory:  cosine >= 0.999   (cfm1_audio.py:89-111)
+  * waveform vs the fp32 vocoder on the same mel:       SNR >= 30 dB raw and mean-removed (models.py:183-205)
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cases as Cs, restated as O, weights as W  # noqa: E402
+
+VEL_TOL = 1e-2     # north_star: per-step velocity max relative error, bf16 vs fp32
+COS_TOL = 0.999    # north_star: final mel latent cosine
+SNR_TOL = 30.0     # north_star: waveform SNR (dB)
+
+
+def _build(model, depth=None):
+    from ma3_b200 import dit as D
+    from ma3_b200.pipeline import MODEL_CONFIGS
+    cfg = dict(MODEL_CONFIGS[model])
+    if depth is not None:
+        cfg["depth"] = depth
+    cfg.pop("max_len")
+    ne = cfg.pop("num_experts", 0)
+    video = ne > 0
+    sd = W.dit_state_dict(**cfg, video=video, num_experts=ne, seed=5)
+    cls = D.VideoFlagLargeDiT if video else D.TxtFlagLargeImprovedDiTV2
+    m = cls(**cfg, **({"num_experts": ne} if video else {}))
+    m.load_state_dict(sd, strict=True)
+    return cfg, ne, sd, m.cuda()
+
+
+def _oracle_velocity(sd, cfg, ne):
+    dsd = O.to_device(sd, "cuda")
+    return lambda x, t, ctx: O.dit_forward(dsd, x, t, ctx, heads=cfg["num_heads"], video=ne > 0, num_experts=ne)
+
+
+def _per_step_parity(model, T, L, n_points, depth=None, steps=None):
+    """Returns (worst per-step velocity error, final-latent cosine, our sampler, inputs) for one prompt."""
+    from ma3_b200.sampler import CFMSampler
+    O.strict_fp32()
+    cfg, ne, sd, m = _build(model, depth)
+    c, uc, x0 = W.synthetic_inputs(prompts=1, latent_ch=20, T=T, L=L, Cd=cfg["context_dim"])
+    c, uc, x0 = c.cuda(), uc.cuda(), x0.cuda()
+    vel = _oracle_velocity(sd, cfg, ne)
+    with torch.no_grad():
+        zr, traj_r, vels_r = O.sample_cfg(vel, x0, c, uc, 3.0, n_points=n_points)
+    ints, _ = O.timestep_ints(n_points)
+    ctx = torch.cat([uc, c])
+    worst = 0.0
+    for k, ti in enumerate(ints if steps is None else ints[:steps]):
+        xk = traj_r[k]                                   # the ORACLE's state at step k
+        t = torch.full((2,), ti, dtype=torch.long, device="cuda")
+        out = m(torch.cat([xk, xk]), t, context=ctx)
+        vg = out[:1] + 3.0 * (out[1:] - out[:1])
+        err = O.max_rel_err(vg.cpu(), vels_r[k].cpu())
+        worst = max(worst, err)
+        assert err <= VEL_TOL, (model, "step", k, "t", ti, err)
+    s = CFMSampler(m)
+    z, traj = s.sample_cfg(c, 3.0, uc, 1, timesteps=n_points, x_latent=x0)
+    cos = O.cosine(z.cpu(), zr.cpu())
+    return worst, cos, (cfg, ne, sd, m, s), (c, uc, x0, zr, traj_r)
+
+
+def test_xl_full_depth_24_steps_and_bench_batch():
+    """(i) BASELINE configs[1]: XL, depth 28, one prompt, 25 points -- per-step velocity at all 24 steps, final latent
+    cosine; (v) the same prompt as clip 5 of an 8-prompt batch (the benchmarked shape, CUDA-graph replay) gives the
+    same latent; a replay with DIFFERENT prompts / noise is checked against the eager path."""
+    from ma3_b200.sampler import CFMSampler
+    worst, cos, (cfg, ne, sd, m, s), (c, uc, x0, zr, traj_r) = _per_step_parity("XL", 312, 154, 25)
+    print(f"XL depth 28: worst per-step velocity rel err {worst:.4f}, final latent cosine {cos:.6f}")
+    assert cos >= COS_TOL
+    g = Cs.gen(501)
+    B = 8
+    cond = torch.randn(B, 154, 1024, generator=g).cuda()
+    x8 = torch.randn(B, 20, 312, generator=g).cuda()
+    cond[5], x8[5] = c[0], x0[0]
+    unc = uc.expand(B, -1, -1).contiguous()
+    z8, _ = s.sample_cfg(cond, 3.0, unc, B, timesteps=25, x_latent=x8)            # eager pass + capture
+    assert O.cosine(z8[5:6].cpu(), zr.cpu()) >= COS_TOL
+    # replay with other inputs of the same shapes: must equal what an eager (graph-free) sampler computes for them
+    cond2 = torch.randn(B, 154, 1024, generator=g).cuda()
+    x82 = torch.randn(B, 20, 312, generator=g).cuda()
+    unc2 = torch.randn(1, 154, 1024, generator=g).cuda().expand(B, -1, -1).contiguous()
+    key = next(iter(s._graphs))
+    s._graphs[key]["traj"][1:].zero_()
+    z_replay, traj_replay = s.sample_cfg(cond2, 3.0, unc2, B, timesteps=25, x_latent=x82)
+    assert next(iter(s._graphs)) == key and s._graphs[key]["graph"] is not None        # it was a replay
+    z_eager, traj_eager = CFMSampler(m, use_graph=False).sample_cfg(cond2, 3.0, unc2, B, timesteps=25, x_latent=x82)
+    assert torch.equal(traj_replay, traj_eager)
+    assert O.cosine(z_replay.cpu(), z8.cpu()) < 0.9       # and it really is a different result
+
+
+def test_m_full_depth_24_steps():
+    """(ii) BASELINE configs[0]: M, depth 16, T=312, L=154."""
+    worst, cos, _, _ = _per_step_parity("M", 312, 154, 25)
+    print(f"M depth 16: worst per-step velocity rel err {worst:.4f}, final latent cosine {cos:.6f}")
+    assert cos >= COS_TOL
+
+
+def test_music_context_length_full_depth():
+    """BASELINE configs[3] (txt2music-cfm-cfg): M, depth 16, L = 77 context tokens."""
+    worst, cos, _, _ = _per_step_parity("M", 312, 77, 25)
+    print(f"M depth 16 / L=77: worst per-step velocity rel err {worst:.4f}, final latent cosine {cos:.6f}")
+    assert cos >= COS_TOL
+
+
+def test_moe_full_depth_24_steps():
+    """(ii) BASELINE configs[4]: video/MoE M, depth 16, 4 time + 4 frequency experts, T=256, 40 video tokens; the 24
+    steps walk through all four time experts (t // 250)."""
+    worst, cos, _, _ = _per_step_parity("MOE", 256, 40, 25)
+    print(f"MoE depth 16: worst per-step velocity rel err {worst:.4f}, final latent cosine {cos:.6f}")
+    assert cos >= COS_TOL
+
+
+def test_xxl_long_context_full_depth():
+    """(iii) BASELINE configs[2]: XXL, depth 32, 30 s clips = T 936 latent frames; 6 points = 5 Euler steps."""
+    worst, cos, _, _ = _per_step_parity("XXL", 936, 154, 6)
+    print(f"XXL depth 32 / T=936: worst per-step velocity rel err {worst:.4f}, final latent cosine {cos:.6f}")
+    assert cos >= COS_TOL
+
+
+def test_bigvgan_full_length_batch2():
+    """(iv) the benchmark vocoder (large-256x layout) on the FULL 624-frame mel of a 10 s clip, batch 2: the long
+    M = 159 744-row tiles of the 48- and 24-channel stages and every ConvTranspose phase are exercised."""
+    from ma3_b200.vocoder import BigVGAN
+    O.strict_fp32()
+    h = W.BIGVGAN_LARGE_256X
+    sd = W.bigvgan_state_dict(h)
+    mel = Cs.mel_inputs(B=2, T=624)
+    with torch.no_grad():
+        ref = O.bigvgan_forward(O.to_device(sd, "cuda"), mel.cuda(), h).cpu()
+    g = BigVGAN(dict(h))
+    g.load_state_dict(sd, strict=True)
+    out = g.cuda()(mel.cuda()).cpu()
+    assert out.shape == ref.shape == (2, 1, 624 * 256)
+    snr, snr0 = O.snr_db(ref, out), O.snr_db(ref - ref.mean(), out - out.mean())
+    print(f"BigVGAN large-256x, 2 x 624 frames: SNR {snr:.1f} dB raw, {snr0:.1f} dB mean-removed")
+    assert snr >= SNR_TOL and snr0 >= SNR_TOL
+    for b in range(2):   # per clip too
+        assert O.snr_db(ref[b] - ref[b].mean(), out[b] - out[b].mean()) >= SNR_TOL
+
+
+def test_vae_and_vocoder_on_sampled_latent_full_size():
+    """decode_first_stage + vocode at the benchmarked shape on a latent with the statistics of a sampled one:
+    mel cosine >= 0.999 vs the fp32 oracle and SNR >= 30 dB vs the fp32 vocoder fed the CUDA path's mel."""
+    from ma3_b200.pipeline import VAE_DDCONFIG
+    from ma3_b200.vae import AutoencoderKL
+    from ma3_b200.vocoder import VocoderBigVGAN
+    O.strict_fp32()
+    vsd = W.vae_decoder_state_dict(VAE_DDCONFIG, 20)
+    h = W.BIGVGAN_LARGE_256X
+    bsd = W.bigvgan_state_dict(h)
+    vae = AutoencoderKL(embed_dim=20, ddconfig=dict(VAE_DDCONFIG), lossconfig=None)
+    vae.load_state_dict(vsd, strict=True)
+    voc = VocoderBigVGAN(h=h, state_dict=bsd)
+    z = torch.randn(2, 20, 312, generator=Cs.gen(91)) * 1.7
+    mel = vae.cuda().decode(z.cuda())
+    with torch.no_grad():
+        mel_ref = O.vae_decode(O.to_device(vsd, "cuda"), z.cuda(), VAE_DDCONFIG)
+        wav_ref = O.bigvgan_forward(O.to_device(bsd, "cuda"), mel, h).squeeze(1)
+    assert O.cosine(mel.cpu(), mel_ref.cpu()) >= COS_TOL
+    wav = voc.vocode_tensor(mel)
+    assert wav.shape == (2, 159744)
+    assert O.snr_db(wav_ref.cpu(), wav.cpu()) >= SNR_TOL
+
+
+def test_dict_and_list_conditioning():
+    """Row a4 (ddpm.py:1406-1420): conditioning handed over as {'c_crossattn': [a, b]} is concatenated on dim 1 --
+    the dual-text-encoder layout (77 + 77 tokens) of the shipped txt2audio configs."""
+    from ma3_b200.sampler import CFMSampler
+    cfg = Cs.DIT_SMALL
+    sd = W.dit_state_dict(**cfg, seed=3)
+    from ma3_b200 import dit as D
+    m = D.TxtFlagLargeImprovedDiTV2(**dict(cfg, max_len=100))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    x0, c, uc = Cs.cfm_inputs(cfg, B=2, T=24, L=10)
+    s = CFMSampler(m, use_graph=False)
+    z_ref, _ = s.sample_cfg(c.cuda(), 3.0, uc.cuda(), 2, timesteps=5, x_latent=x0.cuda())
+    halves = lambda t: [t[:, :4].contiguous().cuda(), t[:, 4:].contiguous().cuda()]
+    z_dict, _ = s.sample_cfg({"c_crossattn": halves(c)}, 3.0, {"c_crossattn": halves(uc)}, 2, timesteps=5,
+                             x_latent=x0.cuda())
+    z_list, _ = s.sample_cfg(halves(c), 3.0, halves(uc), 2, timesteps=5, x_latent=x0.cuda())
+    assert torch.equal(z_ref, z_dict) and torch.equal(z_ref, z_list)
+    vel = lambda x, t, ctx: O.dit_forward(sd, x, t, ctx, heads=cfg["num_heads"], max_len=100)
+    zr, _, _ = O.sample_cfg(vel, x0, c, uc, 3.0, n_points=5)
+    assert O.cosine(z_dict.cpu(), zr) >= COS_TOL
+
+
+def test_sampler_ntk_override_invalidates_plan():
+    """overwriting freqs_cis on the live module (scripts/video2audio_flow_inpaint.py:230-235) between two
+    sample() calls of the same shapes must be honoured by the captured plan."""
+    from ma3_b200 import dit as D
+    from ma3_b200.sampler import CFMSampler
+    cfg = Cs.DIT_TINY
+    sd = W.dit_state_dict(**cfg, seed=3)
+    m = D.TxtFlagLargeImprovedDiTV2(**dict(cfg, max_len=100))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    x0, c, uc = Cs.cfm_inputs(cfg)
+    s = CFMSampler(m, use_graph=True)
+    for _ in range(2):
+        z1, _ = s.sample_cfg(c.cuda(), 3.0, uc.cuda(), 2, timesteps=6, x_latent=x0.cuda())
+    m.freqs_cis = m.precompute_freqs_cis(16, 100, ntk_factor=3.0)          # same shape: updated in place
+    z2, _ = s.sample_cfg(c.cuda(), 3.0, uc.cuda(), 2, timesteps=6, x_latent=x0.cuda())
+    rope = O.rope_table(16, 100, ntk_factor=3.0)
+    vel = lambda x, t, ctx: O.dit_forward(sd, x, t, ctx, heads=4, rope=rope)
+    zr, _, _ = O.sample_cfg(vel, x0, c, uc, 3.0, n_points=6)
+    assert O.cosine(z2.cpu(), zr) >= COS_TOL and O.cosine(z1.cpu(), zr) < 0.9999
+    m.freqs_cis = m.precompute_freqs_cis(16, 50, ntk_factor=2.0)           # other shape: new buffer, new plan
+    z3, _ = s.sample_cfg(c.cuda(), 3.0, uc.cuda(), 2, timesteps=6, x_latent=x0.cuda())
+    rope = O.rope_table(16, 50, ntk_factor=2.0)
+    zr3, _, _ = O.sample_cfg(lambda x, t, ctx: O.dit_forward(sd, x, t, ctx, heads=4, rope=rope), x0, c, uc, 3.0, n_points=6)
+    assert O.cosine(z3.cpu(), zr3) >= COS_TOL
+    m.load_state_dict(W.dit_state_dict(**cfg, seed=9), strict=True)        # new weights: plan must not be reused
+    z4, _ = s.sample_cfg(c.cuda(), 3.0, uc.cuda(), 2, timesteps=6, x_latent=x0.cuda())
+    sd9 = W.dit_state_dict(**cfg, seed=9)
+    zr4, _, _ = O.sample_cfg(lambda x, t, ctx: O.dit_forward(sd9, x, t, ctx, heads=4, rope=rope), x0, c, uc, 3.0, n_points=6)
+    assert O.cosine(z4.cpu(), zr4) >= COS_TOL
