@@ -5,6 +5,8 @@
     torchrun ... bench.py --gpus N --steps K --warmup W           # one rank per GPU, prompts sharded (weak scaling)
     python bench.py --impl reference --steps K --warmup W         # the reference arithmetic on the host CPU
 
+    python bench.py --config N                                    # BASELINE.json configs[N-1] at its stated shape
+
 Workload = BASELINE.json configs[1]: txt2audio-cfm-cfg-XL (Next-DiT D=1152, 16 heads, depth 28), 64 prompts over
 8 GPUs = 8 prompts per GPU, 10 s clips (T=312 latent frames -> 159 744 samples), 25 CFM points = 24 Euler steps,
 CFG 3.0 (DiT batch 16), then VAE decode and BigVGAN (large-256x layout) for the 8 clips.  One "step" = one such batch
@@ -75,77 +77,185 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_sample(model="XL", n_dit_steps=2, mel_frames=156, threads=None):
-    """Bounded sample of the workload on the host CPU through the oracle port of the reference arithmetic
-    (oracle/restated.py, fp32, torch CPU): n_dit_steps Euler steps of one prompt (CFG batch 2) scaled to 24,
-    the full VAE decode of one clip, BigVGAN on mel_frames of the 624 mel frames scaled linearly.
-    Returns (audio-s/s for one clip, description, threads)."""
+# ------------------------------------------------------------------------------------------------ reference arms
+# BASELINE.json configs[0..4] at their stated shapes: model, prompts per GPU, T, L
+CONFIG_PRESETS = {1: ("M", 1, 312, 154), 2: ("XL", 8, 312, 154), 3: ("XXL", 1, 936, 154), 4: ("M", 16, 312, 77),
+                  5: ("MOE", 1, 256, 40)}
+
+
+def _reference_stack(model, device):
+    """The reference's OWN modules (CFM -> DiffusionWrapper -> Next-DiT, AutoencoderKL, BigVGAN) built through its
+    instantiate_from_config from oracle/_ref (or /root/reference), loaded with the same seeded weights the B200 path
+    is tested with.  Returns (cfm, bigvgan) or None when no copy of the reference is present."""
+    from oracle import ref_loader as R, weights as W
+    from ma3_b200.pipeline import MODEL_CONFIGS, VAE_DDCONFIG
+    if not R.available():
+        return None
+    cfg = dict(MODEL_CONFIGS[model])
+    ne = cfg.get("num_experts", 0)
+    wcfg = {k: v for k, v in cfg.items() if k not in ("max_len", "num_experts")}
+    dsd = W.dit_state_dict(**wcfg, video=ne > 0, num_experts=ne, seed=0)
+    vsd = W.vae_decoder_state_dict(VAE_DDCONFIG, 20)
+    cfm = R.build_cfm(cfg, VAE_DDCONFIG, 20, dsd, vsd, video=ne > 0).to(device)
+    voc = R.build_bigvgan(W.bigvgan_state_dict(W.BIGVGAN_LARGE_256X), W.BIGVGAN_LARGE_256X).to(device)
+    return cfm, voc
+
+
+def _reference_clip(stack, c, uc, x0):
+    """cfm1_audio.py:89-111 -> ddpm_audio.py:358-371 -> vocoder/bigvgan/models.py:183-205, exactly the calls of
+    scripts/txt2audio_for_2cap_flow.py:170-188 with the conditioner's output replaced by synthetic embeddings."""
+    cfm, voc = stack
+    z, _ = cfm.sample_cfg(c, GUIDANCE, uc, x0.shape[0], timesteps=N_POINTS, x_latent=x0)
+    mel = cfm.decode_first_stage(z)
+    return voc(mel)
+
+
+def _port_clip(model, c, uc, x0):
+    """Fallback when no copy of the reference is present: the oracle port (oracle/restated.py), whole clip."""
     from ma3_b200.pipeline import MODEL_CONFIGS, VAE_DDCONFIG
     from oracle import restated as O, weights as W
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
     cfg = dict(MODEL_CONFIGS[model])
-    cfg.pop("max_len")
-    video = "num_experts" in cfg
-    dsd = W.dit_state_dict(**cfg, video=video, seed=0)
+    ne = cfg.get("num_experts", 0)
+    wcfg = {k: v for k, v in cfg.items() if k not in ("max_len", "num_experts")}
+    dsd = W.dit_state_dict(**wcfg, video=ne > 0, num_experts=ne, seed=0)
     vsd = W.vae_decoder_state_dict(VAE_DDCONFIG, 20)
-    h = W.BIGVGAN_LARGE_256X
-    bsd = W.bigvgan_state_dict(h)
-    c, uc, x0 = W.synthetic_inputs(prompts=1, latent_ch=20, T=T_LATENT, L=L_CTX, Cd=cfg["context_dim"])
-    ints, dts = O.timestep_ints(N_POINTS)
-    with torch.no_grad():
-        x = x0
-        t0 = time.perf_counter()
-        for ti, dt in list(zip(ints, dts))[:n_dit_steps]:
-            t = torch.full((2,), ti, dtype=torch.long)
-            v = O.dit_forward(dsd, torch.cat([x, x]), t, torch.cat([uc, c]), heads=cfg["num_heads"], video=video,
-                              num_experts=cfg.get("num_experts", 0))
-            x = x + dt * (v[:1] + GUIDANCE * (v[1:] - v[:1]))
-        t_dit = (time.perf_counter() - t0) * (len(ints) / n_dit_steps)
-        t0 = time.perf_counter()
-        mel = O.vae_decode(vsd, x, VAE_DDCONFIG)
-        t_vae = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        O.bigvgan_forward(bsd, mel[..., :mel_frames], h)
-        t_voc = (time.perf_counter() - t0) * (mel.shape[-1] / mel_frames)
-    total = t_dit + t_vae + t_voc
-    desc = (f"oracle port (torch fp32) of the reference arithmetic, 1 prompt of {model}: {n_dit_steps}/24 Euler steps "
-            f"(CFG batch 2) x{len(ints) // n_dit_steps}, full VAE decode, BigVGAN on {mel_frames}/624 mel frames "
-            f"x{624 / mel_frames:.0f}; est. {t_dit:.1f}+{t_vae:.1f}+{t_voc:.1f} s per 9.984 s clip")
-    return clip_seconds() / total, desc, threads
+    bsd = W.bigvgan_state_dict(W.BIGVGAN_LARGE_256X)
+    vel = lambda x, t, ctx: O.dit_forward(dsd, x, t, ctx, heads=cfg["num_heads"], video=ne > 0, num_experts=ne)
+
+    def run():
+        z, _, _ = O.sample_cfg(vel, x0, c, uc, GUIDANCE, n_points=N_POINTS)
+        return O.bigvgan_forward(bsd, O.vae_decode(vsd, z, VAE_DDCONFIG), W.BIGVGAN_LARGE_256X)
+    return run
+
+
+class CpuReference:
+    """The reference's CPU path on the box's host cores: ONE WHOLE clip per step (1 prompt of the workload: 24 Euler
+    steps at CFG batch 2, VAE decode, BigVGAN on all mel frames) -- nothing is extrapolated inside a clip; audio-s/s on
+    the CPU is independent of the prompt count, which is the only scaling to the 8-prompt workload."""
+
+    def __init__(self, model, T, L, threads=None):
+        from ma3_b200.pipeline import MODEL_CONFIGS
+        from oracle import weights as W
+        os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+        self.threads = threads or os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        self.model, self.T, self.L = model, T, L
+        Cd = MODEL_CONFIGS[model]["context_dim"]
+        self.c, self.uc, self.x0 = W.synthetic_inputs(prompts=1, latent_ch=20, T=T, L=L, Cd=Cd)
+        stack = _reference_stack(model, "cpu")
+        if stack is not None:
+            self.kind = "reference"
+            self.fn = lambda: _reference_clip(stack, self.c, self.uc, self.x0)
+        else:
+            self.kind = "port"
+            self.fn = _port_clip(model, self.c, self.uc, self.x0)
+
+    def step(self):
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            wav = self.fn()
+            dt = time.perf_counter() - t0
+        assert wav.shape[-1] == 2 * self.T * HOP
+        return dt
+
+    def describe(self, secs):
+        what = ("the reference's own CFM.sample_cfg -> decode_first_stage -> BigVGAN (unmodified sources under "
+                "oracle/_ref, fp32, torch CPU)"
+                if self.kind == "reference" else "oracle port (oracle/restated.py, fp32, torch CPU)")
+        return (f"{what}: 1 prompt of {self.model} (T={self.T}, L={self.L}), one WHOLE clip per step = 24 Euler steps at "
+                f"CFG batch 2 + full VAE decode + BigVGAN large-256x on all {2 * self.T} mel frames; "
+                f"{secs:.1f} s per {clip_seconds(self.T):.3f} s clip")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    desc, threads = "", 0
     t_all = time.perf_counter()
-    for i in range(args.warmup + args.steps):
-        v, desc, threads = cpu_sample(args.model)
-        if i >= args.warmup:
-            vals.append(v)
-    value = statistics.mean(vals)
+    ref = CpuReference(args.model, args.T, args.L)
+    warm = min(args.warmup, 1)        # a CPU clip takes ~10-30 s: one untimed clip warms caches and allocators
+    for _ in range(warm):
+        ref.step()
+    secs = [ref.step() for _ in range(max(1, args.steps))]
+    per_clip = statistics.mean(secs)
+    value = clip_seconds(args.T) / per_clip
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * clip_seconds() / value,
+            "steps": max(1, args.steps), "warmup": warm, "ms_per_step": 1e3 * per_clip,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.threads, "kind": ref.kind,
+                             "sample": ref.describe(per_clip)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s": time.perf_counter() - t_all}
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
     print(json.dumps(line), flush=True)
 
 
+def library_baseline(model, B, T, L, dev, reps=2):
+    """SURVEY.md section 8(d) / BASELINE.md section 3: the UNMODIFIED reference modules on the same B200 (PyTorch's
+    library kernels: cuBLAS, cuDNN, SDPA), same weights / inputs / batch as the benchmarked step -- (a) fp32 as shipped,
+    (b) bf16 autocast with flag_large_dit_moe.is_flash_attn = False (the only bf16 mode of the reference that runs,
+    flag_large_dit_moe.py:364,382-388).  This, not the CPU arm, is what the hand-written kernels have to beat."""
+    from ma3_b200.pipeline import MODEL_CONFIGS
+    from oracle import ref_loader as R, weights as W
+    if not R.available():
+        return {"unavailable": "no copy of the reference on this box (oracle/_ref is written by build())"}
+    os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+    out = {"what": "reference CFM.sample_cfg -> decode_first_stage -> BigVGAN on this GPU through PyTorch library "
+                   f"kernels, {B} prompts, same weights and inputs"}
+    try:
+        stack = _reference_stack(model, dev)
+        Cd = MODEL_CONFIGS[model]["context_dim"]
+        c, uc, x0 = W.synthetic_inputs(prompts=B, latent_ch=20, T=T, L=L, Cd=Cd)
+        c, uc, x0 = c.to(dev), uc.to(dev), x0.to(dev)
+        import ldm.modules.diffusionmodules.flag_large_dit_moe as moe_mod
+
+        def timed(ctx):
+            ms = []
+            for i in range(reps + 1):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                with torch.no_grad(), ctx():
+                    _reference_clip(stack, c, uc, x0)
+                e1.record()
+                torch.cuda.synchronize()
+                if i:
+                    ms.append(e0.elapsed_time(e1))
+            return statistics.mean(ms)
+
+        import contextlib
+        ms32 = timed(contextlib.nullcontext)
+        out["fp32_as_shipped"] = {"ms_per_step": round(ms32, 2), "value": round(B * clip_seconds(T) / (ms32 / 1e3), 2),
+                                  "unit": UNIT}
+        flag = moe_mod.is_flash_attn
+        moe_mod.is_flash_attn = False
+        try:
+            ms16 = timed(lambda: torch.autocast("cuda", dtype=torch.bfloat16))
+            out["bf16_autocast"] = {"ms_per_step": round(ms16, 2), "value": round(B * clip_seconds(T) / (ms16 / 1e3), 2),
+                                    "unit": UNIT}
+        finally:
+            moe_mod.is_flash_attn = flag
+        del stack
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001  (the repo's own numbers stand without it)
+        out["error"] = repr(e)[:300]
+    return out
+
+
 def workload_config(args, world):
-    return {"workload": f"txt2audio-cfm-cfg-{args.model}: {args.prompts} prompts/GPU x {world} GPU, 10 s clips (T=312, "
-                        f"L=154), 25 CFM points = 24 Euler steps, CFG 3.0 (DiT batch {2 * args.prompts}/GPU), "
-                        "VAE decode + BigVGAN large-256x (assumed h, SURVEY 8(d))",
+    T, L = args.T, args.L
+    return {"workload": f"{CONFIG_NAMES.get(args.model, args.model)} ({args.model}): {args.prompts} prompts/GPU x {world} GPU, "
+                        f"{clip_seconds(T):.3f} s clips (T={T}, L={L}), 25 CFM points = 24 Euler steps, CFG 3.0 "
+                        f"(DiT batch {2 * args.prompts}/GPU), VAE decode + BigVGAN large-256x (assumed h, SURVEY 8(d))",
             "prompts_per_gpu": args.prompts, "global_prompts": args.prompts * world, "parallelism": f"dp{world} (prompts)",
+            "T_latent": T, "L_context": L,
             "precision": "DiT+VAE bf16 operands / fp32 accumulate+residual; vocoder fp16 / fp32 accumulate",
             "l2": "no explicit flush: per-step working set (1.5 GB bf16 DiT weights + >2 GB activations) >> 126 MB L2",
             "weights": "random init"}
+
+
+CONFIG_NAMES = {"M": "txt2audio-cfm-cfg", "XL": "txt2audio-cfm-cfg-XL", "XXL": "txt2audio-cfm-cfg-XXL",
+                "MOE": "video2audio-cfm-cfg-moe"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -155,11 +265,20 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
+                    help="BASELINE.json configs[N-1] at its stated shape (sets --model/--prompts/--T/--L); 0 = use the flags")
     ap.add_argument("--model", default="XL", choices=["M", "XL", "XXL", "MOE"])
     ap.add_argument("--prompts", type=int, default=8, help="prompts per GPU")
+    ap.add_argument("--T", type=int, default=0, help="latent frames (default 312 = 10 s; 936 = 30 s; MOE: 256)")
+    ap.add_argument("--L", type=int, default=0, help="context tokens (default 154; music 77; MOE: 40)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lib-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
+    if args.config:
+        args.model, args.prompts, args.T, args.L = CONFIG_PRESETS[args.config]
+    args.T = args.T or (256 if args.model == "MOE" else T_LATENT)
+    args.L = args.L or (40 if args.model == "MOE" else L_CTX)
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
@@ -183,8 +302,7 @@ def main():
 
     cfg = MODEL_CONFIGS[args.model]
     Cd = cfg["context_dim"]
-    L = 40 if args.model == "MOE" else L_CTX
-    T = 256 if args.model == "MOE" else T_LATENT
+    L, T = args.L, args.T
     B = args.prompts
     pipe = build_random_pipeline(args.model, vocoder_h=dict(BIGVGAN_H), seed=rank, device=dev,
                                  use_graph=not args.no_graph)
@@ -341,11 +459,18 @@ def main():
                 ms, work, n = agg[fam]
                 breakdown[fam]["achieved_TFLOPs"] = round(work / (ms * 1e-3) / 1e12, 1)
 
+    lib_base = None
+    if rank == 0 and world == 1 and not args.no_lib_baseline:
+        pipe.sampler.close()
+        lib_base = library_baseline(args.model, B, T, L, dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, desc, threads = cpu_sample(args.model)
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}
+            ref = CpuReference(args.model, T, L)
+            secs = ref.step()          # one whole clip (about 10-30 s of CPU work)
+            cpu = {"value": clip_seconds(T) / secs, "unit": UNIT, "cores": ref.threads, "kind": ref.kind,
+                   "sample": ref.describe(secs)}
         except Exception as e:  # the GPU numbers stand on their own
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
 
@@ -356,7 +481,8 @@ def main():
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stage_ms,
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "torch_b200_baseline": lib_base, "stage_ms": stage_ms,
                 "kernel_breakdown": breakdown, "gemm_shapes": gemm_shapes}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,13 +1,24 @@
-"""TEST INFRASTRUCTURE: import the *reference's own modules* from /root/reference through the import shims in
-oracle/_shims.  Only usable where the reference tree is mounted (this container); the GPU
-box has no /root/reference, so nothing on the `-m gpu` / smoke / bench paths may call into this module."""
+"""TEST INFRASTRUCTURE: import the *reference's own modules* through the import shims in oracle/_shims (SURVEY.md
+section 8(c)).  The tree is taken from $MA3_REFERENCE_ROOT, else /root/reference (mounted in the build container
+only), else oracle/_ref (the git-ignored copy made by oracle/build_ref.py at build() time, which travels to the GPU
+box).  Callers on the `-m gpu` / bench paths must check `available()` first and say so when it is False."""
 import copy
 import os
 import sys
 
 import torch
 
-REF_ROOT = os.environ.get("MA3_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    for cand in (os.environ.get("MA3_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "ldm")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_shims")
 _ready = False
 
@@ -89,15 +100,16 @@ def build_bigvgan(sd, h):
     return m.eval()
 
 
-def build_cfm(unet_params, ddconfig, embed_dim, dit_sd, vae_sd, *, video=False, mel_dim=20, mel_length=256):
+def build_cfm(unet_params, ddconfig, embed_dim, dit_sd, vae_sd, *, video=False, mel_dim=20, mel_length=256,
+              unet_target=None, first_stage_target=None):
     """The reference's own CFM -> LatentDiffusion_audio -> DDPM -> DiffusionWrapper stack
     (ldm/models/diffusion/cfm1_audio.py:30), with an Identity conditioner (synthetic embeddings)."""
     setup()
     import contextlib
     import io
     from ldm.util import instantiate_from_config
-    target = ("ldm.modules.diffusionmodules.flag_large_dit_moe.VideoFlagLargeDiT" if video else
-              "ldm.modules.diffusionmodules.flag_large_dit.TxtFlagLargeImprovedDiTV2")
+    target = unet_target or ("ldm.modules.diffusionmodules.flag_large_dit_moe.VideoFlagLargeDiT" if video else
+                             "ldm.modules.diffusionmodules.flag_large_dit.TxtFlagLargeImprovedDiTV2")
     cfg = {
         "target": "ldm.models.diffusion.cfm1_audio.CFM",
         "params": {
@@ -106,7 +118,7 @@ def build_cfm(unet_params, ddconfig, embed_dim, dit_sd, vae_sd, *, video=False, 
             "mel_length": mel_length, "channels": 0, "cond_stage_trainable": True, "conditioning_key": "crossattn",
             "monitor": "val/loss_simple_ema", "scale_by_std": True, "use_ema": False,
             "unet_config": {"target": target, "params": dict(unet_params)},
-            "first_stage_config": {"target": "ldm.models.autoencoder1d.AutoencoderKL",
+            "first_stage_config": {"target": first_stage_target or "ldm.models.autoencoder1d.AutoencoderKL",
                                    "params": {"embed_dim": embed_dim, "monitor": "val/rec_loss",
                                               "ddconfig": dict(ddconfig),
                                               "lossconfig": {"target": "torch.nn.Identity"}}},
