@@ -81,7 +81,7 @@ typedef struct ma3_gemm {
   int64_t a_rows, a_ld, a_batch_stride; /* a_batch_stride in elements; 0 = shared by all z */
   const void* b;          /* [b_batch][b_rows][K] with row pitch b_ld elements */
   int64_t b_rows, b_ld, b_batch_stride;
-  int32_t dtype;          /* MA3_BF16 or MA3_F16 (both operands) */
+  int32_t dtype;          /* MA3_BF16 or MA3_F16: A operand (and B unless b_dtype is set) */
   int32_t batch;          /* grid z */
   int32_t M, N, K;        /* output rows per z, output columns, reduction length per tap (multiple of 16) */
   int32_t taps;
@@ -117,6 +117,9 @@ typedef struct ma3_gemm {
   int32_t stream_k;       /* MA3_EPI_GATE_RES only.  0: library heuristic; 1: split the tiles x k-iterations space evenly
                            * over the SMs (partial products are added by separate reductions: fp32 sums may differ in the
                            * last bit from run to run); -1: whole tiles only (bit-reproducible) */
+  int32_t b_dtype;        /* 0: B has the same type as A; MA3_BF16 / MA3_F16: B's own 16-bit type (kind::f16 takes the two
+                           * operand formats independently: bf16 activations x fp16 weights keeps the activations'
+                           * range and gives the weights 3 more mantissa bits at the same tensor throughput) */
 } ma3_gemm_t;
 
 int ma3_gemm(const ma3_gemm_t* g, void* stream);
@@ -188,6 +191,12 @@ int ma3_layernorm_rows(const void* x, int in_dtype, const float* w, const float*
  * at the head of every adaLN_modulation (flag_large_dit.py:50-51,200). */
 int ma3_adaln_input(const float* temb, const float* cap, void* out, int out_dtype, int S, int N, int D, int ts_s,
                     int ts_n, void* stream);
+
+/* x[n] fp32 -> out[0..n) = bf16(x), out[n..2n) = bf16(x - bf16(x)): stacked hi / lo operand copies.  A tap-GEMM over
+ * (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) then carries ~16 mantissa bits through the bf16 tensor cores.  Used for the
+ * step-invariant conditioning path: TimestepEmbedder (flag_large_dit_moe.py:96-133), cap_embedder
+ * (flag_large_dit.py:171-174,198) and every adaLN_modulation Linear (flag_large_dit.py:50-51,120-124). */
+int ma3_split_bf16(const float* x, void* out, int64_t n, void* stream);
 
 /* GroupNorm(groups, eps, affine) optionally followed by swish on channels-last x [B, T, C]
  * (Normalize + nonlinearity, autoencoder1d.py:169-175). */

@@ -694,10 +694,13 @@ int ma3_timestep_embed(const int64_t* t, void* out, int out_dtype, int M, int di
 int ma3_pool_layernorm(const void* ctx, int in_dtype, const float* w, const float* b, void* out, int out_dtype, int N,
                        int L, int Cd, float eps, void* stream) {
   MA3_REQUIRE(ctx && w && b && out && N > 0 && L > 0 && Cd > 0, "pool_layernorm: bad arguments");
-  MA3_REQUIRE(out_dtype == MA3_BF16 && (in_dtype == MA3_F32 || in_dtype == MA3_BF16),
-              "pool_layernorm: in f32/bf16, out bf16 only");
+  MA3_REQUIRE((out_dtype == MA3_BF16 || (out_dtype == MA3_F32 && in_dtype == MA3_F32)) &&
+                  (in_dtype == MA3_F32 || in_dtype == MA3_BF16),
+              "pool_layernorm: in f32/bf16, out bf16 (or f32 from f32)");
   const size_t smem = (size_t)Cd * sizeof(float);
-  if (in_dtype == MA3_F32)
+  if (in_dtype == MA3_F32 && out_dtype == MA3_F32)
+    pool_layernorm_kernel<float, float><<<N, 256, smem, ST(stream)>>>((const float*)ctx, w, b, (float*)out, L, Cd, eps);
+  else if (in_dtype == MA3_F32)
     pool_layernorm_kernel<float, __nv_bfloat16><<<N, 256, smem, ST(stream)>>>((const float*)ctx, w, b,
                                                                                (__nv_bfloat16*)out, L, Cd, eps);
   else
@@ -816,12 +819,37 @@ __global__ void adaln_input_kernel(const float* __restrict__ temb, const float* 
 }
 }  // namespace ma3
 
+// ---------------------------------------------------------------------------------------- bf16 hi/lo split
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): out[i] = hi, out[n + i] = lo (two stacked operand copies).  A GEMM
+// over the taps (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) then carries ~16 mantissa bits through the bf16 tensor cores;
+// used for the step-invariant conditioning path (timestep / caption embedders, adaLN modulation), whose rounding
+// errors are systematic per (sample, channel) and are amplified by the guidance combine.
+namespace ma3 {
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  out[i] = hi;
+  out[n + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+}  // namespace ma3
+
+extern "C" int ma3_split_bf16(const float* x, void* out, int64_t n, void* stream) {
+  MA3_REQUIRE(x && out && n > 0, "split_bf16: bad arguments");
+  ma3::split_bf16_kernel<<<nblk(n, 256), 256, 0, ST(stream)>>>(x, (__nv_bfloat16*)out, n);
+  MA3_LAUNCH_CHECK("split_bf16");
+  return 0;
+}
+
 extern "C" int ma3_adaln_input(const float* temb, const float* cap, void* out, int out_dtype, int S, int N, int D,
                                int ts_s, int ts_n, void* stream) {
   MA3_REQUIRE(temb && cap && out && S > 0 && N > 0 && D > 0, "adaln_input: bad arguments");
-  MA3_REQUIRE(out_dtype == MA3_BF16 || out_dtype == MA3_F16, "adaln_input: 16-bit output only");
+  MA3_REQUIRE(out_dtype >= MA3_F32 && out_dtype <= MA3_F16, "adaln_input: bad output dtype");
   const unsigned grid = nblk((long long)S * N * D, 256);
-  if (out_dtype == MA3_BF16)
+  if (out_dtype == MA3_F32)
+    ma3::adaln_input_kernel<float><<<grid, 256, 0, ST(stream)>>>(temb, cap, (float*)out, S, N, D, ts_s, ts_n);
+  else if (out_dtype == MA3_BF16)
     ma3::adaln_input_kernel<__nv_bfloat16><<<grid, 256, 0, ST(stream)>>>(temb, cap, (__nv_bfloat16*)out, S, N, D, ts_s, ts_n);
   else
     ma3::adaln_input_kernel<__half><<<grid, 256, 0, ST(stream)>>>(temb, cap, (__half*)out, S, N, D, ts_s, ts_n);

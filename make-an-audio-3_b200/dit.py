@@ -11,6 +11,7 @@ K/V are computed once per call to `prepare_context`, the adaLN modulation of eve
 timesteps in one GEMM by `prepare_timesteps`; `run_blocks` then costs 7 launches per block.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -197,16 +198,23 @@ class TxtFlagLargeDiT(nn.Module):
         D, H, F = self.hidden_size, self.num_heads, self.ffn_hidden
         bf = torch.bfloat16
         f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
-        b16 = lambda t: t.detach().to(device=dev, dtype=bf).contiguous()
+        # GEMM weights are stored as fp16 against bf16 activations (one kind::f16 MMA takes the two formats
+        # independently): weights are O(1) so fp16's range is ample, and its 3 extra mantissa bits cut the weight
+        # rounding -- the largest single contributor to the per-step velocity error at depth 28
+        # (tools/precision_study.py) -- by 8x at the same tensor throughput.  MA3_WEIGHT_DTYPE=bf16 restores bf16.
+        wdt = bf if os.environ.get("MA3_WEIGHT_DTYPE", "fp16") == "bf16" else torch.float16
+        b16 = lambda t: t.detach().to(device=dev, dtype=wdt).contiguous()
+        # the step-invariant conditioning path runs as hi/lo split bf16 GEMMs (~fp32 accuracy, ops.gemm_split)
+        sp = lambda t: ops.split_weight(t.to(dev))
         il = lambda w1, w3: torch.stack([w1.detach(), w3.detach()], 1).reshape(2 * w1.shape[0], w1.shape[1])
         p = {}
         p["proj_w"], p["proj_b"] = f32(self.proj_in.weight.detach().t()), f32(self.proj_in.bias)  # [C, D]
         m = self.t_embedder.mlp
-        p["t_w1"], p["t_b1"] = b16(getattr(m, "0").weight), f32(getattr(m, "0").bias)
-        p["t_w2"], p["t_b2"] = b16(getattr(m, "2").weight), f32(getattr(m, "2").bias)
+        p["t_w1"], p["t_b1"] = sp(getattr(m, "0").weight), f32(getattr(m, "0").bias)
+        p["t_w2"], p["t_b2"] = sp(getattr(m, "2").weight), f32(getattr(m, "2").bias)
         ce = self.cap_embedder
         p["cap_ln_w"], p["cap_ln_b"] = f32(getattr(ce, "0").weight), f32(getattr(ce, "0").bias)
-        p["cap_w"], p["cap_b"] = b16(getattr(ce, "1").weight), f32(getattr(ce, "1").bias)
+        p["cap_w"], p["cap_b"] = sp(getattr(ce, "1").weight), f32(getattr(ce, "1").bias)
         if self._video:
             cm = self.c_embedder.mlp
             p["c_w1"], p["c_b1"] = b16(getattr(cm, "0").weight), f32(getattr(cm, "0").bias)
@@ -240,7 +248,7 @@ class TxtFlagLargeDiT(nn.Module):
         fl = self.final_layer
         ada_w.append(getattr(fl.adaLN_modulation, "1").weight.detach())
         ada_b.append(getattr(fl.adaLN_modulation, "1").bias.detach())
-        p["ada_w"], p["ada_b"] = b16(torch.cat(ada_w)), f32(torch.cat(ada_b))
+        p["ada_w"], p["ada_b"] = sp(torch.cat(ada_w)), f32(torch.cat(ada_b))
         p["final_off"] = 6 * D * self.depth
         p["mod_cols"] = 6 * D * self.depth + 2 * D
         p["final_w"], p["final_b"] = f32(fl.linear.weight), f32(fl.linear.bias)
@@ -311,7 +319,7 @@ class TxtFlagLargeDiT(nn.Module):
             c["yn"] = torch.empty(N * Lc, self.y_dim, device=dev, dtype=bf)
             c["ky"] = torch.zeros(self.depth, N, H, Lc, hdp, device=dev, dtype=bf)
             c["vyt"] = ops.alloc_vt(self.depth, N, H, hd=hd, hdp=hdp, tokens_pad=Lp, device=dev, dtype=bf)
-            c["pool"] = torch.empty(N, self.y_dim, device=dev, dtype=bf)
+            c["pool"] = torch.empty(N, self.y_dim, device=dev, dtype=torch.float32)
             c["cap"] = torch.empty(N, D, device=dev, dtype=torch.float32)
             if self._video:
                 c["c1"] = torch.empty(N * Lc, D, device=dev, dtype=bf)
@@ -330,7 +338,7 @@ class TxtFlagLargeDiT(nn.Module):
         else:
             y = context
         ops.pool_layernorm(y, p["cap_ln_w"], p["cap_ln_b"], c["pool"])
-        ops.gemm(c["pool"], p["cap_w"], M=N, N=D, K=self.y_dim, out=c["cap"], bias=p["cap_b"])
+        ops.gemm_split(c["pool"], p["cap_w"], M=N, N=D, K=self.y_dim, out=c["cap"], bias=p["cap_b"])
         ops.rmsnorm_modulate(y.view(N * Lc, self.y_dim), None, c["yn"], eps=self.norm_eps)
         for i, q in enumerate(p["blocks"]):
             ops.gemm(c["yn"], q["wkv_y"], M=N * Lc, N=2 * D, K=self.y_dim, epi=L.EPI_QKV_ROPE, q_out=c["ky"][i],
@@ -354,16 +362,17 @@ class TxtFlagLargeDiT(nn.Module):
         S = 1 if per_sample else Mt
         if per_sample and Mt != N:
             raise ValueError(f"t has {Mt} entries for a batch of {N}")
-        e0 = torch.empty(Mt, 256, device=dev, dtype=bf)
-        e1 = torch.empty(Mt, D, device=dev, dtype=bf)
-        temb = torch.empty(Mt, D, device=dev, dtype=torch.float32)
+        f32 = torch.float32
+        e0 = torch.empty(Mt, 256, device=dev, dtype=f32)
+        e1 = torch.empty(Mt, D, device=dev, dtype=f32)
+        temb = torch.empty(Mt, D, device=dev, dtype=f32)
         ops.timestep_embed(t, e0)
-        ops.gemm(e0, p["t_w1"], M=Mt, N=D, K=256, out=e1, bias=p["t_b1"], act=1)
-        ops.gemm(e1, p["t_w2"], M=Mt, N=D, K=D, out=temb, bias=p["t_b2"])
-        a = torch.empty(S * N, D, device=dev, dtype=bf)
+        ops.gemm_split(e0, p["t_w1"], M=Mt, N=D, K=256, out=e1, bias=p["t_b1"], act=1)
+        ops.gemm_split(e1, p["t_w2"], M=Mt, N=D, K=D, out=temb, bias=p["t_b2"])
+        a = torch.empty(S * N, D, device=dev, dtype=f32)
         ops.adaln_input(temb, c["cap"], a, S, N, 0 if per_sample else 1, 1 if per_sample else 0)
-        mod = torch.empty(S, N, p["mod_cols"], device=dev, dtype=torch.float32)
-        ops.gemm(a, p["ada_w"], M=S * N, N=p["mod_cols"], K=D, out=mod, bias=p["ada_b"])
+        mod = torch.empty(S, N, p["mod_cols"], device=dev, dtype=f32)
+        ops.gemm_split(a, p["ada_w"], M=S * N, N=p["mod_cols"], K=D, out=mod, bias=p["ada_b"])
         return mod
 
     # ---------------------------------------------------------------- per-step work

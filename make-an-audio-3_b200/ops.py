@@ -59,6 +59,7 @@ def declare(lib):
         "ma3_act1d": [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, vp],
         "ma3_attention": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "ma3_l2_persist": [vp, C.c_size_t, vp],
+        "ma3_split_bf16": [vp, vp, i64, vp],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -75,7 +76,7 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
          tile_n=0, cta_group=0, stream_k=0):
     """acc[z,m,n] = sum_taps sum_k A[z, m + a_shift, k] * B[z, n + b_row, k]; see include/ma3_b200.h."""
     lib = L.require_device()
-    assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float16)
+    assert a.dtype in (torch.bfloat16, torch.float16) and b.dtype in (torch.bfloat16, torch.float16)
     d = L.GemmDesc()
     d.a = a.data_ptr()
     d.a_rows = a_rows if a_rows is not None else M
@@ -86,6 +87,7 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
     d.b_ld = b_ld if b_ld is not None else K
     d.b_batch_stride = b_batch_stride
     d.dtype = L.dt(a)
+    d.b_dtype = L.dt(b) if b.dtype != a.dtype else 0
     d.batch, d.M, d.N, d.K = batch, M, N, K
     d.taps = len(taps)
     for i, (s, r) in enumerate(taps):
@@ -224,6 +226,29 @@ def upsample_nearest2(x, out):
     B, T, Cc = x.shape
     _call("ma3_upsample_nearest2", L.ptr(x), L.ptr(out), B * T, Cc)
     return out
+
+
+def split_bf16(x, out):
+    """x fp32 [M, K] -> out bf16 [2M, K]: rows [0, M) = bf16(x), rows [M, 2M) = bf16(x - hi)."""
+    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16 and out.numel() == 2 * x.numel()
+    _call("ma3_split_bf16", L.ptr(x), L.ptr(out), x.numel())
+    return out
+
+
+def gemm_split(x32, w2, *, M, N, K, out, bias=None, act=0):
+    """out = act(x W^T + bias) to ~16 mantissa bits on the bf16 tensor cores: x32 fp32 [M, K]; w2 bf16 [2N, K] = the
+    stacked (hi, lo) halves of W made by `split_weight`.  One tap-GEMM with three taps (hi.hi + lo.hi + hi.lo)."""
+    a2 = torch.empty(2 * M, K, device=x32.device, dtype=torch.bfloat16)
+    split_bf16(x32, a2)
+    return gemm(a2, w2, M=M, N=N, K=K, a_rows=2 * M, b_rows=2 * N, taps=((0, 0), (M, 0), (0, N)), out=out, bias=bias,
+                act=act)
+
+
+def split_weight(w):
+    """fp32 [N, K] -> bf16 [2N, K] (hi rows, then lo rows); done once at pack time."""
+    w = w.detach().float()
+    hi = w.to(torch.bfloat16)
+    return torch.cat([hi, (w - hi.float()).to(torch.bfloat16)]).contiguous()
 
 
 def cast(x, out):
