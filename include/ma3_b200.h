@@ -81,7 +81,8 @@ typedef struct ma3_gemm {
   int64_t a_rows, a_ld, a_batch_stride; /* a_batch_stride in elements; 0 = shared by all z */
   const void* b;          /* [b_batch][b_rows][K] with row pitch b_ld elements */
   int64_t b_rows, b_ld, b_batch_stride;
-  int32_t dtype;          /* MA3_BF16 or MA3_F16: A operand (and B unless b_dtype is set) */
+  int32_t dtype;          /* MA3_BF16 or MA3_F16 (both operands: a kind::f16 MMA whose instruction descriptor names
+                           * different A and B formats raises an illegal-instruction fault on B200 -- measured) */
   int32_t batch;          /* grid z */
   int32_t M, N, K;        /* output rows per z, output columns, reduction length per tap (multiple of 16) */
   int32_t taps;
@@ -117,9 +118,6 @@ typedef struct ma3_gemm {
   int32_t stream_k;       /* MA3_EPI_GATE_RES only.  0: library heuristic; 1: split the tiles x k-iterations space evenly
                            * over the SMs (partial products are added by separate reductions: fp32 sums may differ in the
                            * last bit from run to run); -1: whole tiles only (bit-reproducible) */
-  int32_t b_dtype;        /* 0: B has the same type as A; MA3_BF16 / MA3_F16: B's own 16-bit type (kind::f16 takes the two
-                           * operand formats independently: bf16 activations x fp16 weights keeps the activations'
-                           * range and gives the weights 3 more mantissa bits at the same tensor throughput) */
 } ma3_gemm_t;
 
 int ma3_gemm(const ma3_gemm_t* g, void* stream);

@@ -1132,8 +1132,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
 static int try_conv_narrow(const ma3_gemm_t* g, GemmKParams& kp, cudaStream_t st) {
   static const bool off = getenv("MA3_CONV_NARROW") != nullptr && getenv("MA3_CONV_NARROW")[0] == '0';
   if (off || g->epi != MA3_EPI_STORE || g->K > 64 || g->N > 64 || g->taps < 2 || g->cta_group == 2 || g->tile_n > 0 ||
-      g_gemm_debug_mode != 0 || g_trace != nullptr || g->b_batch_stride != 0 ||
-      (g->b_dtype != 0 && g->b_dtype != g->dtype))
+      g_gemm_debug_mode != 0 || g_trace != nullptr || g->b_batch_stride != 0)
     return 1;
   int lo = g->a_shift[0], hi = g->a_shift[0];
   for (int i = 1; i < g->taps; ++i) { lo = g->a_shift[i] < lo ? g->a_shift[i] : lo; hi = g->a_shift[i] > hi ? g->a_shift[i] : hi; }
@@ -1245,8 +1244,7 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   MA3_REQUIRE(g != nullptr, "gemm: null descriptor");
   MA3_REQUIRE(g->a && g->b, "gemm: null operand");
   MA3_REQUIRE(g->dtype == MA3_BF16 || g->dtype == MA3_F16, "gemm: operand dtype must be bf16 or f16");
-  MA3_REQUIRE(g->b_dtype == 0 || g->b_dtype == MA3_BF16 || g->b_dtype == MA3_F16, "gemm: b_dtype must be 0 / bf16 / f16");
-  const int b_dtype = g->b_dtype ? g->b_dtype : g->dtype;
+
   MA3_REQUIRE(g->M > 0 && g->N > 0 && g->batch > 0, "gemm: empty problem M=%d N=%d batch=%d", g->M, g->N, g->batch);
   MA3_REQUIRE(g->K > 0 && g->K % 16 == 0, "gemm: K=%d must be a positive multiple of 16", g->K);
   MA3_REQUIRE(g->taps >= 1 && g->taps <= MA3_MAX_TAPS, "gemm: taps=%d out of range", g->taps);
@@ -1320,7 +1318,7 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   kp.a_batched = g->a_batch_stride != 0; kp.b_batched = g->b_batch_stride != 0;
   kp.BN = BN; kp.BK = BK; kp.stages = stages;
   kp.tiles_m = (g->M + kBM * CG - 1) / (kBM * CG); kp.tiles_n = (g->N + BN - 1) / BN; kp.batch = g->batch;
-  kp.idesc = umma_idesc2(kBM * CG, BN, g->dtype == MA3_BF16 ? 1 : 0, b_dtype == MA3_BF16 ? 1 : 0);
+  kp.idesc = umma_idesc(kBM * CG, BN, g->dtype == MA3_BF16 ? 1 : 0);
   kp.tmem_stage_cols = pow2_cols(BN);
   kp.tmem_cols = 2 * kp.tmem_stage_cols;
   kp.op_dtype = g->dtype;

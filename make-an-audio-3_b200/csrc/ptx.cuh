@@ -307,12 +307,12 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, int kSw
 
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
 // fmt: 0 = fp16 operands, 1 = bf16 operands.
-// The A and B formats are independent fields (bits 7-9 / 10-12): bf16 activations against fp16 weights is one MMA.
-__host__ __device__ constexpr uint32_t umma_idesc2(int m, int n, int a_fmt, int b_fmt) {
-  return (1u << 4) | (static_cast<uint32_t>(a_fmt) << 7) | (static_cast<uint32_t>(b_fmt) << 10) |
+// The A and B format fields (bits 7-9 / 10-12) must be equal: a descriptor naming bf16 A against fp16 B faults with
+// "illegal instruction" on B200 (measured, round 2), although the fields are separate.
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int fmt) {
+  return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
-__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int fmt) { return umma_idesc2(m, n, fmt, fmt); }
 
 // ---------------------------------------------------------------- packed fp32x2 math (Blackwell FFMA2 / FMUL2)
 __device__ __forceinline__ unsigned long long f2_as_u64(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }

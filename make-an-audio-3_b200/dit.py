@@ -198,12 +198,7 @@ class TxtFlagLargeDiT(nn.Module):
         D, H, F = self.hidden_size, self.num_heads, self.ffn_hidden
         bf = torch.bfloat16
         f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
-        # GEMM weights are stored as fp16 against bf16 activations (one kind::f16 MMA takes the two formats
-        # independently): weights are O(1) so fp16's range is ample, and its 3 extra mantissa bits cut the weight
-        # rounding -- the largest single contributor to the per-step velocity error at depth 28
-        # (tools/precision_study.py) -- by 8x at the same tensor throughput.  MA3_WEIGHT_DTYPE=bf16 restores bf16.
-        wdt = bf if os.environ.get("MA3_WEIGHT_DTYPE", "fp16") == "bf16" else torch.float16
-        b16 = lambda t: t.detach().to(device=dev, dtype=wdt).contiguous()
+        b16 = lambda t: t.detach().to(device=dev, dtype=bf).contiguous()
         # the step-invariant conditioning path runs as hi/lo split bf16 GEMMs (~fp32 accuracy, ops.gemm_split)
         sp = lambda t: ops.split_weight(t.to(dev))
         il = lambda w1, w3: torch.stack([w1.detach(), w3.detach()], 1).reshape(2 * w1.shape[0], w1.shape[1])

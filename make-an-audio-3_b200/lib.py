@@ -44,7 +44,6 @@ class GemmDesc(C.Structure):
         ("tokens", C.c_int32), ("tokens_pad", C.c_int32),
         ("q_scale", C.c_float), ("first_section", C.c_int32),
         ("tile_n", C.c_int32), ("cta_group", C.c_int32), ("stream_k", C.c_int32),
-        ("b_dtype", C.c_int32),
     ]
 
 

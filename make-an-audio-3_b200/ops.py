@@ -76,7 +76,7 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
          tile_n=0, cta_group=0, stream_k=0):
     """acc[z,m,n] = sum_taps sum_k A[z, m + a_shift, k] * B[z, n + b_row, k]; see include/ma3_b200.h."""
     lib = L.require_device()
-    assert a.dtype in (torch.bfloat16, torch.float16) and b.dtype in (torch.bfloat16, torch.float16)
+    assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float16)
     d = L.GemmDesc()
     d.a = a.data_ptr()
     d.a_rows = a_rows if a_rows is not None else M
@@ -87,7 +87,6 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
     d.b_ld = b_ld if b_ld is not None else K
     d.b_batch_stride = b_batch_stride
     d.dtype = L.dt(a)
-    d.b_dtype = L.dt(b) if b.dtype != a.dtype else 0
     d.batch, d.M, d.N, d.K = batch, M, N, K
     d.taps = len(taps)
     for i, (s, r) in enumerate(taps):
