@@ -825,20 +825,57 @@ __global__ void adaln_input_kernel(const float* __restrict__ temb, const float* 
 // used for the step-invariant conditioning path (timestep / caption embedders, adaLN modulation), whose rounding
 // errors are systematic per (sample, channel) and are amplified by the guidance combine.
 namespace ma3 {
-__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n) {
+// slice b of the input = columns [col0 + b * col_step, + cols) of the [rows, ld] fp32 matrix x;
+// out[b] = [2 * rows, cols] bf16: hi rows, then lo rows
+__global__ void split_bf16_kernel(const float* __restrict__ x, long long ld, int col0, int col_step, int rows, int cols,
+                                  __nv_bfloat16* __restrict__ out, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float v = x[i];
+  if (i >= total) return;
+  const int c = (int)(i % cols);
+  const long long rb = i / cols;
+  const int r = (int)(rb % rows), b = (int)(rb / rows);
+  const float v = x[(long long)r * ld + col0 + (long long)b * col_step + c];
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  out[i] = hi;
-  out[n + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  __nv_bfloat16* ob = out + (long long)b * 2 * rows * cols;
+  ob[(long long)r * cols + c] = hi;
+  ob[(long long)(rows + r) * cols + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// tail[r, (2 i + j) * D + d] = norm_w[i][j][d] * (1 + mod[r, 6 D i + (j ? 4 D : D) + d]): the folded RMSNorm weight
+// wn_s = w * (1 + scale_s) of both norms of every block, stored behind the modulation columns of the same row so that
+// it shares the row pitch of the gate vectors (fused-RMSNorm producer, see ma3_gemm_t.norm_w).
+__global__ void norm_weights_kernel(float* __restrict__ mod, long long ld, const float* __restrict__ nw, int depth, int D,
+                                    int tail_off, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int d = (int)(i % D);
+  const long long t = i / D;
+  const int ij = (int)(t % (2 * depth));
+  const long long r = t / (2 * depth);
+  const int blk = ij >> 1, j = ij & 1;
+  float* row = mod + r * ld;
+  row[tail_off + (long long)ij * D + d] = nw[(long long)ij * D + d] * (1.f + row[6LL * D * blk + (j ? 4 : 1) * D + d]);
 }
 }  // namespace ma3
 
-extern "C" int ma3_split_bf16(const float* x, void* out, int64_t n, void* stream) {
-  MA3_REQUIRE(x && out && n > 0, "split_bf16: bad arguments");
-  ma3::split_bf16_kernel<<<nblk(n, 256), 256, 0, ST(stream)>>>(x, (__nv_bfloat16*)out, n);
+extern "C" int ma3_split_bf16(const float* x, int64_t ld, int col0, int col_step, int nb, int rows, int cols, void* out,
+                              void* stream) {
+  MA3_REQUIRE(x && out && nb > 0 && rows > 0 && cols > 0 && ld >= cols, "split_bf16: bad arguments");
+  const long long total = (long long)nb * rows * cols;
+  ma3::split_bf16_kernel<<<nblk(total, 256), 256, 0, ST(stream)>>>(x, ld, col0, col_step, rows, cols,
+                                                                    (__nv_bfloat16*)out, total);
   MA3_LAUNCH_CHECK("split_bf16");
+  return 0;
+}
+
+extern "C" int ma3_norm_weights(float* mod, int64_t ld, const float* norm_w, int rows, int depth, int D, int tail_off,
+                                void* stream) {
+  MA3_REQUIRE(mod && norm_w && rows > 0 && depth > 0 && D > 0 && tail_off >= 6 * D * depth &&
+                  ld >= tail_off + 2LL * depth * D,
+              "norm_weights: bad arguments");
+  const long long total = (long long)rows * 2 * depth * D;
+  ma3::norm_weights_kernel<<<nblk(total, 256), 256, 0, ST(stream)>>>(mod, ld, norm_w, depth, D, tail_off, total);
+  MA3_LAUNCH_CHECK("norm_weights");
   return 0;
 }
 

@@ -53,6 +53,15 @@ struct GemmKParams {
   int debug_mode;    // diagnostics: 1 = no TMA loads, 2 = no MMAs
   // narrow-conv kernel (conv_narrow_kernel): rows of the staged A tile, smallest tap shift, padded N, A stages
   int cn_rows_a, cn_min_shift, cn_bnp, cn_stages;
+  // fused RMSNorm (see ma3_gemm_t): producer outputs of GATE_RES, consumer pre-op of any epilogue
+  void* norm_out;
+  const float* norm_w;
+  float* ss_out;
+  const float* row_ss;
+  int ss_cols;
+  float ss_inv_dim, ss_eps;
+  const float* col_bias2;
+  long long col_bias2_ld;
   int stream_k;      // GATE_RES only: workers take equal contiguous ranges of (tile, k-iteration) instead of whole tiles
   long long* trace;  // diagnostics: when non-null, CTA 0 records clock64() at pipeline events (tools/probe_trace.py)
 };
@@ -326,7 +335,56 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
     float* out = reinterpret_cast<float*>(p.out);
     const int cg = (lane & 7) * 4;
     const int col = n0 + cg;
-    if (cg < w && col < p.N) {  // N % 4 == 0 enforced on the host
+    if (p.norm_out != nullptr) {
+      if (n0 >= p.N) { __syncwarp(); return; }   // chunk of a ragged last column tile that lies wholly beyond N
+      // Fused-RMSNorm producer (w == 32 and N % 32 == 0 guaranteed by the host checks): this tile owns its elements of h,
+      // so the update is a plain load-add-store, and the same pass emits the next GEMM's 16-bit operand h_new * wn_s
+      // and the chunk's per-row sum of squares (8 lanes of a row reduce by shuffles; one store per row and chunk, so
+      // the partial sums are deterministic).
+      uint16_t* gout = reinterpret_cast<uint16_t*>(p.norm_out);
+      const float* sp = stg + (lane >> 3) * kStagePitch + cg;
+      float* ssp = p.ss_out + (long long)(m0 + (lane >> 3)) * p.ss_cols + (n0 >> 5);
+      const long long ss_step = 4LL * p.ss_cols;
+#pragma unroll
+      for (int hp = 0; hp < 4; ++hp) {
+        float4 gv[2], hv[2], wv[2];
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+          const int pass = hp * 2 + q2;
+          if (rc.off[pass] >= 0) {
+            gv[q2] = *reinterpret_cast<const float4*>(p.gate + rc.aux[pass] + col);
+            wv[q2] = *reinterpret_cast<const float4*>(p.norm_w + rc.aux[pass] + col);
+            hv[q2] = *reinterpret_cast<const float4*>(out + rc.off[pass] + col);
+          }
+        }
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+          const int pass = hp * 2 + q2;
+          float ss = 0.f;
+          if (rc.off[pass] >= 0) {
+            const float4 a = lds_f4(sp);
+            float4 hn;
+            hn.x = fmaf(gv[q2].x, a.x, hv[q2].x); hn.y = fmaf(gv[q2].y, a.y, hv[q2].y);
+            hn.z = fmaf(gv[q2].z, a.z, hv[q2].z); hn.w = fmaf(gv[q2].w, a.w, hv[q2].w);
+            *reinterpret_cast<float4*>(out + rc.off[pass] + col) = hn;
+            uint2 u;
+            if (p.op_dtype == MA3_BF16) {
+              u.x = pack_bf16(hn.x * wv[q2].x, hn.y * wv[q2].y); u.y = pack_bf16(hn.z * wv[q2].z, hn.w * wv[q2].w);
+            } else {
+              u.x = pack_f16(hn.x * wv[q2].x, hn.y * wv[q2].y); u.y = pack_f16(hn.z * wv[q2].z, hn.w * wv[q2].w);
+            }
+            *reinterpret_cast<uint2*>(gout + rc.off[pass] + col) = u;
+            ss = fmaf(hn.x, hn.x, fmaf(hn.y, hn.y, fmaf(hn.z, hn.z, hn.w * hn.w)));
+          }
+          ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+          ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+          ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+          if ((lane & 7) == 0 && rc.off[pass] >= 0) *ssp = ss;
+          ssp += ss_step;
+          sp += 4 * kStagePitch;
+        }
+      }
+    } else if (cg < w && col < p.N) {  // N % 4 == 0 enforced on the host
       float4 gv[8];
 #pragma unroll
       for (int pass = 0; pass < 8; ++pass)
@@ -909,6 +967,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       float* stg = staging + ew * (32 * kStagePitch);
       RowCtx rc;
       make_row_ctx<EPI>(p, z, m0, lane, rc);
+      // fused-RMSNorm consumer: this thread's accumulator row (TMEM lane) is m0 + lane; its rstd comes from the
+      // producer's per-chunk sums of squares, its bias row from the row's sample (computed while the mainloop runs)
+      float pre_rstd = 0.f;
+      const float* pre_bias = nullptr;
+      constexpr bool kPreOp = EPI == MA3_EPI_QKV_ROPE || EPI == MA3_EPI_SWIGLU;   // the two consumers of a norm in the DiT
+      if (kPreOp && p.row_ss != nullptr) {
+        const int m = m0 + lane;
+        const int mc = m < p.M ? m : p.M - 1;
+        const float4* ssr = reinterpret_cast<const float4*>(p.row_ss + (long long)mc * p.ss_cols);
+        float s4 = 0.f;
+        for (int j = 0; j < (p.ss_cols >> 2); ++j) {
+          const float4 v = __ldg(ssr + j);
+          s4 += (v.x + v.y) + (v.z + v.w);
+        }
+        pre_rstd = rsqrtf(s4 * p.ss_inv_dim + p.ss_eps);
+        pre_bias = p.col_bias2 + (long long)fast_div(mc, p.inv_rows_per_sample) * p.col_bias2_ld;
+      }
       if (ew == 0 && lane == 0) trace_evt(p, lt, 4);
       mbar_wait(&tfull[as], aph);
       if (ew == 0 && lane == 0) trace_evt(p, lt, 5);
@@ -934,6 +1009,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
         }
         tmem_ld_wait();
         if (tr0) trace_evt(p, lt, 9);
+        if (kPreOp && pre_bias != nullptr && n_t * p.BN + c0 < p.N) {   // acc <- acc * rstd[row] + (shift_s W^T)[n]  (N % 32 == 0)
+          const float4* b4 = reinterpret_cast<const float4*>(pre_bias + n_t * p.BN + c0);
+          const float2 rs2 = make_float2(pre_rstd, pre_rstd);
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 b = __ldg(b4 + (e >> 2));   // same address in every lane of a sample: one broadcast request
+            const float2 lo = ffma2(make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), rs2, make_float2(b.x, b.y));
+            const float2 hi = ffma2(make_float2(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])), rs2, make_float2(b.z, b.w));
+            r[e] = __float_as_uint(lo.x); r[e + 1] = __float_as_uint(lo.y);
+            r[e + 2] = __float_as_uint(hi.x); r[e + 3] = __float_as_uint(hi.y);
+          }
+        }
         if constexpr (EPI == MA3_EPI_STORE) {
           epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc, &rp);
         } else if constexpr (EPI == MA3_EPI_QKV_ROPE) {
@@ -1357,6 +1444,17 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   }
   kp.trace = g_trace;
   kp.debug_mode = g_gemm_debug_mode;
+  if (g->row_ss != nullptr) {
+    MA3_REQUIRE(g->col_bias2 && g->rows_per_sample > 0 && g->ss_dim > 0 && g->ss_cols > 0 && g->ss_cols % 4 == 0,
+                "gemm/fused-norm consumer: col_bias2, rows_per_sample, ss_dim and ss_cols %% 4 == 0 required");
+    MA3_REQUIRE(g->N % 32 == 0 && BN % 32 == 0 && g->batch == 1 && aligned16(g->row_ss) && aligned16(g->col_bias2) &&
+                    g->col_bias2_ld % 4 == 0,
+                "gemm/fused-norm consumer: N and tile_n must be multiples of 32, batch 1, 16-byte aligned tables");
+    MA3_REQUIRE(g->epi == MA3_EPI_QKV_ROPE || g->epi == MA3_EPI_SWIGLU,
+                "gemm/fused-norm consumer: only the QKV_ROPE and SWIGLU epilogues take a normalised input in the DiT");
+    kp.row_ss = g->row_ss; kp.ss_cols = g->ss_cols; kp.ss_inv_dim = 1.0f / (float)g->ss_dim; kp.ss_eps = g->ss_eps;
+    kp.col_bias2 = g->col_bias2; kp.col_bias2_ld = g->col_bias2_ld;
+  }
 
   const int total_tiles = kp.tiles_m * kp.tiles_n * kp.batch;
   const int workers = num_sms() / CG;   // CTAs (CG = 1) or CTA pairs (CG = 2)
@@ -1394,6 +1492,16 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
       MA3_REQUIRE(g->N % 4 == 0 && g->out_ld % 4 == 0 && g->gate_ld % 4 == 0 && aligned16(g->out) && aligned16(g->gate),
                   "gemm/gate_res: N, out_ld, gate_ld must be multiples of 4 and pointers 16-byte aligned");
       MA3_REQUIRE(g->stream_k >= -1 && g->stream_k <= 1, "gemm/gate_res: stream_k must be -1, 0 or 1");
+      if (g->norm_out != nullptr) {
+        MA3_REQUIRE(g->norm_w && g->ss_out && g->N % 32 == 0 && BN % 32 == 0 && g->stream_k != 1,
+                    "gemm/gate_res fused norm: norm_w, ss_out, N %% 32 == 0, tile_n %% 32 == 0, no stream-K");
+        MA3_REQUIRE(g->ss_cols >= g->N / 32 && g->ss_cols % 4 == 0, "gemm/gate_res fused norm: ss_cols >= N/32, %% 4 == 0");
+        kp.ss_cols = g->ss_cols;
+        MA3_REQUIRE(aligned16(g->norm_out) && aligned16(g->norm_w) && aligned16(g->ss_out) && g->out_ld % 8 == 0,
+                    "gemm/gate_res fused norm: 16-byte aligned pointers, out_ld %% 8 == 0");
+        kp.norm_out = g->norm_out; kp.norm_w = g->norm_w; kp.ss_out = g->ss_out;
+        return launch<MA3_EPI_GATE_RES>(kp, smem, grid, CG, st);
+      }
       {
         // stream-K when whole tiles would leave a large part of the last wave idle and every worker still gets a
         // reasonable run of k-iterations

@@ -59,7 +59,8 @@ def declare(lib):
         "ma3_act1d": [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, vp],
         "ma3_attention": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "ma3_l2_persist": [vp, C.c_size_t, vp],
-        "ma3_split_bf16": [vp, vp, i64, vp],
+        "ma3_split_bf16": [vp, i64, i32, i32, i32, i32, i32, vp, vp],
+        "ma3_norm_weights": [vp, i64, vp, i32, i32, i32, i32, vp],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -73,7 +74,8 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
          out_row_mul=1, out_row_off=0, bias=None, bias_per_row=False, res=None, res_ld=None, res_batch_stride=0,
          alpha=1.0, accumulate=False, gate=None, rows_per_sample=0, q_out=None, k_out=None, vt_out=None, rope=None,
          model_dim=0, head_dim=0, head_dim_pad=0, tokens=0, tokens_pad=0, q_scale=1.0, first_section=0, act=0,
-         tile_n=0, cta_group=0, stream_k=0):
+         tile_n=0, cta_group=0, stream_k=0, norm_out=None, norm_w=None, ss_out=None, row_ss=None, ss_dim=0,
+         ss_eps=1e-5, col_bias2=None):
     """acc[z,m,n] = sum_taps sum_k A[z, m + a_shift, k] * B[z, n + b_row, k]; see include/ma3_b200.h."""
     lib = L.require_device()
     assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float16)
@@ -126,6 +128,16 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
     d.tile_n = tile_n
     d.cta_group = cta_group
     d.stream_k = stream_k
+    if norm_out is not None:   # fused-RMSNorm producer (GATE_RES): see include/ma3_b200.h
+        assert norm_w.dtype == torch.float32 and norm_w.stride(0) == gate.stride(0) and ss_out.dtype == torch.float32
+        assert norm_out.dtype == a.dtype and N % 32 == 0 and ss_out.shape[-1] >= N // 32 and ss_out.shape[-1] % 4 == 0
+        d.norm_out, d.norm_w, d.ss_out = norm_out.data_ptr(), norm_w.data_ptr(), ss_out.data_ptr()
+        d.ss_cols = ss_out.shape[-1]
+        d.stream_k = -1
+    if row_ss is not None:     # fused-RMSNorm consumer
+        assert row_ss.dtype == torch.float32 and col_bias2.dtype == torch.float32 and rows_per_sample > 0
+        d.row_ss, d.ss_cols, d.ss_dim, d.ss_eps = row_ss.data_ptr(), row_ss.shape[-1], ss_dim, ss_eps
+        d.col_bias2, d.col_bias2_ld = col_bias2.data_ptr(), col_bias2.stride(0)
     with _Span(f"tap_gemm/{_EPI_NAMES[epi]}/M{M} N{N} K{K} taps{len(taps)} batch{batch}", 2.0 * M * N * K * len(taps) * batch):
         L.check(lib.ma3_gemm(C.byref(d), L.stream_ptr()), "ma3_gemm")
     return out
@@ -227,20 +239,31 @@ def upsample_nearest2(x, out):
     return out
 
 
-def split_bf16(x, out):
-    """x fp32 [M, K] -> out bf16 [2M, K]: rows [0, M) = bf16(x), rows [M, 2M) = bf16(x - hi)."""
-    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16 and out.numel() == 2 * x.numel()
-    _call("ma3_split_bf16", L.ptr(x), L.ptr(out), x.numel())
+def split_bf16(x, out, *, col0=0, col_step=0, nb=1, cols=None):
+    """x fp32 [M, ld] -> out bf16 [nb, 2M, cols]: slice b = columns [col0 + b*col_step, +cols) of x;
+    rows [0, M) = bf16(slice), rows [M, 2M) = bf16(slice - hi)."""
+    M = x.shape[0]
+    cols = x.shape[1] if cols is None else cols
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and out.dtype == torch.bfloat16
+    assert out.is_contiguous() and out.numel() == 2 * nb * M * cols
+    _call("ma3_split_bf16", L.ptr(x), x.stride(0), col0, col_step, nb, M, cols, L.ptr(out))
     return out
 
 
-def gemm_split(x32, w2, *, M, N, K, out, bias=None, act=0):
+def norm_weights(mod2d, norm_w, depth, D, tail_off):
+    """mod2d fp32 [rows, ld] (in place): tail columns <- norm_w[i][j] * (1 + scale slot), see include/ma3_b200.h."""
+    assert mod2d.dtype == torch.float32 and mod2d.stride(1) == 1 and norm_w.is_contiguous()
+    _call("ma3_norm_weights", L.ptr(mod2d), mod2d.stride(0), L.ptr(norm_w), mod2d.shape[0], depth, D, tail_off)
+    return mod2d
+
+
+def gemm_split(x32, w2, *, M, N, K, out, bias=None, act=0, out_ld=None):
     """out = act(x W^T + bias) to ~16 mantissa bits on the bf16 tensor cores: x32 fp32 [M, K]; w2 bf16 [2N, K] = the
     stacked (hi, lo) halves of W made by `split_weight`.  One tap-GEMM with three taps (hi.hi + lo.hi + hi.lo)."""
     a2 = torch.empty(2 * M, K, device=x32.device, dtype=torch.bfloat16)
     split_bf16(x32, a2)
     return gemm(a2, w2, M=M, N=N, K=K, a_rows=2 * M, b_rows=2 * N, taps=((0, 0), (M, 0), (0, N)), out=out, bias=bias,
-                act=act)
+                act=act, out_ld=out_ld)
 
 
 def split_weight(w):

@@ -127,11 +127,11 @@ class CFMSampler:
         st = self._graphs.get(key)
         if st is None:
             st = {"traj": torch.empty(S + 1, B, C, T, device=dev, dtype=torch.float32),
-                  "mod": torch.empty(S, N, dit._ensure()["mod_cols"], device=dev, dtype=torch.float32),
+                  "cond": dit.cond_buffers(S, N),
                   "v": torch.empty(N, C, T, device=dev, dtype=torch.float32), "graph": None,
                   "keep": (dit._packed, cbuf, work)}
             self._graphs = {key: st}          # keep one plan: buffers are large
-        st["mod"].copy_(dit.prepare_timesteps(torch.tensor(ints, dtype=torch.int64)))
+        dit.prepare_timesteps(torch.tensor(ints, dtype=torch.int64), out=st["cond"])   # step-invariant, outside the loop
         st["traj"][0].copy_(x0)
 
         def loop():
@@ -200,8 +200,8 @@ class CFMSampler:
         dit = self.dit
         p = dit._packed
         D = dit.hidden_size
-        mod = st["mod"][k]
-        w = dit.run_blocks(st["traj"][k], mod, t_ints=[t_int] * N if dit.num_experts else None)
+        mod = st["cond"]["mod"][k]
+        w = dit.run_blocks(st["traj"][k], st["cond"], k, t_ints=[t_int] * N if dit.num_experts else None)
         off = p["final_off"]
         if cfg:
             ops.final_layer_cfg_euler(w.h, mod, off, off + D, p["final_w"], p["final_b"], N, T, scale, dt,

@@ -114,7 +114,7 @@ def test_sampler_golden(golden):
         for rep in range(2):  # second call with graphs replays the captured loop
             for st in s._graphs.values():      # a replay that did nothing must not pass on the first call's result
                 st["traj"].fill_(float("nan"))
-                st["mod"].fill_(float("nan"))
+                st["cond"]["mod"].fill_(float("nan"))
             xf, traj = s.sample_cfg(c.cuda(), 3.0, uc.cuda(), 2, timesteps=6, x_latent=x0.cuda())
             assert traj.shape == golden["cfm_cfg_traj"].shape
             assert O.cosine(xf.cpu(), golden["cfm_cfg_final"]) > 0.999
@@ -276,9 +276,11 @@ def test_pipeline_full_size_properties():
     x0 = torch.randn(B, 20, T, generator=g).cuda()
     w_eager = pipe.generate(cond, unc, x0, scale=3.0, timesteps=25).clone()     # first call: eager pass + capture
     for st in list(pipe.sampler._graphs.values()) + list(pipe._tail.values()):  # a no-op replay must not pass
-        for k in ("traj", "mod", "wav", "zin"):
+        for k in ("traj", "wav", "zin"):
             if k in st:
                 st[k].fill_(float("nan"))
+        if "cond" in st:
+            st["cond"]["mod"].fill_(float("nan"))
     w_graph = pipe.generate(cond, unc, x0, scale=3.0, timesteps=25).clone()     # second call: graph replay
     assert w_graph.shape == (B, 2 * T * 256)
     assert torch.equal(w_eager, w_graph)
