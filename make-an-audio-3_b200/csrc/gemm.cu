@@ -1008,8 +1008,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
         continue;
       }
       float* stg = staging + ew * (32 * kStagePitch);
-      RowCtx rc;
-      make_row_ctx<EPI>(p, z, m0, lane, rc);
       // fused-RMSNorm consumer: this thread's accumulator row (TMEM lane) is m0 + lane; its rstd comes from the
       // producer's per-chunk sums of squares, its bias row from the row's sample (computed while the mainloop runs)
       // (done while the mainloop of the tile runs).  The bias values of the warp's own column chunks -- for the at most
@@ -1021,30 +1019,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
       if (kPreOp && p.row_ss != nullptr) {
         const int m = m0 + lane;
         const int mc = m < p.M ? m : p.M - 1;
+        // every load of this prologue is issued before the first use (fully unrolled, predicated): a rolled loop would
+        // pay one L2 round trip per iteration and delay the warp's start on the tile by more than a mainloop
         const float4* ssr = reinterpret_cast<const float4*>(p.row_ss + (long long)mc * p.ss_cols);
-        float s4 = 0.f;
-        for (int j = 0; j < (p.ss_cols >> 2); ++j) {
-          const float4 v = __ldg(ssr + j);
-          s4 += (v.x + v.y) + (v.z + v.w);
-        }
-        pre_rstd = rsqrtf(s4 * p.ss_inv_dim + p.ss_eps);
+        const int n4 = p.ss_cols >> 2;   // <= 16 (host check)
+        float4 sv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sv[j] = j < n4 ? __ldg(ssr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         const int s_first = fast_div(m0 < p.M ? m0 : p.M - 1, p.inv_rows_per_sample);
         const int s_mine = fast_div(mc, p.inv_rows_per_sample);
         const int s_last = __shfl_sync(0xffffffffu, s_mine, 31);
         float* bs = bias_stage + ew * 256;               // [2 samples][4 chunks][32 columns]
-        const int nchunk = (p.BN - half * 32 + 63) >> 6;  // chunks this warp owns in a tile
-        for (int idx = lane; idx < 2 * nchunk * 8; idx += 32) {
-          const int sidx = idx / (nchunk * 8), jj = idx - sidx * nchunk * 8;
-          const int jc = jj >> 3, within = (jj & 7) * 4;
-          const int col = n_t * p.BN + half * 32 + jc * 64 + within;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (col < p.N)
-            v = __ldg(reinterpret_cast<const float4*>(p.col_bias2 + (long long)(sidx ? s_last : s_first) * p.col_bias2_ld + col));
-          *reinterpret_cast<float4*>(bs + sidx * 128 + jc * 32 + within) = v;
+        // lane l stages float4 #(l & 7) of chunk (l >> 3) for both samples
+        const int bcol = n_t * p.BN + half * 32 + (lane >> 3) * 64 + (lane & 7) * 4;
+        float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0;
+        if (bcol < p.N && (lane >> 3) * 64 + half * 32 < p.BN) {
+          bv0 = __ldg(reinterpret_cast<const float4*>(p.col_bias2 + (long long)s_first * p.col_bias2_ld + bcol));
+          bv1 = __ldg(reinterpret_cast<const float4*>(p.col_bias2 + (long long)s_last * p.col_bias2_ld + bcol));
         }
+        float s4 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s4 += (sv[j].x + sv[j].y) + (sv[j].z + sv[j].w);
+        pre_rstd = rsqrtf(s4 * p.ss_inv_dim + p.ss_eps);
+        *reinterpret_cast<float4*>(bs + lane * 4) = bv0;
+        *reinterpret_cast<float4*>(bs + 128 + lane * 4) = bv1;
         __syncwarp();
         pre_bias = bs + (s_mine == s_first ? 0 : 128);
       }
+      RowCtx rc;
+      make_row_ctx<EPI>(p, z, m0, lane, rc);
       if (ew == 0 && lane == 0) trace_evt(p, lt, 4);
       mbar_wait(&tfull[as], aph);
       if (ew == 0 && lane == 0) trace_evt(p, lt, 5);
@@ -1514,8 +1517,9 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   kp.trace = g_trace;
   kp.debug_mode = g_gemm_debug_mode;
   if (g->row_ss != nullptr) {
-    MA3_REQUIRE(g->col_bias2 && g->rows_per_sample > 0 && g->ss_dim > 0 && g->ss_cols > 0 && g->ss_cols % 4 == 0,
-                "gemm/fused-norm consumer: col_bias2, rows_per_sample, ss_dim and ss_cols %% 4 == 0 required");
+    MA3_REQUIRE(g->col_bias2 && g->rows_per_sample >= 32 && g->ss_dim > 0 && g->ss_cols > 0 && g->ss_cols % 4 == 0 &&
+                    g->ss_cols <= 64,
+                "gemm/fused-norm consumer: col_bias2, rows_per_sample >= 32, ss_dim, ss_cols %% 4 == 0 (<= 64) required");
     MA3_REQUIRE(g->N % 32 == 0 && BN % 32 == 0 && g->batch == 1 && aligned16(g->row_ss) && aligned16(g->col_bias2) &&
                     g->col_bias2_ld % 4 == 0,
                 "gemm/fused-norm consumer: N and tile_n must be multiples of 32, batch 1, 16-byte aligned tables");

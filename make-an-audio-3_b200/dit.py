@@ -442,7 +442,7 @@ class TxtFlagLargeDiT(nn.Module):
         w = self._workspace(N, T)
         M = N * T
         mod = cond["mod"][k]
-        fused = p["fused"]
+        fused = p["fused"] and T >= 32      # a warp's 32 accumulator rows must lie in at most two samples
         qs = math.log2(math.e) / math.sqrt(hd)
         eps = self.norm_eps
         if T > p["rope"].shape[0]:
