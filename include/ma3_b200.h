@@ -139,6 +139,20 @@ typedef struct ma3_gemm {
 } ma3_gemm_t;
 
 int ma3_gemm(const ma3_gemm_t* g, void* stream);
+
+/* Row-owning gated-residual GEMM with the following RMSNorm + adaLN modulate fused in -- the wo and w2 projections of a
+ * Next-DiT block together with the normalisation that feeds the next projection (flag_large_dit.py:79-91,
+ * flag_large_dit_moe.py:63-81):
+ *     h[m, :] <- h[m, :] + gate[s, :] * (a[m, :] . w^T)                                   (fp32, in place)
+ *     u_out[m, :] <- 16-bit( h_new[m, :] * rsqrt(mean_D(h_new[m, :]^2) + eps) * wn[s, :] + shift[s, :] )
+ * with s = m / rows_per_sample and wn = norm_weight * (1 + scale) (ma3_norm_weights).  a [M][K] and w [D][K] are 16-bit
+ * (`dtype`), row pitches a_ld / w_ld in elements; gate / wn / shift are fp32 [samples][mod_ld].  u_out == NULL: only the
+ * residual update (last block).  D must be 384 * {1, 2, 3, 4}: a thread-block cluster of D / 384 CTAs owns 128 complete
+ * rows (384 TMEM columns per CTA), the row sums of squares cross the cluster through distributed shared memory.  No
+ * atomics: bit-reproducible. */
+int ma3_gemm_rownorm(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int dtype, int M, int K, int D, float* h,
+                     const float* gate, const float* wn, const float* shift, int64_t mod_ld, int rows_per_sample,
+                     void* u_out, float eps, void* stream);
 /* diagnostics only: device buffer (>= 256 int64) that CTA 0 of later ma3_gemm launches fills with clock64() stamps of
  * its pipeline events; NULL switches tracing off (tools/probe_trace.py). */
 int ma3_debug_set_gemm_trace(void* buf);

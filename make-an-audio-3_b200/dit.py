@@ -216,22 +216,17 @@ class TxtFlagLargeDiT(nn.Module):
             p["c_w2"], p["c_b2"] = b16(getattr(cm, "2").weight), f32(getattr(cm, "2").bias)
             p["c_ln_w"], p["c_ln_b"] = f32(getattr(cm, "3").weight), f32(getattr(cm, "3").bias)
         ada_w, ada_b, blocks = [], [], []
-        # dense FFN blocks run with the RMSNorms fused into the GEMMs around them (MA3_FUSED_NORM=0: stand-alone norms)
-        fused = not self.num_experts and D % 32 == 0 and os.environ.get("MA3_FUSED_NORM", "1") != "0"
+        # Dense blocks whose width is a multiple of 384 run wo / w2 as row-owning cluster GEMMs that also emit the
+        # normalised, modulated operand of the next projection (ma3_gemm_rownorm): 5 launches per block, no stand-alone
+        # RMSNorm pass.  MA3_ROWNORM=0 restores the 7-launch form.
+        fused = not self.num_experts and D % 384 == 0 and D // 384 <= 4 and os.environ.get("MA3_ROWNORM", "1") != "0"
         if fused:
-            # one contiguous tensor per weight kind, so that the per-block shift_s W^T tables are ONE batched GEMM
-            p["wqkv_all"] = torch.empty(self.depth, 3 * D, D, device=dev, dtype=bf)
-            p["w13_all"] = torch.empty(self.depth, 2 * F, D, device=dev, dtype=bf)
             p["norm_w"] = torch.stack([torch.stack([f32(b_.attention_norm.weight), f32(b_.ffn_norm.weight)])
                                        for b_ in self.blocks]).contiguous()          # [depth, 2, D]
         for bi, blk in enumerate(self.blocks):
             a = blk.attention
             q = {}
-            if fused:
-                p["wqkv_all"][bi].copy_(torch.cat([a.wq.weight, a.wk.weight, a.wv.weight]).detach())
-                q["wqkv"] = p["wqkv_all"][bi]
-            else:
-                q["wqkv"] = b16(torch.cat([a.wq.weight, a.wk.weight, a.wv.weight]))
+            q["wqkv"] = b16(torch.cat([a.wq.weight, a.wk.weight, a.wv.weight]))
             yw = blk.attention_y_norm.weight.detach()[None, :]  # RMSNorm_y scale folded into the projections
             q["wkv_y"] = b16(torch.cat([a.wk_y.weight.detach() * yw, a.wv_y.weight.detach() * yw]))
             q["wo"] = b16(a.wo.weight)
@@ -247,8 +242,7 @@ class TxtFlagLargeDiT(nn.Module):
                               for j, e in enumerate(ff.freq_experts.values())]
                 q["f_w2"] = [b16(e.w2.weight[j * band:(j + 1) * band, :]) for j, e in enumerate(ff.freq_experts.values())]
             else:
-                p["w13_all"][bi].copy_(il(ff.w1.weight, ff.w3.weight))
-                q["w13"] = p["w13_all"][bi]
+                q["w13"] = b16(il(ff.w1.weight, ff.w3.weight))
                 q["w2"] = b16(ff.w2.weight)
             blocks.append(q)
             ada_w.append(getattr(blk.adaLN_modulation, "1").weight.detach())
@@ -301,9 +295,6 @@ class TxtFlagLargeDiT(nn.Module):
             w.hdp, w.Tp = hdp, Tp
             w.h = torch.empty(N * T, D, device=dev, dtype=torch.float32)
             w.u = torch.empty(N * T, D, device=dev, dtype=bf)
-            w.g = torch.empty(N * T, D, device=dev, dtype=bf)                       # h * wn_s (fused RMSNorm operand)
-            # per-chunk sums of squares of h (row pitch padded to 4 floats; the pad columns stay zero)
-            w.ss = torch.zeros(N * T, (D // 32 + 3) // 4 * 4, device=dev, dtype=torch.float32)
             w.q = torch.zeros(N, H, T, hdp, device=dev, dtype=bf)
             w.k = torch.zeros(N, H, T, hdp, device=dev, dtype=bf)
             w.vt = ops.alloc_vt(N, H, hd=hd, hdp=hdp, tokens_pad=Tp, device=dev, dtype=bf)
@@ -363,23 +354,15 @@ class TxtFlagLargeDiT(nn.Module):
 
     def cond_buffers(self, S, N):
         """Device buffers of one (steps, batch) conditioning: `mod` fp32 [S, N, mod_ld] = the adaLN modulation of every
-        block and of the final layer (+ the folded norm weights of dense models); dense models also get the per-block
-        bias tables of the fused RMSNorm, b2q [depth, S*N, 3D] = shift_1 Wqkv^T and b2f [depth, S*N, 2F] = shift_2 W13^T."""
+        block and of the final layer; fused models append wn_s = w * (1 + scale_s) of both norms of every block."""
         p = self._ensure()
         dev = self.proj_in.weight.device
-        D, F = self.hidden_size, self.ffn_hidden
-        c = {"S": S, "N": N, "mod": torch.empty(S, N, p["mod_ld"], device=dev, dtype=torch.float32)}
-        if p["fused"]:
-            c["b2q"] = torch.empty(self.depth, S * N, 3 * D, device=dev, dtype=torch.float32)
-            c["b2f"] = torch.empty(self.depth, S * N, 2 * F, device=dev, dtype=torch.float32)
-            c["sh2"] = torch.empty(2 * self.depth, 2 * S * N, D, device=dev, dtype=torch.bfloat16)
-        return c
+        return {"S": S, "N": N, "mod": torch.empty(S, N, p["mod_ld"], device=dev, dtype=torch.float32)}
 
     @torch.no_grad()
     def prepare_timesteps(self, t, per_sample=False, out=None):
         """adaLN modulation of every block (+ final layer) for all requested timesteps in ONE GEMM (hi/lo split bf16:
-        ~fp32 accuracy), plus -- dense models -- what the fused RMSNorms need: wn_s = w (1 + scale_s) behind the
-        modulation columns and the shift_s W^T bias tables (two batched GEMMs over all blocks).
+        ~fp32 accuracy), plus -- fused models -- wn_s = w (1 + scale_s) of every norm behind the modulation columns.
         t: int64 [S] (per_sample=False: every sample shares t[s]) or [N] (per_sample=True: one step, t per sample).
         Returns the cond_buffers dict (filled in place when `out` is given)."""
         p = self._ensure()
@@ -407,19 +390,7 @@ class TxtFlagLargeDiT(nn.Module):
         R = S * N
         ops.gemm_split(a, p["ada_w"], M=R, N=p["mod_cols"], K=D, out=mod, out_ld=p["mod_ld"], bias=p["ada_b"])
         if p["fused"]:
-            m2 = mod.view(R, p["mod_ld"])
-            ops.norm_weights(m2, p["norm_w"], self.depth, D, p["wn_off"])
-            # shift_s W^T with W the bf16 weights the main GEMMs use: A = (hi, lo) halves of the fp32 shift vectors
-            sh = cb["sh2"]
-            ops.split_bf16(m2, sh[:self.depth], col0=0, col_step=6 * D, nb=self.depth, cols=D)            # shift_1
-            ops.split_bf16(m2, sh[self.depth:], col0=3 * D, col_step=6 * D, nb=self.depth, cols=D)        # shift_2
-            taps = ((0, 0), (R, 0))
-            ops.gemm(sh[:self.depth], p["wqkv_all"], M=R, N=3 * D, K=D, batch=self.depth, a_rows=2 * R,
-                     a_batch_stride=2 * R * D, b_rows=3 * D, b_batch_stride=3 * D * D, taps=taps, out=cb["b2q"],
-                     out_batch_stride=R * 3 * D)
-            ops.gemm(sh[self.depth:], p["w13_all"], M=R, N=2 * F, K=D, batch=self.depth, a_rows=2 * R,
-                     a_batch_stride=2 * R * D, b_rows=2 * F, b_batch_stride=2 * F * D, taps=taps, out=cb["b2f"],
-                     out_batch_stride=R * 2 * F)
+            ops.norm_weights(mod.view(R, p["mod_ld"]), p["norm_w"], self.depth, D, p["wn_off"])
         return cb
 
     # ---------------------------------------------------------------- per-step work
@@ -428,11 +399,10 @@ class TxtFlagLargeDiT(nn.Module):
         """x [xB, C, T] fp32 (xB divides N: the CFG halves share x); cond = prepare_timesteps(...) and k the step index
         into it -> workspace with w.h filled.
 
-        Dense models run 5 launches per block: the RMSNorm + modulate between a gated-residual GEMM and the next
-        projection is folded into the two GEMMs (include/ma3_b200.h, ma3_gemm_t.norm_out / row_ss): the wo / w2
-        epilogue writes h_new, the next operand g = bf16(h_new * wn_s) and per-row partial sums of squares; the QKV / w1|w3
-        GEMM scales its accumulator rows by rstd and adds shift_s W^T.  Only the very first norm of a step (on the
-        proj_in output) is a stand-alone launch.  MoE models keep the 7(+8)-launch form."""
+        Fused models run 5 launches per block: QKV GEMM (+RoPE) -> attention -> wo -> w1|w3 GEMM (+SwiGLU) -> w2, where
+        wo and w2 are row-owning cluster GEMMs (ma3_gemm_rownorm) that update the fp32 residual stream in place and
+        write the RMS-normalised, adaLN-modulated 16-bit operand of the next projection.  Only the first norm of a step
+        (on the proj_in output) is a stand-alone launch.  MoE models and other widths keep the 7(+8)-launch form."""
         p = self._ensure()
         c = self._ctx
         N = c["shape"][0]
@@ -442,43 +412,41 @@ class TxtFlagLargeDiT(nn.Module):
         w = self._workspace(N, T)
         M = N * T
         mod = cond["mod"][k]
-        fused = p["fused"] and T >= 32      # a warp's 32 accumulator rows must lie in at most two samples
+        fused = p["fused"]
         qs = math.log2(math.e) / math.sqrt(hd)
         eps = self.norm_eps
         if T > p["rope"].shape[0]:
             raise ValueError(f"sequence length {T} exceeds the RoPE table ({p['rope'].shape[0]} positions)")
         ops.proj_in(x, p["proj_w"], p["proj_b"], w.h, N)
-        qkv_kw = dict(M=M, N=3 * D, K=D, epi=L.EPI_QKV_ROPE, q_out=w.q, k_out=w.k, vt_out=w.vt, rope=p["rope"],
-                      model_dim=D, head_dim=hd, head_dim_pad=w.hdp, tokens=T, tokens_pad=w.Tp, q_scale=qs)
         for i, q in enumerate(p["blocks"]):
             o = 6 * D * i
             gate1, gate2 = mod[:, o + 2 * D:o + 3 * D], mod[:, o + 5 * D:o + 6 * D]
-            if fused and i > 0:
-                # attention_norm of this block was folded into the previous block's w2 epilogue (w.g, w.ss)
-                ops.gemm(w.g, q["wqkv"], rows_per_sample=T, row_ss=w.ss, ss_dim=D, ss_eps=eps,
-                         col_bias2=cond["b2q"][i, k * N:(k + 1) * N], **qkv_kw)
-            else:
+            if not fused or i == 0:
                 ops.rmsnorm_modulate(w.h, q["attn_norm"], w.u, mod=mod, shift_off=o, scale_off=o + D, rows_per_sample=T,
                                      eps=eps)
-                ops.gemm(w.u, q["wqkv"], **qkv_kw)
+            ops.gemm(w.u, q["wqkv"], M=M, N=3 * D, K=D, epi=L.EPI_QKV_ROPE, q_out=w.q, k_out=w.k, vt_out=w.vt,
+                     rope=p["rope"], model_dim=D, head_dim=hd, head_dim_pad=w.hdp, tokens=T, tokens_pad=w.Tp, q_scale=qs)
             ops.attention(w.q, w.k, w.vt, c["ky"][i] if Lc else None, c["vyt"][i] if Lc else None, q["gate"], w.att,
                           hd=hd)
             if fused:
                 wn = p["wn_off"] + 2 * D * i
-                ops.gemm(w.att, q["wo"], M=M, N=D, K=D, epi=L.EPI_GATE_RES, out=w.h, gate=gate1, rows_per_sample=T,
-                         norm_out=w.g, norm_w=mod[:, wn + D:wn + 2 * D], ss_out=w.ss)            # -> ffn_norm
-                ops.gemm(w.g, q["w13"], M=M, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=w.mid, out_ld=F, rows_per_sample=T,
-                         row_ss=w.ss, ss_dim=D, ss_eps=eps, col_bias2=cond["b2f"][i, k * N:(k + 1) * N])
-                if i + 1 < self.depth:
-                    ops.gemm(w.mid, q["w2"], M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=w.h, gate=gate2, rows_per_sample=T,
-                             norm_out=w.g, norm_w=mod[:, wn + 2 * D:wn + 3 * D], ss_out=w.ss)    # -> next attention_norm
+                ops.gemm_rownorm(w.att, q["wo"], w.h, gate1, rows_per_sample=T, eps=eps, u_out=w.u,
+                                 wn=mod[:, wn + D:wn + 2 * D], shift=mod[:, o + 3 * D:o + 4 * D])            # -> ffn_norm
+                ops.gemm(w.u, q["w13"], M=M, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=w.mid, out_ld=F)
+                if i + 1 < self.depth:   # -> attention_norm of the next block
+                    ops.gemm_rownorm(w.mid, q["w2"], w.h, gate2, rows_per_sample=T, eps=eps, u_out=w.u,
+                                     wn=mod[:, wn + 2 * D:wn + 3 * D], shift=mod[:, o + 6 * D:o + 7 * D])
                 else:
-                    ops.gemm(w.mid, q["w2"], M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=w.h, gate=gate2, rows_per_sample=T)
+                    ops.gemm_rownorm(w.mid, q["w2"], w.h, gate2, rows_per_sample=T)
                 continue
             ops.gemm(w.att, q["wo"], M=M, N=D, K=D, epi=L.EPI_GATE_RES, out=w.h, gate=gate1, rows_per_sample=T)
             ops.rmsnorm_modulate(w.h, q["ffn_norm"], w.u, mod=mod, shift_off=o + 3 * D, scale_off=o + 4 * D,
                                  rows_per_sample=T, eps=eps)
-            self._moe_ffn(q, w, gate2, t_ints, N, T)
+            if self.num_experts:
+                self._moe_ffn(q, w, gate2, t_ints, N, T)
+            else:
+                ops.gemm(w.u, q["w13"], M=M, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=w.mid, out_ld=F)
+                ops.gemm(w.mid, q["w2"], M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=w.h, gate=gate2, rows_per_sample=T)
         return w
 
     def _moe_ffn(self, q, w, gate2, t_ints, N, T):

@@ -61,6 +61,7 @@ def declare(lib):
         "ma3_l2_persist": [vp, C.c_size_t, vp],
         "ma3_split_bf16": [vp, i64, i32, i32, i32, i32, i32, vp, vp],
         "ma3_norm_weights": [vp, i64, vp, i32, i32, i32, i32, vp],
+        "ma3_gemm_rownorm": [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, i32, vp, f32, vp],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -141,6 +142,24 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
     with _Span(f"tap_gemm/{_EPI_NAMES[epi]}/M{M} N{N} K{K} taps{len(taps)} batch{batch}", 2.0 * M * N * K * len(taps) * batch):
         L.check(lib.ma3_gemm(C.byref(d), L.stream_ptr()), "ma3_gemm")
     return out
+
+
+def gemm_rownorm(a, w, h, gate, *, rows_per_sample, wn=None, shift=None, u_out=None, eps=1e-5):
+    """h += gate_s * (a w^T) in place (fp32 [M, D]); with u_out: u_out = 16-bit(rms(h_new) * wn_s + shift_s).
+    gate / wn / shift: fp32 [samples, D] views sharing one row pitch.  See include/ma3_b200.h (ma3_gemm_rownorm)."""
+    M, K = a.shape
+    D = w.shape[0]
+    assert a.dtype == w.dtype and h.dtype == torch.float32 and h.is_contiguous() and h.shape == (M, D)
+    assert gate.dtype == torch.float32 and a.stride(1) == 1 and w.stride(1) == 1
+    ld = gate.stride(0)
+    if u_out is not None:
+        assert wn.stride(0) == ld and shift.stride(0) == ld and u_out.is_contiguous() and u_out.dtype == a.dtype
+    lib = L.require_device()
+    with _Span(f"tap_gemm/rownorm/M{M} N{D} K{K} taps1 batch1", 2.0 * M * D * K):
+        L.check(lib.ma3_gemm_rownorm(L.ptr(a), a.stride(0), L.ptr(w), w.stride(0), L.dt(a), M, K, D, L.ptr(h), L.ptr(gate),
+                                     L.ptr(wn), L.ptr(shift), ld, rows_per_sample, L.ptr(u_out), eps, L.stream_ptr()),
+                "ma3_gemm_rownorm")
+    return h
 
 
 _EPI_NAMES = {L.EPI_STORE: "store", L.EPI_GATE_RES: "gate_res", L.EPI_SWIGLU: "swiglu", L.EPI_QKV_ROPE: "qkv_rope"}

@@ -534,3 +534,31 @@ def test_split_bf16_strided_and_norm_weights(ops):
         x = mod[:, 6 * D * i + 3 * D: 6 * D * i + 4 * D]
         assert torch.equal(out[i, :R], x.bfloat16())
         assert rel(out[i, :R].float() + out[i, R:].float(), x) < 2e-5
+
+
+@pytest.mark.parametrize("samples,T,D,K", [(16, 312, 1152, 1152), (16, 312, 1152, 3072), (2, 312, 768, 2048),
+                                           (2, 936, 1536, 1536), (3, 40, 384, 64), (1, 100, 1152, 256), (2, 5, 768, 80)])
+def test_gemm_rownorm(ops, samples, T, D, K):
+    """Row-owning cluster GEMM: h += gate_s * (a w^T) in place, u = bf16(rms(h_new) * wn_s + shift_s); the row sums of
+    squares cross the cluster (D / 384 CTAs) through distributed shared memory.  Ragged M, sample boundaries inside a
+    row block, K not a multiple of 64."""
+    M = samples * T
+    a = torch.randn(M, K, generator=g(31)).bfloat16().cuda()
+    w = (torch.randn(D, K, generator=g(32)) / K ** 0.5).bfloat16().cuda()
+    h = (torch.randn(M, D, generator=g(33)) * 2).cuda()
+    mod = torch.randn(samples, 3 * D + 4, generator=g(34)).cuda()
+    gate, wn, shift = mod[:, :D], mod[:, D:2 * D], mod[:, 2 * D:3 * D]
+    rows = torch.arange(M, device="cuda") // T
+    h_ref = h.double() + gate[rows].double() * (a.double() @ w.double().t())
+    u_ref = h_ref * torch.rsqrt(h_ref.pow(2).mean(1, keepdim=True) + 1e-5) * wn[rows].double() + shift[rows].double()
+    hh = h.clone()
+    u = torch.full((M, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm_rownorm(a, w, hh, gate, rows_per_sample=T, wn=wn, shift=shift, u_out=u)
+    assert rel(hh, h_ref) < 2e-6
+    assert rel(u, u_ref) < 5e-3 and bool(torch.isfinite(u.float()).all())
+    h2, u2 = h.clone(), torch.empty_like(u)
+    ops.gemm_rownorm(a, w, h2, gate, rows_per_sample=T, wn=wn, shift=shift, u_out=u2)
+    assert torch.equal(h2, hh) and torch.equal(u2, u)            # no atomics: bit-reproducible
+    h3 = h.clone()
+    ops.gemm_rownorm(a, w, h3, gate, rows_per_sample=T)          # residual update only (last block)
+    assert torch.equal(h3, hh)
