@@ -554,7 +554,7 @@ def test_gemm_rownorm(ops, samples, T, D, K):
     hh = h.clone()
     u = torch.full((M, D), float("nan"), device="cuda", dtype=torch.bfloat16)
     ops.gemm_rownorm(a, w, hh, gate, rows_per_sample=T, wn=wn, shift=shift, u_out=u)
-    assert rel(hh, h_ref) < 2e-6
+    assert rel(hh, h_ref) < 1e-5      # fp32 accumulation over K vs float64
     assert rel(u, u_ref) < 5e-3 and bool(torch.isfinite(u.float()).all())
     h2, u2 = h.clone(), torch.empty_like(u)
     ops.gemm_rownorm(a, w, h2, gate, rows_per_sample=T, wn=wn, shift=shift, u_out=u2)
