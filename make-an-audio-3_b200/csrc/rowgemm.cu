@@ -21,6 +21,8 @@
 #include "host_common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace ma3 {
 
 constexpr int kRgThreads = 320;
@@ -46,7 +48,13 @@ struct RowGemmParams {
   void* u_out;              // [M][D] 16-bit, or nullptr: residual update only
   int bf16;
   uint32_t idesc256, idesc128;
+  int dbg;                  // diagnostics (MA3_RG_DBG): 1 no h stores, 2 no h_old loads, 4 no row sums; results are garbage
+  long long* trace;         // diagnostics (ma3_debug_set_gemm_trace): CTA 0 records clock64() at its phase boundaries
 };
+
+__device__ __forceinline__ void rg_trace(const RowGemmParams& p, int slot) {
+  if (p.trace && blockIdx.x == 0) p.trace[slot] = clock64();
+}
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {
   uint32_t r;
@@ -97,12 +105,21 @@ __global__ void __launch_bounds__(kRgThreads, 1) rowgemm_norm_kernel(const __gri
   float* rs_all = reinterpret_cast<float*>(bars + 16);   // [cluster rank][128]: per-row sums of squares of every CTA's slice
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank(), csize = cluster_nctarank();
+  const uint32_t csize = (uint32_t)(p.D / kRgCN);
+  const bool no_cluster = (p.dbg & 16) != 0;   // diagnostics: launched without a cluster (row sums stay CTA-local: wrong)
+  const uint32_t rank = no_cluster ? blockIdx.x % csize : cluster_ctarank();
   const int m0 = (int)(blockIdx.x / csize) * kRgBM;
   const int n0 = (int)rank * kRgCN;
   const int kchunks = (p.K + kRgBK - 1) / kRgBK;
   const bool norm = p.u_out != nullptr;
 
+  if (threadIdx.x == 0) rg_trace(p, 0);
+  if (p.trace && threadIdx.x == 0) {   // launch span over all CTAs (ns): first entry [32], last exit [33]; CTA 0: [34], [35]
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(reinterpret_cast<unsigned long long*>(p.trace) + 32, t);
+    if (blockIdx.x == 0) p.trace[34] = (long long)t;
+  }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
@@ -121,10 +138,19 @@ __global__ void __launch_bounds__(kRgThreads, 1) rowgemm_norm_kernel(const __gri
   }
   pdl_launch_dependents();
   tc_fence_before();
-  cluster_sync_all();   // every CTA of the cluster is running (its shared memory may be written remotely from here on)
+  __syncwarp();
+  if (no_cluster) __syncthreads();
+  else cluster_sync_all();   // every CTA of the cluster is running (its shared memory may be written remotely from here on)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef RG_CHECK_TMEM
+  if (tmem_base != 0) {
+    if (lane == 0) printf("rowgemm: block %d warp %d tmem_base %08x\n", blockIdx.x, warp, tmem_base);
+    __trap();
+  }
+#endif
   pdl_wait();
+  if (threadIdx.x == 0) rg_trace(p, 1);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -149,38 +175,65 @@ __global__ void __launch_bounds__(kRgThreads, 1) rowgemm_norm_kernel(const __gri
       const uint64_t desc0 = umma_desc_kmajor(smem_u32(base), 128);
       const uint32_t desc_hi = (uint32_t)(desc0 >> 32), lo0 = (uint32_t)desc0;
       const uint32_t full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
-      const uint32_t stage16 = kRgStageBytes >> 4, a16 = kRgABytes >> 4, b1_16 = (256 * 128) >> 4;
-      const uint32_t id256 = p.idesc256, id128 = p.idesc128;
+      const uint32_t stage16 = kRgStageBytes >> 4, a16 = kRgABytes >> 4, b1_16 = (192 * 128) >> 4;
+      const uint32_t id192 = p.idesc256;   // two symmetric N = 192 MMAs per k-step: one per TMA box of B
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < kchunks; ++i) {
         while (!mbar_try_wait(full_u32 + 8 * s, ph)) {
         }
+        if (i == 0) rg_trace(p, 2);
+        if (i == kchunks / 2) rg_trace(p, 3);
         tc_fence_after();
         const uint32_t alo = lo0 + (uint32_t)s * stage16, blo = alo + a16;
+        // first the four K = 16 steps of slice columns 0..191, then the four of columns 192..383 (TMEM 256..447)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t acc = (i | k) != 0 ? 1u : 0u;
-          umma_f16_lohi<1>(tmem_base, alo + 2 * k, blo + 2 * k, desc_hi, id256, acc);                   // columns 0..255
-          umma_f16_lohi<1>(tmem_base + 256, alo + 2 * k, blo + b1_16 + 2 * k, desc_hi, id128, acc);     // columns 256..383
-        }
+        for (int k = 0; k < 4; ++k)
+          if (!(p.dbg & 128)) umma_f16_lohi<1>(tmem_base, alo + 2 * k, blo + 2 * k, desc_hi, id192, (i | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (!(p.dbg & 32))
+            umma_f16_lohi<1>(tmem_base + 256, alo + 2 * k, blo + b1_16 + 2 * k, desc_hi, id192, (i | k) != 0 ? 1u : 0u);
         umma_commit_u32<1>(empty_u32 + 8 * s);
         if (++s == kRgStages) { s = 0; ph ^= 1; }
       }
       umma_commit(tfull);
     }
   } else {
-    const int ew = warp - 2;
+    const int ew = warp - 2, r0 = ew * 16;
+    // Everything this warp needs from global memory is requested as early as the registers allow: the first four rows
+    // of h_old and the gate vector while the mainloop still runs, then row batches double-buffered against the
+    // processing of the previous batch -- the phase is bound by how many bytes are in flight, not by instructions.
+    auto load_rows = [&](int rb, float4(&ho)[4][3]) {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int m = m0 + r0 + rb + rr;
+        if (m < p.M && !(p.dbg & 2)) {
+          const float* hp = p.h + (long long)m * p.D + n0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ho[rr][i] = *reinterpret_cast<const float4*>(hp + 4 * (lane + 32 * i));
+        }
+      }
+    };
+    float4 hoA[4][3], hoB[4][3];
+    RgVec gate;
+    const int m_first = m0 + r0 < p.M ? m0 + r0 : p.M - 1;
+    int cur_s = rg_div(m_first, p.inv_rps);
+    load_rows(0, hoA);
+    rg_load_vec(p.gate, (long long)cur_s * p.mod_ld, n0, lane, gate);
+
     // ---- phase A: accumulator (thread <-> row) -> fp32 tile in shared memory (the operand stages are dead by now)
     {
       const int q = warp & 3, hf = ew >> 2;
       mbar_wait(tfull, 0);
+      if (ew == 0 && lane == 0) rg_trace(p, 4);
       tc_fence_after();
+      if (p.dbg & 64) goto done;   // diagnostics: mainloop only
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
       float* trow = tile + (q * 32 + lane) * kRgPitch;
       for (int c = hf; c < kRgCN / 32; c += 2) {
         uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
+        tmem_ld32(taddr + (c < 6 ? c * 32 : 256 + (c - 6) * 32), r);   // slice columns 192.. live at TMEM column 256..
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; e += 4)
@@ -190,27 +243,16 @@ __global__ void __launch_bounds__(kRgThreads, 1) rowgemm_norm_kernel(const __gri
       tc_fence_before();
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps: the tile is complete
+    if (ew == 0 && lane == 0) rg_trace(p, 5);
 
-    // ---- phase B: rows ew*16 .. ew*16+15, lanes along columns (3 float4 per lane): h_new = h + gate * acc
-    const int r0 = ew * 16;
-    int cur_s = -1;
-    RgVec gate;
+    // ---- phase B: rows r0 .. r0+15, lanes along columns (3 float4 per lane): h_new = h + gate * acc
     float my_ss = 0.f;
-    for (int rb = 0; rb < 16; rb += 4) {
-      float4 ho[4][3];
-#pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int m = m0 + r0 + rb + rr;
-        if (m < p.M) {
-          const float* hp = p.h + (long long)m * p.D + n0;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) ho[rr][i] = *reinterpret_cast<const float4*>(hp + 4 * (lane + 32 * i));
-        }
-      }
+    auto process = [&](int rb, float4(&ho)[4][3]) {
+      float ssr[4];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
         const int r = r0 + rb + rr, m = m0 + r;
-        float ss = 0.f;
+        ssr[rr] = 0.f;
         if (m < p.M) {   // warp-uniform
           const int s = rg_div(m, p.inv_rps);
           if (s != cur_s) {
@@ -219,6 +261,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) rowgemm_norm_kernel(const __gri
           }
           float* tp = tile + r * kRgPitch;
           float* hp = p.h + (long long)m * p.D + n0;
+          float part[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int c = 4 * (lane + 32 * i);
@@ -226,65 +269,120 @@ __global__ void __launch_bounds__(kRgThreads, 1) rowgemm_norm_kernel(const __gri
             float4 hn;
             hn.x = fmaf(gate.v[i].x, a.x, ho[rr][i].x); hn.y = fmaf(gate.v[i].y, a.y, ho[rr][i].y);
             hn.z = fmaf(gate.v[i].z, a.z, ho[rr][i].z); hn.w = fmaf(gate.v[i].w, a.w, ho[rr][i].w);
-            *reinterpret_cast<float4*>(hp + c) = hn;
+            if (!(p.dbg & 1)) *reinterpret_cast<float4*>(hp + c) = hn;
             if (norm) rg_sts4(tp + c, hn);
-            ss = fmaf(hn.x, hn.x, fmaf(hn.y, hn.y, fmaf(hn.z, hn.z, fmaf(hn.w, hn.w, ss))));
+            part[i] = fmaf(hn.x, hn.x, hn.y * hn.y) + fmaf(hn.z, hn.z, hn.w * hn.w);
           }
+          ssr[rr] = part[0] + part[1] + part[2];
         }
-        ss = rg_warp_sum(ss);
-        if (lane == rb + rr) my_ss = ss;
       }
-    }
-    if (norm && lane < 16) {
-      // this CTA's partial row sums go to slot [rank] of EVERY CTA of the cluster (distributed shared memory)
-      const uint32_t slot = smem_u32(rs_all + rank * kRgBM + r0 + lane);
-      for (uint32_t k = 0; k < csize; ++k) st_cluster_f32(mapa_u32(slot, k), my_ss);
-    }
-  }
+      // four row sums across the warp in 6 shuffles (transposing butterfly) instead of 4 x 5: after the xor-16 and
+      // xor-8 steps every lane carries ONE row (row = 2 * bit4 + bit3 of the lane), three more steps finish it
+#ifdef RG_OLD_SUM
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const float t = rg_warp_sum(ssr[rr]);
+        if (lane == rb + rr) my_ss = t;
+      }
+      return;
+#endif
+      const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+      float x0 = hi16 ? ssr[2] : ssr[0], y0 = hi16 ? ssr[0] : ssr[2];
+      float x1 = hi16 ? ssr[3] : ssr[1], y1 = hi16 ? ssr[1] : ssr[3];
+      x0 += __shfl_xor_sync(0xffffffffu, y0, 16);
+      x1 += __shfl_xor_sync(0xffffffffu, y1, 16);
+      float x = hi8 ? x1 : x0;
+      const float y = hi8 ? x0 : x1;
+      x += __shfl_xor_sync(0xffffffffu, y, 8);
+      x += __shfl_xor_sync(0xffffffffu, x, 4);
+      x += __shfl_xor_sync(0xffffffffu, x, 2);
+      x += __shfl_xor_sync(0xffffffffu, x, 1);
+      // row rr of the batch now sits in lanes with (bit4, bit3) = (rr >> 1, rr & 1); lane rb + rr keeps it
+      const float t = __shfl_sync(0xffffffffu, x, ((lane & 2) << 3) | ((lane & 1) << 3));
+      if ((lane >> 2) == (rb >> 2) && lane < 16) my_ss = t;
+    };
+    load_rows(4, hoB);
+    process(0, hoA);
+    load_rows(8, hoA);
+    process(4, hoB);
+    load_rows(12, hoB);
+    process(8, hoA);
+    process(12, hoB);
+    if (ew == 0 && lane == 0) rg_trace(p, 6);
 
-  if (norm) {
-    cluster_sync_all();   // release / acquire: every CTA's partial sums are visible in every CTA's rs_all
-    if (warp >= 2) {
+    if (norm) {
+      // the modulation vectors of phase C are requested before the cluster-wide wait
+      RgVec wn, sh;
+      int cs = rg_div(m_first, p.inv_rps);
+      rg_load_vec(p.wn, (long long)cs * p.mod_ld, n0, lane, wn);
+      rg_load_vec(p.shift, (long long)cs * p.mod_ld, n0, lane, sh);
+      if (lane < 16) {
+        // this CTA's partial row sums go to slot [rank] of EVERY CTA of the cluster (distributed shared memory)
+        const uint32_t slot = smem_u32(rs_all + rank * kRgBM + r0 + lane);
+        if (!(p.dbg & 24))
+          for (uint32_t k = 0; k < csize; ++k) st_cluster_f32(mapa_u32(slot, k), my_ss);
+      }
+      __syncwarp();
+      if (!(p.dbg & 24)) cluster_sync_all();   // release / acquire: every CTA's partial sums are visible in every CTA's rs_all
+      if (ew == 0 && lane == 0) rg_trace(p, 7);
       // ---- phase C: u = h_new * rstd * wn_s + shift_s for the same rows (h_new is still in this warp's tile rows)
-      const int ew = warp - 2, r0 = ew * 16;
       float rstd = 0.f;
       if (lane < 16) {
         float tot = 0.f;
         for (uint32_t k = 0; k < csize; ++k) tot += rs_all[k * kRgBM + r0 + lane];   // rank order: same sum in every CTA
         rstd = rsqrtf(tot * p.inv_D + p.eps);
       }
-      int cur_s = -1;
-      RgVec wn, sh;
       uint16_t* ub = reinterpret_cast<uint16_t*>(p.u_out);
-      for (int rr = 0; rr < 16; ++rr) {
-        const int r = r0 + rr, m = m0 + r;
-        const float rs = __shfl_sync(0xffffffffu, rstd, rr);
-        if (m >= p.M) break;   // warp-uniform
-        const int s = rg_div(m, p.inv_rps);
-        if (s != cur_s) {
-          rg_load_vec(p.wn, (long long)s * p.mod_ld, n0, lane, wn);
-          rg_load_vec(p.shift, (long long)s * p.mod_ld, n0, lane, sh);
-          cur_s = s;
-        }
-        const float* tp = tile + r * kRgPitch;
-        uint16_t* up = ub + (long long)m * p.D + n0;
+      for (int rb = 0; rb < 16; rb += 4) {
+        float4 hn[4][3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int c = 4 * (lane + 32 * i);
-          const float4 hn = rg_lds4(tp + c);
-          const float v0 = fmaf(hn.x * rs, wn.v[i].x, sh.v[i].x), v1 = fmaf(hn.y * rs, wn.v[i].y, sh.v[i].y);
-          const float v2 = fmaf(hn.z * rs, wn.v[i].z, sh.v[i].z), v3 = fmaf(hn.w * rs, wn.v[i].w, sh.v[i].w);
-          uint2 u;
-          if (p.bf16) { u.x = pack_bf16(v0, v1); u.y = pack_bf16(v2, v3); }
-          else { u.x = pack_f16(v0, v1); u.y = pack_f16(v2, v3); }
-          *reinterpret_cast<uint2*>(up + c) = u;
+        for (int rr = 0; rr < 4; ++rr) {
+          const float* tp = tile + (r0 + rb + rr) * kRgPitch;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) hn[rr][i] = rg_lds4(tp + 4 * (lane + 32 * i));
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int m = m0 + r0 + rb + rr;
+          const float rs = __shfl_sync(0xffffffffu, rstd, rb + rr);
+          if (m < p.M) {   // warp-uniform
+            const int s = rg_div(m, p.inv_rps);
+            if (s != cs) {
+              rg_load_vec(p.wn, (long long)s * p.mod_ld, n0, lane, wn);
+              rg_load_vec(p.shift, (long long)s * p.mod_ld, n0, lane, sh);
+              cs = s;
+            }
+            uint16_t* up = ub + (long long)m * p.D + n0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const float4 v = hn[rr][i];
+              const float v0 = fmaf(v.x * rs, wn.v[i].x, sh.v[i].x), v1 = fmaf(v.y * rs, wn.v[i].y, sh.v[i].y);
+              const float v2 = fmaf(v.z * rs, wn.v[i].z, sh.v[i].z), v3 = fmaf(v.w * rs, wn.v[i].w, sh.v[i].w);
+              uint2 u;
+              if (p.bf16) { u.x = pack_bf16(v0, v1); u.y = pack_bf16(v2, v3); }
+              else { u.x = pack_f16(v0, v1); u.y = pack_f16(v2, v3); }
+              *reinterpret_cast<uint2*>(up + 4 * (lane + 32 * i)) = u;
+            }
+          }
         }
       }
     }
   }
+done:
+  if (warp < 2 && norm && !(p.dbg & 24)) {   // the producer / MMA warps take part in the cluster-wide barrier
+    __syncwarp();                            // (.aligned: the elected lane has to have rejoined its warp)
+    cluster_sync_all();
+  }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) rg_trace(p, 8);
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(reinterpret_cast<unsigned long long*>(p.trace) + 33, t);
+    if (blockIdx.x == 0) p.trace[35] = (long long)t;
+  }
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, 512);
@@ -314,8 +412,13 @@ extern "C" int ma3_gemm_rownorm(const void* a, int64_t a_ld, const void* w, int6
   p.M = M; p.K = K; p.D = D; p.h = h; p.gate = gate; p.wn = wn; p.shift = shift; p.mod_ld = mod_ld;
   p.rows_per_sample = rows_per_sample; p.inv_rps = 1.0f / (float)rows_per_sample; p.inv_D = 1.0f / (float)D; p.eps = eps;
   p.u_out = u_out; p.bf16 = dtype == MA3_BF16 ? 1 : 0;
-  p.idesc256 = umma_idesc(kRgBM, 256, p.bf16);
-  p.idesc128 = umma_idesc(kRgBM, 128, p.bf16);
+  p.idesc256 = umma_idesc(kRgBM, 192, p.bf16);
+  p.idesc128 = 0;
+  p.trace = g_trace;
+  {
+    static const int dbg = getenv("MA3_RG_DBG") ? atoi(getenv("MA3_RG_DBG")) : 0;
+    p.dbg = dbg;
+  }
   int rc;
   {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, 1};
@@ -338,7 +441,7 @@ extern "C" int ma3_gemm_rownorm(const void* a, int64_t a_ld, const void* w, int6
   const int csize = D / kRgCN;
   const int grid = ((M + kRgBM - 1) / kRgBM) * csize;
   cudaError_t e = launch_pdl(rowgemm_norm_kernel, dim3((unsigned)grid), dim3(kRgThreads), kRgSmem,
-                             reinterpret_cast<cudaStream_t>(stream), csize, p);
+                             reinterpret_cast<cudaStream_t>(stream), (p.dbg & 16) ? 1 : csize, p);
   if (e != cudaSuccess) MA3_FAIL((int)e, "gemm_rownorm launch: %s", cudaGetErrorString(e));
   MA3_LAUNCH_CHECK("gemm_rownorm");
   return 0;
