@@ -102,6 +102,9 @@ class _Final(nn.Module):
         self.adaLN_modulation = _Seq(_1=_Lin(dim, 2 * dim))
 
 
+_ROWNORM_MIN_CTAS = 100
+
+
 class _Work:
     """Device buffers for one (N, T, L) problem size."""
     pass
@@ -412,7 +415,10 @@ class TxtFlagLargeDiT(nn.Module):
         w = self._workspace(N, T)
         M = N * T
         mod = cond["mod"][k]
-        fused = p["fused"]
+        # the row-owning GEMM is ONE wave of ceil(M / 128) * D / 384 CTAs with an exposed epilogue: it pays when that wave
+        # fills most of the GPU (XL x 8 prompts: 117 of 148 SMs); small batches keep the tiled GEMM + stand-alone norm
+        n_cta = (M + 127) // 128 * (D // 384) if p["fused"] else 0
+        fused = p["fused"] and (_ROWNORM_MIN_CTAS <= n_cta <= ops.sm_count() or os.environ.get("MA3_ROWNORM") == "force")
         qs = math.log2(math.e) / math.sqrt(hd)
         eps = self.norm_eps
         if T > p["rope"].shape[0]:

@@ -133,6 +133,16 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
     return out
 
 
+_SM_COUNT = {}
+
+
+def sm_count():
+    dev = torch.cuda.current_device()
+    if dev not in _SM_COUNT:
+        _SM_COUNT[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _SM_COUNT[dev]
+
+
 def gemm_rownorm(a, w, h, gate, *, rows_per_sample, wn=None, shift=None, u_out=None, eps=1e-5):
     """h += gate_s * (a w^T) in place (fp32 [M, D]); with u_out: u_out = 16-bit(rms(h_new) * wn_s + shift_s).
     gate / wn / shift: fp32 [samples, D] views sharing one row pitch.  See include/ma3_b200.h (ma3_gemm_rownorm)."""

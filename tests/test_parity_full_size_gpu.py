@@ -77,6 +77,24 @@ def test_xl_full_depth_24_steps_and_bench_batch():
     worst, cos, (cfg, ne, sd, m, s), (c, uc, x0, zr, traj_r) = _per_step_parity("XL", 312, 154, 25)
     print(f"XL depth 28: worst per-step velocity rel err {worst:.4f}, final latent cosine {cos:.6f}")
     assert cos >= COS_TOL
+    # the same gate through the row-owning wo / w2 GEMMs (ma3_gemm_rownorm), which a one-prompt batch would not pick
+    import os
+    os.environ["MA3_ROWNORM"] = "force"
+    try:
+        ints, _ = O.timestep_ints(25)
+        ctx = torch.cat([uc, c])
+        vel = _oracle_velocity(sd, cfg, ne)
+        for k in (0, 7, 23):
+            t = torch.full((2,), ints[k], dtype=torch.long, device="cuda")
+            xk = traj_r[k]
+            with torch.no_grad():
+                ref = vel(torch.cat([xk, xk]), t, ctx)
+            out = m(torch.cat([xk, xk]), t, context=ctx)
+            err = O.max_rel_err((out[:1] + 3.0 * (out[1:] - out[:1])).cpu(), (ref[:1] + 3.0 * (ref[1:] - ref[:1])).cpu())
+            print(f"XL depth 28, row-owning GEMM path, step {k}: velocity rel err {err:.4f}")
+            assert err <= VEL_TOL
+    finally:
+        os.environ.pop("MA3_ROWNORM", None)
     g = Cs.gen(501)
     B = 8
     cond = torch.randn(B, 154, 1024, generator=g).cuda()
