@@ -55,6 +55,18 @@ class Txt2AudioPipeline:
         return self.sampler.sample_cfg(cond, unconditional_guidance_scale, unconditional_conditioning, batch_size,
                                        timesteps, shape, x_latent, t_start)
 
+    @property
+    def device(self):
+        return self.dit.proj_in.weight.device
+
+    def get_learned_conditioning(self, c):
+        """Identity conditioner for precomputed embeddings (ddpm_audio.py:343-356 calls cond_stage_model here; the
+        CLAP / T5 encoders are SURVEY.md section 8(f) rank 1 and stay with the caller)."""
+        if not torch.is_tensor(c):
+            raise TypeError("Txt2AudioPipeline takes precomputed embeddings [B, L, context_dim]; text / video "
+                            "conditioners are not part of this package")
+        return c.to(self.device, torch.float32)
+
     @torch.no_grad()
     def decode_first_stage(self, z):
         """ddpm_audio.py:358-371: z / scale_factor -> first_stage_model.decode."""
