@@ -73,6 +73,34 @@ class Txt2AudioPipeline:
         return self.first_stage_model.decode((1.0 / self.scale_factor) * z)
 
     @torch.no_grad()
+    def encode_first_stage(self, x):
+        """ddpm_audio.py:372-374: mel [B, 80, 2T] -> posterior over the latent (VAE Encoder1D on the GPU)."""
+        return self.first_stage_model.encode(x)
+
+    def get_first_stage_encoding(self, encoder_posterior, sample=True):
+        """ddpm.py get_first_stage_encoding: scale_factor * (posterior sample | tensor)."""
+        z = encoder_posterior
+        if hasattr(encoder_posterior, "sample"):
+            z = encoder_posterior.sample() if sample else encoder_posterior.mode()
+        return self.scale_factor * z
+
+    @torch.no_grad()
+    def generate_windows(self, conds, unconds, scale=3.0, timesteps=25, length=None, x0=None):
+        """Long-form generation over independent windows (scripts/video2audio_flow.py:483-523: 40-frame video windows,
+        one sample_cfg + decode_first_stage per window, mels concatenated along time, then ONE vocoder pass).  The
+        reference runs the windows one after the other at batch 1; they are independent, so here they are one batch.
+        conds / unconds: [W, L, Cd] (window-major); length: latent frames per window (default mel_length; callers that
+        stretch a window overwrite dit.freqs_cis for NTK scaling first, as the reference script does)."""
+        Wn = conds.shape[0]
+        T = length or self.mel_length
+        if x0 is None:
+            x0 = torch.randn(Wn, self.mel_dim, T, device=self.device)
+        z, _ = self.sample_cfg(conds, scale, unconds, Wn, timesteps=timesteps, x_latent=x0)
+        mel = self.decode_first_stage(z)                                  # [W, 80, 2T]
+        mel = mel.permute(1, 0, 2).reshape(1, mel.shape[1], -1)            # np.concatenate(mel_list, 1) of the script
+        return self.vocoder.vocode_tensor(mel.contiguous()), mel
+
+    @torch.no_grad()
     def generate(self, cond, uncond, x0, scale=3.0, timesteps=25):
         """cond/uncond [B, L, Cd], x0 [B, 20, T] (device tensors) -> waveforms [B, 2T*hop] on the device."""
         B = x0.shape[0]

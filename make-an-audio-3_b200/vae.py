@@ -1,10 +1,11 @@
-"""Drop-in first-stage model: the decode() half of ldm/models/autoencoder1d.py:18-62 (AutoencoderKL with the 1-D
-Decoder1D, autoencoder1d.py:415-517).
+"""Drop-in first-stage model: ldm/models/autoencoder1d.py:18-62 (AutoencoderKL) with the 1-D Decoder1D
+(autoencoder1d.py:415-517) on the sampling path and the Encoder1D (autoencoder1d.py:319-413) for the inpainting /
+ground-truth paths.
 
-Same constructor arguments and state_dict keys (`post_quant_conv.*`, `decoder.*`; encoder / loss keys of a full
-checkpoint are ignored -- the encoder is not on the sampling path).  decode() runs channels-last in bf16 on the
-tap-GEMM (implicit-GEMM conv1d on tcgen05) with GroupNorm+swish as the only separate elementwise pass; the residual
-stream is kept in fp32.
+Same constructor arguments and state_dict keys (`encoder.*`, `quant_conv.*`, `post_quant_conv.*`, `decoder.*`; loss
+keys of a full checkpoint are ignored; a decoder-only state_dict is accepted and leaves encode() disabled).  Both
+halves run channels-last in bf16 on the tap-GEMM (implicit-GEMM conv1d on tcgen05) with GroupNorm+swish as the only
+separate elementwise pass; the residual stream is kept in fp32.
 """
 import torch
 import torch.nn as nn
@@ -30,10 +31,10 @@ class _GN(nn.Module):
 
 
 class _Res(nn.Module):
-    def __init__(self, cin, cout):
+    def __init__(self, cin, cout, k=3):
         super().__init__()
-        self.norm1, self.conv1 = _GN(cin), _Conv(cin, cout, 3)
-        self.norm2, self.conv2 = _GN(cout), _Conv(cout, cout, 3)
+        self.norm1, self.conv1 = _GN(cin), _Conv(cin, cout, k)
+        self.norm2, self.conv2 = _GN(cout), _Conv(cout, cout, k)
         if cin != cout:
             self.nin_shortcut = _Conv(cin, cout, 1)
 
@@ -82,16 +83,90 @@ class Decoder1D(nn.Module):
         self.conv_out = _Conv(block_in, out_ch, kernel_size)
 
 
+class Encoder1D(nn.Module):
+    """Parameter tree of autoencoder1d.py:319-381 (here the ResNet blocks DO take `kernel_size`, unlike the decoder)."""
+
+    def __init__(self, *, ch, out_ch=None, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_layers=[], down_layers=[],
+                 dropout=0.0, resamp_with_conv=True, in_channels, z_channels, double_z=True, kernel_size=3,
+                 **ignore_kwargs):
+        super().__init__()
+        if not resamp_with_conv:
+            raise NotImplementedError("resamp_with_conv=False is not used by any shipped config")
+        self.ch, self.ch_mult, self.num_res_blocks = ch, list(ch_mult), num_res_blocks
+        self.kernel_size, self.in_channels = kernel_size, in_channels
+        self.down_layers, self.attn_layers = list(down_layers), list(attn_layers)
+        self.conv_in = _Conv(in_channels, ch, kernel_size)
+        self.down = nn.ModuleList()
+        block_in = ch
+        for lvl in range(len(self.ch_mult)):
+            block_out = ch * self.ch_mult[lvl]
+            down = nn.Module()
+            down.block, down.attn = nn.ModuleList(), nn.ModuleList()
+            for _ in range(num_res_blocks):
+                down.block.append(_Res(block_in, block_out, kernel_size))
+                block_in = block_out
+                if lvl in self.attn_layers:
+                    down.attn.append(_Attn(block_in))
+            if lvl in self.down_layers:
+                down.downsample = nn.Module()
+                down.downsample.conv = _Conv(block_in, block_in, 3)
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = _Res(block_in, block_in, kernel_size)
+        self.mid.attn_1 = _Attn(block_in)
+        self.mid.block_2 = _Res(block_in, block_in, kernel_size)
+        self.norm_out = _GN(block_in)
+        self.conv_out = _Conv(block_in, 2 * z_channels if double_z else z_channels, kernel_size)
+
+
+class DiagonalGaussianDistribution:
+    """ldm/modules/distributions/distributions.py:24-77: the posterior returned by encode() (tiny tensors: plain torch)."""
+
+    def __init__(self, parameters, deterministic=False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self):
+        return self.mean + self.std * torch.randn(self.mean.shape, device=self.parameters.device)
+
+    def mode(self):
+        return self.mean
+
+    def kl(self, other=None):
+        if self.deterministic:
+            return torch.Tensor([0.0])
+        dims = list(range(1, self.mean.dim()))
+        if other is None:
+            return 0.5 * torch.sum(self.mean.pow(2) + self.var - 1.0 - self.logvar, dim=dims)
+        return 0.5 * torch.sum((self.mean - other.mean).pow(2) / other.var + self.var / other.var - 1.0 - self.logvar
+                               + other.logvar, dim=dims)
+
+    def nll(self, sample, dims=[1, 2, 3]):
+        if self.deterministic:
+            return torch.Tensor([0.0])
+        import math
+        return 0.5 * torch.sum(math.log(2.0 * math.pi) + self.logvar + (sample - self.mean).pow(2) / self.var, dim=dims)
+
+
 class AutoencoderKL(nn.Module):
-    """B200 drop-in for ldm.models.autoencoder1d.AutoencoderKL (decode side)."""
+    """B200 drop-in for ldm.models.autoencoder1d.AutoencoderKL."""
 
     def __init__(self, embed_dim, ddconfig, lossconfig=None, ckpt_path=None, ignore_keys=[], image_key="image",
                  monitor=None):
         super().__init__()
         assert ddconfig["double_z"]
         self.image_key, self.embed_dim = image_key, embed_dim
+        self.encoder = Encoder1D(**ddconfig)
         self.decoder = Decoder1D(**ddconfig)
+        self.quant_conv = _Conv(2 * ddconfig["z_channels"], 2 * embed_dim, 1)
         self.post_quant_conv = _Conv(embed_dim, ddconfig["z_channels"], 1)
+        self._has_encoder = True
         if monitor is not None:
             self.monitor = monitor
         self._packed = None
@@ -114,8 +189,19 @@ class AutoencoderKL(nn.Module):
                 del sd[k]
         self.load_state_dict(sd, strict=False)
 
-    def encode(self, x):
-        raise NotImplementedError("the VAE encoder is outside the sampling path (SURVEY.md section 2, row 5)")
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """As nn.Module.load_state_dict; a state_dict without `encoder.*` / `quant_conv.*` (the sampling path only needs
+        the decoder) is accepted under strict=True and disables encode(); `loss.*` keys of a full checkpoint are ignored."""
+        sd = {k: v for k, v in state_dict.items() if not k.startswith("loss.")}
+        r = super().load_state_dict(sd, strict=False, **kw)
+        enc_missing = [k for k in r.missing_keys if k.startswith(("encoder.", "quant_conv."))]
+        other_missing = [k for k in r.missing_keys if k not in enc_missing]
+        self._has_encoder = not enc_missing
+        if enc_missing:
+            r.missing_keys[:] = other_missing
+        if strict and (other_missing or r.unexpected_keys):
+            raise RuntimeError(f"AutoencoderKL.load_state_dict: missing {other_missing}, unexpected {r.unexpected_keys}")
+        return r
 
     # ---------------------------------------------------------------- packing
     def _pack(self):
@@ -151,6 +237,25 @@ class AutoencoderKL(nn.Module):
             p["up"].append(e)
         p["nout"] = gn(d.norm_out)
         p["cout"] = pc(d.conv_out, padding=ks // 2)
+        if self._has_encoder:
+            e = self.encoder
+            q = {"cin": pc(e.conv_in), "down": [], "mid1": res(e.mid.block_1), "mida": attn(e.mid.attn_1),
+                 "mid2": res(e.mid.block_2), "nout": gn(e.norm_out), "cout": pc(e.conv_out), "qc": pc(self.quant_conv)}
+            for lvl in range(len(e.ch_mult)):
+                dn = e.down[lvl]
+                ent = {"blocks": [res(b) for b in dn.block], "attn": [attn(a) for a in dn.attn]}
+                if hasattr(dn, "downsample"):
+                    # Downsample1D (autoencoder1d.py:296-317): zero-pad one frame on the right, conv k3 stride 2.  On the
+                    # frame-PAIR view [B, T/2, 2C] of the input it is a two-tap GEMM:
+                    #   out[t] = [W0 | W1] . pair[t] + [W2 | 0] . pair[t+1]     (pair[T/2] = 0 by TMA zero fill)
+                    wt = dn.downsample.conv.weight.detach().float()           # [C, C, 3]
+                    C = wt.shape[0]
+                    wp = torch.zeros(2 * C, 2 * C)
+                    wp[:C, :C], wp[:C, C:], wp[C:, :C] = wt[:, :, 0], wt[:, :, 1], wt[:, :, 2]
+                    ent["down_w"] = wp.to(device=dev, dtype=bf).contiguous()
+                    ent["down_b"] = f32(dn.downsample.conv.bias)
+                q["down"].append(ent)
+            p["enc"] = q
         self._packed = p
 
     def _buf(self, name, shape, dtype, zero=False):
@@ -237,5 +342,50 @@ class AutoencoderKL(nn.Module):
         out = torch.empty(B, d.out_ch, T, device=dev, dtype=torch.float32)
         return ops.ntc_to_nct(y, out)
 
+    @torch.no_grad()
+    def encode(self, x):
+        """x fp32 [B, in_channels, T] -> DiagonalGaussianDistribution over [B, embed_dim, T / 2^len(down_layers)]
+        (autoencoder1d.py:49-53, 383-413)."""
+        if not self._has_encoder:
+            raise L.Ma3Error("this AutoencoderKL was loaded from a decoder-only state_dict: encode() needs encoder.* / quant_conv.*")
+        if self._packed is None:
+            self._pack()
+        q, e = self._packed["enc"], self.encoder
+        dev = self.post_quant_conv.weight.device
+        x = x.to(device=dev, dtype=torch.float32).contiguous()
+        B, _, T = x.shape
+        bf = torch.bfloat16
+        xin = ops.nct_to_ntc(x, self._buf("xin", (B, T, q["cin"].cin_pad), bf, zero=True))
+        h = q["cin"](xin, self._buf("hA", (B, T, q["cin"].cout), torch.float32))
+        for lvl, ent in enumerate(q["down"]):
+            for ib, r in enumerate(ent["blocks"]):
+                h = self._res(r, h, B, T)
+                if ent["attn"]:
+                    h = self._attn(ent["attn"][ib], h, B, T)
+            if "down_w" in ent:
+                C = h.shape[-1]
+                Te = T + (T & 1)                                  # an odd length gets its zero frame explicitly
+                h16 = self._buf("d16", (B, Te, C), bf, zero=True)
+                ops.cast(h, h16[:, :T]) if T == Te else [ops.cast(h[b], h16[b, :T]) for b in range(B)]
+                To = (T + 1 - 3) // 2 + 1
+                out = self._next_h(B, To, C, h)
+                ops.gemm(h16, ent["down_w"], M=To, N=C, K=2 * C, batch=B, a_rows=Te // 2, a_batch_stride=Te * C,
+                         b_rows=2 * C, taps=((0, 0), (1, C)), out=out, out_ld=C, out_batch_stride=To * C,
+                         bias=ent["down_b"])
+                h, T = out, To
+        h = self._res(q["mid1"], h, B, T)
+        h = self._attn(q["mida"], h, B, T)
+        h = self._res(q["mid2"], h, B, T)
+        C = h.shape[-1]
+        t1 = ops.groupnorm_swish(h, *q["nout"], self._buf("t1", (B, T, C), bf))
+        mo = q["cout"](t1, self._buf("emo", (B, T, q["qc"].cin_pad), bf, zero=True))
+        mq = q["qc"](mo, self._buf("emq", (B, T, q["qc"].cout), torch.float32))
+        moments = torch.empty(B, q["qc"].cout, T, device=dev, dtype=torch.float32)
+        return DiagonalGaussianDistribution(ops.ntc_to_nct(mq, moments))
+
+    @torch.no_grad()
     def forward(self, input, sample_posterior=True):
-        raise NotImplementedError("training forward (encode + decode) is outside the sampling path")
+        """autoencoder1d.py:64-71: (reconstruction, posterior)."""
+        posterior = self.encode(input)
+        z = posterior.sample() if sample_posterior else posterior.mode()
+        return self.decode(z), posterior

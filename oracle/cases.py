@@ -43,6 +43,16 @@ def mel_inputs(B=2, T=12, seed=14):
     return torch.randn(B, 80, T, generator=gen(seed)) * 1.5 - 2.0
 
 
+MEL_HP = dict(fft_size=1024, audio_num_mel_bins=80, audio_sample_rate=16000, hop_size=256, win_size=1024, fmin=0, fmax=8000)
+
+
+def wave_inputs(B=2, n=4096, seed=16):
+    g = gen(seed)
+    t = torch.arange(n) / 16000.0
+    tone = 0.4 * torch.sin(2 * 3.14159265 * 440.0 * t)[None] + 0.2 * torch.sin(2 * 3.14159265 * 3100.0 * t)[None]
+    return (tone + 0.3 * torch.randn(B, n, generator=g)) * torch.tensor([[1.0], [2.5]])[:B]   # second row clips at +-1
+
+
 def act_inputs(B=2, C=24, T=50, seed=15):
     g = gen(seed)
     return torch.randn(B, C, T, generator=g), torch.randn(C, generator=g) * 0.3, torch.randn(C, generator=g) * 0.3

@@ -62,14 +62,20 @@ def attention(sd, p, x, y, cos, sin, heads):
     """flag_large_dit_moe.py:325-408 (qk_norm is Identity in every shipped config)."""
     N, T, D = x.shape
     hd = D // heads
-    q = (x @ sd[p + "wq.weight"].t()).view(N, T, heads, hd)
-    k = (x @ sd[p + "wk.weight"].t()).view(N, T, heads, hd)
+    q, k = x @ sd[p + "wq.weight"].t(), x @ sd[p + "wk.weight"].t()
+    if p + "q_norm.weight" in sd:   # qk_norm=True: nn.LayerNorm over the full model dim (flag_large_dit_moe.py:199-207,345-346)
+        q = Fn.layer_norm(q, (D,), sd[p + "q_norm.weight"], sd[p + "q_norm.bias"], 1e-5)
+        k = Fn.layer_norm(k, (D,), sd[p + "k_norm.weight"], sd[p + "k_norm.bias"], 1e-5)
+    q, k = q.view(N, T, heads, hd), k.view(N, T, heads, hd)
     v = (x @ sd[p + "wv.weight"].t()).view(N, T, heads, hd)
     q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
     qh = q.permute(0, 2, 1, 3)
     o = _softmax_attention(qh, k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3))
     L = y.shape[1]
-    yk = (y @ sd[p + "wk_y.weight"].t()).view(N, L, heads, hd).permute(0, 2, 1, 3)
+    yk = y @ sd[p + "wk_y.weight"].t()
+    if p + "ky_norm.weight" in sd:
+        yk = Fn.layer_norm(yk, (D,), sd[p + "ky_norm.weight"], sd[p + "ky_norm.bias"], 1e-5)
+    yk = yk.view(N, L, heads, hd).permute(0, 2, 1, 3)
     yv = (y @ sd[p + "wv_y.weight"].t()).view(N, L, heads, hd).permute(0, 2, 1, 3)
     oy = _softmax_attention(qh, yk, yv) * torch.tanh(sd[p + "gate"]).view(1, heads, 1, 1)
     o = (o + oy).permute(0, 2, 1, 3).reshape(N, T, D)
@@ -203,9 +209,10 @@ def _c1d(x, sd, name, padding=0, dilation=1):
 
 
 def _resblock(x, sd, name):
-    """autoencoder1d.py:215-235 (temb is None; dropout 0)."""
-    h = _c1d(_swish(_gn(x, sd, name + ".norm1")), sd, name + ".conv1", padding=1)
-    h = _c1d(_swish(_gn(h, sd, name + ".norm2")), sd, name + ".conv2", padding=1)
+    """autoencoder1d.py:215-235 (temb is None; dropout 0); kernel 3 in the decoder, `kernel_size` in the encoder."""
+    pad = sd[name + ".conv1.weight"].shape[-1] // 2
+    h = _c1d(_swish(_gn(x, sd, name + ".norm1")), sd, name + ".conv1", padding=pad)
+    h = _c1d(_swish(_gn(h, sd, name + ".norm2")), sd, name + ".conv2", padding=pad)
     if name + ".nin_shortcut.weight" in sd:
         x = _c1d(x, sd, name + ".nin_shortcut")
     return x + h
@@ -245,6 +252,82 @@ def vae_decode(sd, z, ddconfig, scale_factor=1.0):
             h = _c1d(h, sd, f"decoder.up.{lvl}.upsample.conv", padding=1)
     h = _swish(_gn(h, sd, "decoder.norm_out"))
     return _c1d(h, sd, "decoder.conv_out", padding=ks // 2)
+
+
+def vae_encode(sd, x, ddconfig):
+    """AutoencoderKL.encode (autoencoder1d.py:49-53) -> Encoder1D.forward (autoencoder1d.py:319-413) -> quant_conv.
+    x [B, in_channels, T] -> moments [B, 2 * embed_dim, T / 2^len(down_layers)] (mean | logvar, before the clamp of
+    DiagonalGaussianDistribution, ldm/modules/distributions/distributions.py:24-35)."""
+    ch_mult = list(ddconfig["ch_mult"])
+    nrb = ddconfig["num_res_blocks"]
+    ks = ddconfig.get("kernel_size", 3)
+    down_layers = list(ddconfig.get("down_layers", []))
+    attn_layers = ddconfig.get("attn_layers", [])
+    h = _c1d(x, sd, "encoder.conv_in", padding=ks // 2)
+    for lvl in range(len(ch_mult)):
+        for ib in range(nrb):
+            h = _resblock(h, sd, f"encoder.down.{lvl}.block.{ib}")
+            if lvl in attn_layers:
+                h = _attnblock(h, sd, f"encoder.down.{lvl}.attn.{ib}")
+        if lvl in down_layers:   # Downsample1D: zero-pad one sample on the right, conv k3 stride 2 (:296-317)
+            h = Fn.conv1d(Fn.pad(h, (0, 1)), sd[f"encoder.down.{lvl}.downsample.conv.weight"],
+                          sd[f"encoder.down.{lvl}.downsample.conv.bias"], stride=2)
+    h = _resblock(h, sd, "encoder.mid.block_1")
+    h = _attnblock(h, sd, "encoder.mid.attn_1")
+    h = _resblock(h, sd, "encoder.mid.block_2")
+    h = _c1d(_swish(_gn(h, sd, "encoder.norm_out")), sd, "encoder.conv_out", padding=ks // 2)
+    return _c1d(h, sd, "quant_conv")
+
+
+def posterior_mode_sample(moments, noise=None):
+    """DiagonalGaussianDistribution (distributions.py:24-44): mean, logvar clamped to [-30, 20], std = exp(logvar / 2)."""
+    mean, logvar = moments.chunk(2, dim=1)
+    std = torch.exp(0.5 * logvar.clamp(-30.0, 20.0))
+    return mean, (mean + std * noise if noise is not None else None)
+
+
+# ------------------------------------------------------------------------------------------------ mel front-end
+def slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax):
+    """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax) with its defaults (htk=False, norm='slaney') -- restated from
+    the published algorithm because librosa is not installed here (preprocess/NAT_mel.py:54 calls it): linear below
+    1 kHz (200/3 Hz per mel), logarithmic above (step log(6.4)/27), triangular filters on the FFT bin centres,
+    each scaled by 2 / (f_hi - f_lo).  -> [n_mels, n_fft/2 + 1]"""
+    def hz_to_mel(f):
+        f = torch.as_tensor(f, dtype=torch.float64)
+        lin = f / (200.0 / 3)
+        log = 15.0 + torch.log(f.clamp_min(1e-10) / 1000.0) / (math.log(6.4) / 27.0)
+        return torch.where(f >= 1000.0, log, lin)
+
+    def mel_to_hz(m):
+        lin = m * (200.0 / 3)
+        log = 1000.0 * torch.exp((math.log(6.4) / 27.0) * (m - 15.0))
+        return torch.where(m >= 15.0, log, lin)
+
+    fft_f = torch.linspace(0, sr / 2, n_fft // 2 + 1, dtype=torch.float64)
+    mel_f = mel_to_hz(torch.linspace(float(hz_to_mel(fmin)), float(hz_to_mel(fmax)), n_mels + 2, dtype=torch.float64))
+    fdiff = mel_f[1:] - mel_f[:-1]
+    ramps = mel_f[:, None] - fft_f[None, :]
+    lower = -ramps[:-2] / fdiff[:-1, None]
+    upper = ramps[2:] / fdiff[1:, None]
+    w = torch.clamp(torch.minimum(lower, upper), min=0)
+    w = w * (2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels]))[:, None]
+    return w.float()
+
+
+def melnet(y, hp, mel_basis=None):
+    """MelNet.forward (preprocess/NAT_mel.py:65-85, center=False, complex=False): clamp to [-1, 1], reflect-pad
+    (n_fft - hop) / 2 on both sides, STFT (Hann window of win_size), magnitude sqrt(re^2 + im^2 + 1e-9), mel filterbank,
+    log10(clamp(., 1e-5)).  y [B, samples] -> [B, n_mels, frames]."""
+    n_fft, hop, win = hp["fft_size"], hp["hop_size"], hp["win_size"]
+    if mel_basis is None:
+        mel_basis = slaney_mel_filterbank(hp["audio_sample_rate"], n_fft, hp["audio_num_mel_bins"], hp["fmin"], hp["fmax"])
+    y = y.clamp(-1.0, 1.0)
+    pad = int((n_fft - hop) / 2)
+    y = Fn.pad(y.unsqueeze(1), [pad, pad], mode="reflect").squeeze(1)
+    spec = torch.stft(y, n_fft, hop_length=hop, win_length=win, window=torch.hann_window(win).to(y.device), center=False,
+                      pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+    mag = torch.sqrt(spec.real.pow(2) + spec.imag.pow(2) + 1e-9)
+    return torch.log10(torch.clamp(torch.matmul(mel_basis.to(y.device), mag), min=1e-5))
 
 
 # ------------------------------------------------------------------------------------------------ BigVGAN

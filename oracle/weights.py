@@ -31,7 +31,8 @@ def ffn_hidden(dim, multiple_of=256):
     return multiple_of * ((h + multiple_of - 1) // multiple_of)
 
 
-def dit_state_dict(*, in_channels, context_dim, hidden_size, num_heads, depth, video=False, num_experts=0, seed=0):
+def dit_state_dict(*, in_channels, context_dim, hidden_size, num_heads, depth, video=False, num_experts=0, seed=0,
+                   qk_norm=False):
     """Keys of TxtFlagLargeImprovedDiTV2 (flag_large_dit.py:256-299) or VideoFlagLargeDiT
     (flag_large_dit_moe.py:613-662)."""
     g = _gen(seed)
@@ -64,6 +65,10 @@ def dit_state_dict(*, in_channels, context_dim, hidden_size, num_heads, depth, v
         sd[p + "attention.wk_y.weight"] = _lin(g, D, y_dim)
         sd[p + "attention.wv_y.weight"] = _lin(g, D, y_dim)
         sd[p + "attention.gate"] = _vec(g, num_heads, 0.5)
+        if qk_norm:   # nn.LayerNorm(D) on q, k and the cross k (flag_large_dit_moe.py:199-207)
+            for n in ("q_norm", "k_norm", "ky_norm"):
+                sd[p + f"attention.{n}.weight"] = _vec(g, D, 0.1, 1.0)
+                sd[p + f"attention.{n}.bias"] = _vec(g, D, 0.05)
         if num_experts:
             for kind in ("time_experts", "freq_experts"):
                 for e in range(num_experts):
@@ -139,6 +144,48 @@ def vae_decoder_state_dict(ddconfig, embed_dim, seed=1):
             _conv(g, sd, f"decoder.up.{lvl}.upsample.conv", block_in, block_in, 3)
     _norm(g, sd, "decoder.norm_out", block_in)
     _conv(g, sd, "decoder.conv_out", ddconfig["out_ch"], block_in, ks)
+    return sd
+
+
+def vae_encoder_state_dict(ddconfig, embed_dim, seed=7):
+    """Keys of AutoencoderKL.{encoder, quant_conv} (ldm/models/autoencoder1d.py:18-53, 319-413)."""
+    g = _gen(seed)
+    ch, ch_mult = ddconfig["ch"], list(ddconfig["ch_mult"])
+    nrb, zc, ks = ddconfig["num_res_blocks"], ddconfig["z_channels"], ddconfig.get("kernel_size", 3)
+    down_layers = list(ddconfig.get("down_layers", []))
+    attn_layers = ddconfig.get("attn_layers", [])
+    sd = {}
+    _conv(g, sd, "encoder.conv_in", ch, ddconfig["in_channels"], ks)
+
+    def res(name, cin, cout):
+        _norm(g, sd, name + ".norm1", cin)
+        _conv(g, sd, name + ".conv1", cout, cin, ks)     # the encoder's ResNet blocks take kernel_size (:345-349)
+        _norm(g, sd, name + ".norm2", cout)
+        _conv(g, sd, name + ".conv2", cout, cout, ks)
+        if cin != cout:
+            _conv(g, sd, name + ".nin_shortcut", cout, cin, 1)
+
+    def attn(name, c):
+        _norm(g, sd, name + ".norm", c)
+        for n in ("q", "k", "v", "proj_out"):
+            _conv(g, sd, name + "." + n, c, c, 1)
+
+    block_in = ch
+    for lvl in range(len(ch_mult)):
+        block_out = ch * ch_mult[lvl]
+        for ib in range(nrb):
+            res(f"encoder.down.{lvl}.block.{ib}", block_in, block_out)
+            block_in = block_out
+            if lvl in attn_layers:
+                attn(f"encoder.down.{lvl}.attn.{ib}", block_in)
+        if lvl in down_layers:
+            _conv(g, sd, f"encoder.down.{lvl}.downsample.conv", block_in, block_in, 3)
+    res("encoder.mid.block_1", block_in, block_in)
+    attn("encoder.mid.attn_1", block_in)
+    res("encoder.mid.block_2", block_in, block_in)
+    _norm(g, sd, "encoder.norm_out", block_in)
+    _conv(g, sd, "encoder.conv_out", 2 * zc if ddconfig.get("double_z", True) else zc, block_in, ks)
+    _conv(g, sd, "quant_conv", 2 * embed_dim, 2 * zc, 1)
     return sd
 
 

@@ -65,12 +65,18 @@ def test_vae_and_vocoder_state_dict_keys():
     from ma3_b200.vocoder import BigVGAN
     vae = AutoencoderKL(embed_dim=20, ddconfig=dict(Cs.VAE_TINY), lossconfig={"target": "torch.nn.Identity"})
     sd = W.vae_decoder_state_dict(Cs.VAE_TINY, 20)
-    assert set(vae.state_dict().keys()) == set(sd.keys())
-    assert all(vae.state_dict()[k].shape == v.shape for k, v in sd.items())
-    # a full reference checkpoint also carries encoder / quant_conv / loss keys: tolerated with strict=False
-    r = vae.load_state_dict(dict(sd, **{"encoder.conv_in.weight": torch.zeros(1), "quant_conv.bias": torch.zeros(1)}),
-                            strict=False)
-    assert sorted(r.unexpected_keys) == ["encoder.conv_in.weight", "quant_conv.bias"] and not r.missing_keys
+    esd = W.vae_encoder_state_dict(Cs.VAE_TINY, 20)
+    assert set(vae.state_dict().keys()) == set(sd.keys()) | set(esd.keys())
+    assert all(vae.state_dict()[k].shape == v.shape for k, v in dict(sd, **esd).items())
+    # the sampling path only needs the decoder: a decoder-only state_dict loads under strict=True (encode() disabled);
+    # a full reference checkpoint also carries loss keys, which are ignored
+    r = vae.load_state_dict(sd, strict=True)
+    assert not r.missing_keys and not r.unexpected_keys and not vae._has_encoder
+    r = vae.load_state_dict(dict(sd, **esd, **{"loss.logvar": torch.zeros(1)}), strict=True)
+    assert not r.missing_keys and not r.unexpected_keys and vae._has_encoder
+    import pytest
+    with pytest.raises(RuntimeError):
+        vae.load_state_dict({k: v for k, v in sd.items() if k != "decoder.conv_in.bias"}, strict=True)
     for h in (Cs.BIGVGAN_TINY, dict(W.BIGVGAN_BASE_256X, upsample_initial_channel=64, resblock="2",
                                     resblock_dilation_sizes=[[1, 3], [1, 3], [1, 3]])):
         g = BigVGAN(dict(h))

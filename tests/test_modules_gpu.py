@@ -291,3 +291,70 @@ def test_pipeline_full_size_properties():
     w1 = pipe.decode_and_vocode(z1)
     w8 = pipe.decode_and_vocode(z8)
     assert O.snr_db(w8[3:4].cpu(), w1.cpu()) > 40
+
+
+# ------------------------------------------------------------------------------------------------ round 2: VAE encoder
+def test_vae_encode_golden():
+    """AutoencoderKL.encode (Encoder1D + quant_conv) against moments produced by the reference module."""
+    import os
+    from ma3_b200.vae import AutoencoderKL
+    g2 = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden_r02.pt"))
+    sd = dict(W.vae_encoder_state_dict(Cs.VAE_TINY, 20), **W.vae_decoder_state_dict(Cs.VAE_TINY, 20))
+    vae = AutoencoderKL(embed_dim=20, ddconfig=dict(Cs.VAE_TINY), lossconfig=None)
+    vae.load_state_dict(sd, strict=True)
+    post = vae.cuda().encode(Cs.mel_inputs(B=2, T=48).cuda())
+    assert post.parameters.shape == g2["vae_enc_moments"].shape
+    assert O.cosine(post.parameters.cpu(), g2["vae_enc_moments"]) > 0.999
+    assert O.max_rel_err(post.mode().cpu(), g2["vae_enc_mode"]) < 3e-2
+    z = post.sample()
+    assert z.shape == (2, 20, 24) and bool(torch.isfinite(z).all())
+    rec, post2 = vae(Cs.mel_inputs(B=2, T=48).cuda(), sample_posterior=False)       # autoencoder1d.py:64-71
+    assert rec.shape == (2, 80, 48) and torch.equal(post2.parameters, post.parameters)
+    dec_only = AutoencoderKL(embed_dim=20, ddconfig=dict(Cs.VAE_TINY), lossconfig=None)
+    dec_only.load_state_dict(W.vae_decoder_state_dict(Cs.VAE_TINY, 20), strict=True)
+    from ma3_b200.lib import Ma3Error
+    with pytest.raises(Ma3Error):
+        dec_only.cuda().encode(Cs.mel_inputs(B=1, T=48).cuda())
+
+
+def test_vae_encode_full_size_and_odd_length():
+    """The shipped ddconfig on a 624-frame mel (10 s clip) and on an odd length (Downsample1D pads one frame)."""
+    from ma3_b200.pipeline import VAE_DDCONFIG
+    from ma3_b200.vae import AutoencoderKL
+    O.strict_fp32()
+    sd = dict(W.vae_encoder_state_dict(VAE_DDCONFIG, 20), **W.vae_decoder_state_dict(VAE_DDCONFIG, 20))
+    vae = AutoencoderKL(embed_dim=20, ddconfig=dict(VAE_DDCONFIG), lossconfig=None)
+    vae.load_state_dict(sd, strict=True)
+    vae = vae.cuda()
+    dsd = O.to_device(sd, "cuda")
+    for B, T in ((2, 624), (1, 101)):
+        mel = Cs.mel_inputs(B=B, T=T).cuda()
+        with torch.no_grad():
+            ref = O.vae_encode(dsd, mel, VAE_DDCONFIG)
+        out = vae.encode(mel).parameters
+        assert out.shape == ref.shape == (B, 40, (T + 1 - 3) // 2 + 1)
+        assert O.cosine(out.cpu(), ref.cpu()) > 0.999 and O.max_rel_err(out.cpu(), ref.cpu()) < 3e-2
+
+
+def test_windowed_generation():
+    """pipeline.generate_windows == the per-window loop of scripts/video2audio_flow.py:483-523 (windows are independent)."""
+    from ma3_b200 import dit as D
+    from ma3_b200.pipeline import Txt2AudioPipeline
+    from ma3_b200.vae import AutoencoderKL
+    from ma3_b200.vocoder import VocoderBigVGAN
+    cfg = Cs.DIT_SMALL
+    dit = _dit(dict(cfg, max_len=100), W.dit_state_dict(**cfg, seed=3))
+    vae = AutoencoderKL(embed_dim=20, ddconfig=dict(Cs.VAE_TINY))
+    vae.load_state_dict(W.vae_decoder_state_dict(Cs.VAE_TINY, 20), strict=True)
+    h = Cs.BIGVGAN_SMALL
+    pipe = Txt2AudioPipeline(dit, vae.cuda(), VocoderBigVGAN(h=h, state_dict=W.bigvgan_state_dict(h)), mel_length=24,
+                             use_graph=False)
+    x0, c, uc = Cs.cfm_inputs(cfg, B=3, T=24, L=10)
+    wav, mel = pipe.generate_windows(c.cuda(), uc.cuda(), scale=3.0, timesteps=5, x0=x0.cuda())
+    assert mel.shape == (1, 80, 3 * 48) and wav.shape == (1, 3 * 48 * 16)
+    mels = []
+    for i in range(3):   # the reference's loop: one window at a time
+        z, _ = pipe.sample_cfg(c[i:i + 1].cuda(), 3.0, uc[i:i + 1].cuda(), 1, timesteps=5, x_latent=x0[i:i + 1].cuda())
+        mels.append(pipe.decode_first_stage(z))
+    ref = torch.cat(mels, 2)
+    assert O.cosine(mel.cpu(), ref.cpu()) > 0.9999

@@ -70,3 +70,50 @@ def test_fold_weight_norm():
     sd = O.fold_weight_norm({"c.weight_g": gg, "c.weight_v": v, "c.bias": torch.zeros(6)})
     ref = torch._weight_norm(v, gg, 0)
     assert torch.allclose(sd["c.weight"], ref, atol=1e-6) and "c.weight_v" not in sd
+
+
+# ------------------------------------------------------------------------------------------------ round 2 additions
+import os as _os
+
+import pytest as _pytest
+
+
+@_pytest.fixture(scope="module")
+def golden2():
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    return torch.load(_os.path.join(root, "tests", "golden", "ref_golden_r02.pt"))
+
+
+def test_vae_encode(golden2):
+    sd = W.vae_encoder_state_dict(Cs.VAE_TINY, 20)
+    mom = O.vae_encode(sd, Cs.mel_inputs(B=2, T=48), Cs.VAE_TINY)
+    assert mom.shape == golden2["vae_enc_moments"].shape
+    assert O.max_rel_err(mom, golden2["vae_enc_moments"]) < TOL
+    mean, _ = O.posterior_mode_sample(mom)
+    assert O.max_rel_err(mean, golden2["vae_enc_mode"]) < TOL
+
+
+def test_dit_qk_norm(golden2):
+    cfg = Cs.DIT_SMALL
+    sd = W.dit_state_dict(**cfg, seed=9, qk_norm=True)
+    x, ctx = Cs.dit_inputs(cfg)
+    out = O.dit_forward(sd, x, torch.tensor([41, 958]), ctx, heads=cfg["num_heads"], max_len=100)
+    assert O.max_rel_err(out, golden2["dit_small_qknorm"]) < TOL
+
+
+def test_melnet(golden2):
+    out = O.melnet(Cs.wave_inputs(), Cs.MEL_HP)
+    assert out.shape == golden2["melnet"].shape
+    assert O.max_rel_err(out, golden2["melnet"]) < 1e-4
+
+
+def test_slaney_filterbank_matches_torchaudio():
+    """The filterbank is restated from librosa's published algorithm (librosa is not installed); torchaudio ships the
+    same construction (norm='slaney', mel_scale='slaney')."""
+    ta = _pytest.importorskip("torchaudio")
+    hp = Cs.MEL_HP
+    ref = ta.functional.melscale_fbanks(hp["fft_size"] // 2 + 1, hp["fmin"], hp["fmax"], hp["audio_num_mel_bins"],
+                                        hp["audio_sample_rate"], norm="slaney", mel_scale="slaney").t()
+    fb = O.slaney_mel_filterbank(hp["audio_sample_rate"], hp["fft_size"], hp["audio_num_mel_bins"], hp["fmin"], hp["fmax"])
+    assert fb.shape == ref.shape == (80, 513)
+    assert float((fb - ref).abs().max()) < 1e-6
