@@ -212,6 +212,16 @@ int ma3_adaln_input(const float* temb, const float* cap, void* out, int out_dtyp
 int ma3_split_bf16(const float* x, int64_t ld, int col0, int col_step, int nb, int rows, int cols, void* out,
                    void* stream);
 
+/* Mel front-end (preprocess/NAT_mel.py:65-85, MelNet.forward, center=False): the elementwise glue around two tap-GEMMs
+ * (STFT as a 4-tap GEMM over hop-sized rows with the windowed DFT basis, then the mel filterbank), all 16-bit operands as
+ * (hi, lo) bf16 splits.
+ *   ma3_melnet_prep: y [B][n] fp32 -> hops [B][2][nh][hop] bf16 of clamp(y, -1, 1) reflect-padded by `pad` on both sides
+ *   ma3_melnet_mag:  S [B*F][ld] fp32 (re, im interleaved) -> mag [B][2][F][bins_pad] bf16 split of sqrt(re^2+im^2+1e-9)
+ *   ma3_melnet_log:  mel [B*F][n_mels] fp32 -> out [B][n_mels][F] = log10(max(mel, 1e-5)) */
+int ma3_melnet_prep(const float* y, void* hops, int B, int n, int pad, int nh, int hop, void* stream);
+int ma3_melnet_mag(const float* S, int64_t ld, void* mag, int B, int F, int bins, int bins_pad, void* stream);
+int ma3_melnet_log(const float* mel, float* out, int B, int F, int n_mels, void* stream);
+
 /* mod[r, tail_off + (2i+j)*D + d] = norm_w[i][j][d] * (1 + mod[r, 6*D*i + (j ? 4*D : D) + d]) for r < rows, i < depth,
  * j in {0: attention_norm, 1: ffn_norm}: wn_s = w * (1 + scale_s) of flag_large_dit.py:83-91, written behind the
  * modulation columns of the same row so that it shares their row pitch (the `wn` operand of ma3_gemm_rownorm). */

@@ -61,6 +61,9 @@ def declare(lib):
         "ma3_l2_persist": [vp, C.c_size_t, vp],
         "ma3_split_bf16": [vp, i64, i32, i32, i32, i32, i32, vp, vp],
         "ma3_norm_weights": [vp, i64, vp, i32, i32, i32, i32, vp],
+        "ma3_melnet_prep": [vp, vp, i32, i32, i32, i32, i32, vp],
+        "ma3_melnet_mag": [vp, i64, vp, i32, i32, i32, i32, vp],
+        "ma3_melnet_log": [vp, vp, i32, i32, i32, vp],
         "ma3_gemm_rownorm": [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, i32, vp, f32, vp],
     }
     for name, args in protos.items():

@@ -122,3 +122,18 @@ def test_shard_prompts():
     parts = [shard_prompts(64, r, 8) for r in range(8)]
     assert all(len(p) == 8 for p in parts) and sorted(sum(parts, [])) == list(range(64))
     assert shard_prompts(3, 2, 8) == [2] and shard_prompts(3, 5, 8) == []
+
+
+def test_mel_filterbank_restatement():
+    """ma3_b200.mel.mel_filterbank == the oracle's restatement of librosa.filters.mel == torchaudio's slaney filterbank."""
+    import pytest
+    from ma3_b200.mel import MelNet, mel_filterbank
+    from oracle import restated as O
+    hp = Cs.MEL_HP
+    fb = mel_filterbank(hp["audio_sample_rate"], hp["fft_size"], hp["audio_num_mel_bins"], hp["fmin"], hp["fmax"])
+    ref = O.slaney_mel_filterbank(hp["audio_sample_rate"], hp["fft_size"], hp["audio_num_mel_bins"], hp["fmin"], hp["fmax"])
+    assert fb.shape == (80, 513) and float((fb - ref).abs().max()) < 1e-7
+    net = MelNet(hp, device="cpu")                      # construction needs no GPU; forward does
+    assert net.mel_basis.shape == (80, 513) and net.hann_window.shape == (1024,)
+    with pytest.raises(ValueError):
+        MelNet(dict(hp, hop_size=300))

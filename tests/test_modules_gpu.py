@@ -358,3 +358,27 @@ def test_windowed_generation():
         mels.append(pipe.decode_first_stage(z))
     ref = torch.cat(mels, 2)
     assert O.cosine(mel.cpu(), ref.cpu()) > 0.9999
+
+
+# ------------------------------------------------------------------------------------------------ round 2: mel front-end
+def test_melnet_golden_and_long():
+    """MelNet drop-in (preprocess/NAT_mel.py:42-85): STFT + filterbank as split-bf16 tap-GEMMs.  Tolerance: 2e-2 absolute
+    on the log10-mel (values span [-5, 2]); the reference-generated golden and a 10 s signal against the oracle."""
+    import os
+    from ma3_b200.mel import MelNet
+    g2 = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden_r02.pt"))
+    net = MelNet(Cs.MEL_HP)
+    out = net(Cs.wave_inputs().cuda()).cpu()
+    assert out.shape == g2["melnet"].shape == (2, 80, 16)
+    err = float((out - g2["melnet"]).abs().max())
+    print(f"MelNet vs reference golden: max abs log10 diff {err:.2e}")
+    assert err < 2e-2
+    y = Cs.wave_inputs(B=2, n=159744, seed=17)
+    ref = O.melnet(y, Cs.MEL_HP)
+    got = net(y.numpy()[0]).cpu()                      # numpy 1-D input, as the reference accepts
+    assert got.shape == (1, 80, 624)
+    assert float((got - ref[:1]).abs().max()) < 2e-2
+    got2 = net(y.cuda()).cpu()
+    assert got2.shape == (2, 80, 624) and float((got2 - ref).abs().max()) < 2e-2
+    with pytest.raises(NotImplementedError):
+        net(y[:1], center=True)
