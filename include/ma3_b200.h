@@ -212,6 +212,14 @@ int ma3_adaln_input(const float* temb, const float* cap, void* out, int out_dtyp
 int ma3_split_bf16(const float* x, int64_t ld, int col0, int col_step, int nb, int rows, int cols, void* out,
                    void* stream);
 
+/* qk_norm=True variant of the QKV path (flag_large_dit_moe.py:199-207,345-352): x fp32 [M][ld] holds the raw projections
+ * q | k | v (first_section 0) or k | v (first_section 1, cross-attention with ky_norm); per row: LayerNorm over the full
+ * model dim of q (qw, qb) and k (kw, kb) (NULL weights = no norm), RoPE (rope NULL = none), q * q_scale, and the scatter
+ * into q, k [sample, head, t, hd_pad] and V^T [sample, head, hd_pad, t_pad] (same layouts as MA3_EPI_QKV_ROPE). */
+int ma3_qknorm_rope(const float* x, int64_t ld, int first_section, const float* qw, const float* qb, const float* kw,
+                    const float* kb, float eps, const float* rope, void* q_out, void* k_out, void* vt_out, int dtype, int M,
+                    int tokens, int tokens_pad, int D, int hd, int hdp, float q_scale, void* stream);
+
 /* Mel front-end (preprocess/NAT_mel.py:65-85, MelNet.forward, center=False): the elementwise glue around two tap-GEMMs
  * (STFT as a 4-tap GEMM over hop-sized rows with the windowed DFT basis, then the mel filterbank), all 16-bit operands as
  * (hi, lo) bf16 splits.

@@ -819,6 +819,87 @@ __global__ void adaln_input_kernel(const float* __restrict__ temb, const float* 
 }
 }  // namespace ma3
 
+// ---------------------------------------------------------------------------------------- QK-norm + RoPE + scatter
+// qk_norm=True (flag_large_dit_moe.py:199-207,345-352): q and k are LayerNorm-ed over the FULL model dim (all heads,
+// affine, eps 1e-5) before the rotary embedding.  A GEMM tile cannot see a whole row, so this variant stores the raw
+// projections (fp32 [M, sections * D]) and this kernel finishes the job in one pass per row: LayerNorm(q), LayerNorm(k),
+// RoPE, the softmax scale on q, and the scatter into the attention layouts q, k [sample, head, t, hd_pad] and
+// V^T [sample, head, hd_pad, t_pad].  first_section = 1: the row holds k | v only (cross-attention K/V with ky_norm).
+// No shipped config enables qk_norm; the path is functional, HBM-bound and not tuned further.
+namespace ma3 {
+template <typename T16>
+__global__ void __launch_bounds__(256) qknorm_rope_kernel(const float* __restrict__ x, long long ld, int first_section,
+                                                           const float* __restrict__ qw, const float* __restrict__ qb,
+                                                           const float* __restrict__ kw, const float* __restrict__ kb,
+                                                           float eps, const float* __restrict__ rope, T16* __restrict__ q_out,
+                                                           T16* __restrict__ k_out, T16* __restrict__ vt_out, int tokens,
+                                                           int tokens_pad, int D, int hd, int hdp, float q_scale) {
+  __shared__ float red[64];
+  const int m = blockIdx.x, sample = m / tokens, t = m - sample * tokens;
+  const int H = D / hd, half = hd >> 1;
+  const float* row = x + (long long)m * ld;
+  for (int sec = first_section; sec < 3; ++sec) {
+    const float* src = row + (long long)(sec - first_section) * D;
+    float mean = 0.f, rstd = 1.f;
+    const float* w = sec == 0 ? qw : kw;
+    const float* b = sec == 0 ? qb : kb;
+    const bool norm = sec < 2 && w != nullptr;
+    if (norm) {
+      float s = 0.f;
+      for (int i = threadIdx.x; i < D; i += blockDim.x) s += src[i];
+      mean = block_sum(s, red) / (float)D;
+      float v = 0.f;
+      for (int i = threadIdx.x; i < D; i += blockDim.x) { const float d0 = src[i] - mean; v += d0 * d0; }
+      rstd = rsqrtf(block_sum(v, red) / (float)D + eps);
+    }
+    for (int p = threadIdx.x; p < (D >> 1); p += blockDim.x) {
+      const int c = 2 * p, h = c / hd, d = c - h * hd;
+      float a0 = src[c], a1 = src[c + 1];
+      if (norm) {
+        a0 = (a0 - mean) * rstd * w[c] + b[c];
+        a1 = (a1 - mean) * rstd * w[c + 1] + b[c + 1];
+      }
+      if (sec < 2) {
+        if (rope != nullptr) {
+          const float2 cs = *reinterpret_cast<const float2*>(rope + ((long long)t * half + (d >> 1)) * 2);
+          const float r0 = a0 * cs.x - a1 * cs.y, r1 = a0 * cs.y + a1 * cs.x;
+          a0 = r0; a1 = r1;
+        }
+        if (sec == 0) { a0 *= q_scale; a1 *= q_scale; }
+        T16* dst = (sec == 0 ? q_out : k_out) + (((long long)sample * H + h) * tokens + t) * hdp + d;
+        dst[0] = Cvt<T16>::to(a0);
+        dst[1] = Cvt<T16>::to(a1);
+      } else {
+        T16* dst = vt_out + (((long long)sample * H + h) * hdp + d) * tokens_pad + t;
+        dst[0] = Cvt<T16>::to(a0);
+        dst[tokens_pad] = Cvt<T16>::to(a1);
+      }
+    }
+    __syncthreads();
+  }
+}
+}  // namespace ma3
+
+extern "C" int ma3_qknorm_rope(const float* x, int64_t ld, int first_section, const float* qw, const float* qb,
+                               const float* kw, const float* kb, float eps, const float* rope, void* q_out, void* k_out,
+                               void* vt_out, int dtype, int M, int tokens, int tokens_pad, int D, int hd, int hdp,
+                               float q_scale, void* stream) {
+  MA3_REQUIRE(x && k_out && vt_out && M > 0 && tokens > 0 && M % tokens == 0, "qknorm_rope: bad arguments");
+  MA3_REQUIRE(first_section == 0 || first_section == 1, "qknorm_rope: first_section must be 0 or 1");
+  MA3_REQUIRE(first_section == 1 || q_out != nullptr, "qknorm_rope: q_out required");
+  MA3_REQUIRE(D % hd == 0 && hd % 2 == 0 && hdp >= hd && tokens_pad >= tokens && ld >= (3 - first_section) * (int64_t)D,
+              "qknorm_rope: D %% hd == 0, hd even, hdp >= hd, tokens_pad >= tokens, ld >= sections * D");
+  MA3_REQUIRE(dtype == MA3_BF16 || dtype == MA3_F16, "qknorm_rope: 16-bit outputs only");
+  if (dtype == MA3_BF16)
+    ma3::qknorm_rope_kernel<__nv_bfloat16><<<M, 256, 0, ST(stream)>>>(x, ld, first_section, qw, qb, kw, kb, eps, rope,
+        (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_out, (__nv_bfloat16*)vt_out, tokens, tokens_pad, D, hd, hdp, q_scale);
+  else
+    ma3::qknorm_rope_kernel<__half><<<M, 256, 0, ST(stream)>>>(x, ld, first_section, qw, qb, kw, kb, eps, rope,
+        (__half*)q_out, (__half*)k_out, (__half*)vt_out, tokens, tokens_pad, D, hd, hdp, q_scale);
+  MA3_LAUNCH_CHECK("qknorm_rope");
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------- bf16 hi/lo split
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi): out[i] = hi, out[n + i] = lo (two stacked operand copies).  A GEMM
 // over the taps (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) then carries ~16 mantissa bits through the bf16 tensor cores;

@@ -64,8 +64,10 @@ class _Seq(nn.Module):
 
 
 class _Attention(nn.Module):
-    def __init__(self, dim, n_heads, y_dim):
+    def __init__(self, dim, n_heads, y_dim, qk_norm=False):
         super().__init__()
+        if qk_norm:   # nn.LayerNorm over the full model dim (flag_large_dit_moe.py:199-207)
+            self.q_norm, self.k_norm, self.ky_norm = _LN(dim), _LN(dim), _LN(dim)
         self.wq, self.wk, self.wv = _Lin(dim, dim, False), _Lin(dim, dim, False), _Lin(dim, dim, False)
         self.wk_y, self.wv_y = _Lin(y_dim, dim, False), _Lin(y_dim, dim, False)
         self.gate = nn.Parameter(torch.zeros(n_heads))
@@ -86,9 +88,9 @@ class _MoE(nn.Module):
 
 
 class _Block(nn.Module):
-    def __init__(self, dim, n_heads, y_dim, hidden, num_experts):
+    def __init__(self, dim, n_heads, y_dim, hidden, num_experts, qk_norm=False):
         super().__init__()
-        self.attention = _Attention(dim, n_heads, y_dim)
+        self.attention = _Attention(dim, n_heads, y_dim, qk_norm)
         self.feed_forward = _MoE(dim, hidden, num_experts) if num_experts else _FFN(dim, hidden)
         self.attention_norm, self.ffn_norm = _Weight(dim), _Weight(dim)
         self.adaLN_modulation = _Seq(_1=_Lin(dim, 6 * dim))
@@ -119,8 +121,7 @@ class TxtFlagLargeDiT(nn.Module):
                  n_kv_heads=None, multiple_of: int = 256, ffn_dim_multiplier=None, norm_eps=1e-5, qk_norm=None,
                  rope_scaling_factor: float = 1.0, ntk_factor: float = 1.0, num_experts=0):
         super().__init__()
-        if qk_norm:
-            raise NotImplementedError("qk_norm=True is not used by any shipped config (flag_large_dit.py:145,270)")
+        self.qk_norm = bool(qk_norm)
         if n_kv_heads not in (None, num_heads):
             raise NotImplementedError("grouped KV heads are not used by any shipped config")
         if hidden_size % num_heads or (hidden_size // num_heads) % 8:
@@ -141,7 +142,7 @@ class TxtFlagLargeDiT(nn.Module):
             self.c_embedder.mlp = _Seq(_0=_Lin(context_dim, D), _2=_Lin(D, D), _3=_LN(D))
         self.proj_in = _Lin(in_channels, D)
         self.cap_embedder = _Seq(_0=_LN(y_dim), _1=_Lin(y_dim, D))
-        self.blocks = nn.ModuleList([_Block(D, num_heads, y_dim, self.ffn_hidden, self.num_experts)
+        self.blocks = nn.ModuleList([_Block(D, num_heads, y_dim, self.ffn_hidden, self.num_experts, self.qk_norm)
                                      for _ in range(depth)])
         self.final_layer = _Final(D, in_channels)
         self.rope_scaling_factor, self.ntk_factor = rope_scaling_factor, ntk_factor
@@ -234,6 +235,10 @@ class TxtFlagLargeDiT(nn.Module):
             q["wkv_y"] = b16(torch.cat([a.wk_y.weight.detach() * yw, a.wv_y.weight.detach() * yw]))
             q["wo"] = b16(a.wo.weight)
             q["gate"] = f32(a.gate)
+            if self.qk_norm:
+                q["qn"] = (f32(a.q_norm.weight), f32(a.q_norm.bias))
+                q["kn"] = (f32(a.k_norm.weight), f32(a.k_norm.bias))
+                q["kyn"] = (f32(a.ky_norm.weight), f32(a.ky_norm.bias))
             q["attn_norm"], q["ffn_norm"] = f32(blk.attention_norm.weight), f32(blk.ffn_norm.weight)
             ff = blk.feed_forward
             if self.num_experts:
@@ -303,6 +308,8 @@ class TxtFlagLargeDiT(nn.Module):
             w.vt = ops.alloc_vt(N, H, hd=hd, hdp=hdp, tokens_pad=Tp, device=dev, dtype=bf)
             w.att = torch.empty(N * T, D, device=dev, dtype=bf)
             w.mid = torch.empty(N * T, F, device=dev, dtype=bf)
+            if self.qk_norm:
+                w.qkv_raw = torch.empty(N * T, 3 * D, device=dev, dtype=torch.float32)
             if self.num_experts:
                 w.y1 = torch.empty(N * T, D, device=dev, dtype=bf)
             self._work[key] = w
@@ -350,6 +357,12 @@ class TxtFlagLargeDiT(nn.Module):
         ops.gemm_split(c["pool"], p["cap_w"], M=N, N=D, K=self.y_dim, out=c["cap"], bias=p["cap_b"])
         ops.rmsnorm_modulate(y.view(N * Lc, self.y_dim), None, c["yn"], eps=self.norm_eps)
         for i, q in enumerate(p["blocks"]):
+            if self.qk_norm:   # ky_norm: LayerNorm over the full dim of the cross K before the head split
+                raw = torch.empty(N * Lc, 2 * D, device=dev, dtype=torch.float32)
+                ops.gemm(c["yn"], q["wkv_y"], M=N * Lc, N=2 * D, K=self.y_dim, out=raw)
+                ops.qknorm_rope(raw, first_section=1, qn=None, kn=q["kyn"], rope=None, q_out=None, k_out=c["ky"][i],
+                                vt_out=c["vyt"][i], tokens=Lc, tokens_pad=Lp, D=D, hd=hd, hdp=hdp)
+                continue
             ops.gemm(c["yn"], q["wkv_y"], M=N * Lc, N=2 * D, K=self.y_dim, epi=L.EPI_QKV_ROPE, q_out=c["ky"][i],
                      k_out=c["ky"][i], vt_out=c["vyt"][i], rope=None, model_dim=D, head_dim=hd, head_dim_pad=hdp,
                      tokens=Lc, tokens_pad=Lp, first_section=1)
@@ -430,8 +443,15 @@ class TxtFlagLargeDiT(nn.Module):
             if not fused or i == 0:
                 ops.rmsnorm_modulate(w.h, q["attn_norm"], w.u, mod=mod, shift_off=o, scale_off=o + D, rows_per_sample=T,
                                      eps=eps)
-            ops.gemm(w.u, q["wqkv"], M=M, N=3 * D, K=D, epi=L.EPI_QKV_ROPE, q_out=w.q, k_out=w.k, vt_out=w.vt,
-                     rope=p["rope"], model_dim=D, head_dim=hd, head_dim_pad=w.hdp, tokens=T, tokens_pad=w.Tp, q_scale=qs)
+            if self.qk_norm:
+                # LayerNorm(q), LayerNorm(k) need whole rows: raw fp32 projections, then one fused norm+RoPE+scatter pass
+                ops.gemm(w.u, q["wqkv"], M=M, N=3 * D, K=D, out=w.qkv_raw)
+                ops.qknorm_rope(w.qkv_raw, first_section=0, qn=q["qn"], kn=q["kn"], rope=p["rope"], q_out=w.q, k_out=w.k,
+                                vt_out=w.vt, tokens=T, tokens_pad=w.Tp, D=D, hd=hd, hdp=w.hdp, q_scale=qs)
+            else:
+                ops.gemm(w.u, q["wqkv"], M=M, N=3 * D, K=D, epi=L.EPI_QKV_ROPE, q_out=w.q, k_out=w.k, vt_out=w.vt,
+                         rope=p["rope"], model_dim=D, head_dim=hd, head_dim_pad=w.hdp, tokens=T, tokens_pad=w.Tp,
+                         q_scale=qs)
             ops.attention(w.q, w.k, w.vt, c["ky"][i] if Lc else None, c["vyt"][i] if Lc else None, q["gate"], w.att,
                           hd=hd)
             if fused:

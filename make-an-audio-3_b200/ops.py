@@ -61,6 +61,7 @@ def declare(lib):
         "ma3_l2_persist": [vp, C.c_size_t, vp],
         "ma3_split_bf16": [vp, i64, i32, i32, i32, i32, i32, vp, vp],
         "ma3_norm_weights": [vp, i64, vp, i32, i32, i32, i32, vp],
+        "ma3_qknorm_rope": [vp, i64, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
         "ma3_melnet_prep": [vp, vp, i32, i32, i32, i32, i32, vp],
         "ma3_melnet_mag": [vp, i64, vp, i32, i32, i32, i32, vp],
         "ma3_melnet_log": [vp, vp, i32, i32, i32, vp],
@@ -292,6 +293,18 @@ def split_weight(w):
     w = w.detach().float()
     hi = w.to(torch.bfloat16)
     return torch.cat([hi, (w - hi.float()).to(torch.bfloat16)]).contiguous()
+
+
+def qknorm_rope(x, *, first_section, qn, kn, rope, q_out, k_out, vt_out, tokens, tokens_pad, D, hd, hdp, q_scale=1.0,
+                eps=1e-5):
+    """x fp32 [M, sections*D] raw projections -> LayerNorm(q), LayerNorm(k), RoPE, scale, scatter (qk_norm=True path).
+    qn / kn: (weight, bias) fp32 or None."""
+    M = x.shape[0]
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    qw, qb = qn if qn is not None else (None, None)
+    kw, kb = kn if kn is not None else (None, None)
+    _call("ma3_qknorm_rope", L.ptr(x), x.stride(0), first_section, L.ptr(qw), L.ptr(qb), L.ptr(kw), L.ptr(kb), eps,
+          L.ptr(rope), L.ptr(q_out), L.ptr(k_out), L.ptr(vt_out), L.dt(k_out), M, tokens, tokens_pad, D, hd, hdp, q_scale)
 
 
 def cast(x, out):

@@ -382,3 +382,25 @@ def test_melnet_golden_and_long():
     assert got2.shape == (2, 80, 624) and float((got2 - ref).abs().max()) < 2e-2
     with pytest.raises(NotImplementedError):
         net(y[:1], center=True)
+
+
+# ------------------------------------------------------------------------------------------------ round 2: QK-norm
+def test_dit_qk_norm_golden():
+    """qk_norm=True (flag_large_dit_moe.py:199-207,345-352): LayerNorm over the full model dim of q, k and the cross k,
+    against the reference-generated golden and the oracle at another shape / other timesteps."""
+    import os
+    from ma3_b200 import dit as D
+    g2 = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden_r02.pt"))
+    cfg = Cs.DIT_SMALL
+    sd = W.dit_state_dict(**cfg, seed=9, qk_norm=True)
+    m = D.TxtFlagLargeDiT(cfg["in_channels"], cfg["context_dim"], hidden_size=cfg["hidden_size"], depth=cfg["depth"],
+                          num_heads=cfg["num_heads"], max_len=100, qk_norm=True)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    x, ctx = Cs.dit_inputs(cfg)
+    out = m(x.cuda(), torch.tensor([41, 958]).cuda(), context=ctx.cuda())
+    assert O.max_rel_err(out.cpu(), g2["dit_small_qknorm"]) < 1e-2
+    x2, ctx2 = Cs.dit_inputs(cfg, N=3, T=50, L=7, seed=21)
+    t2 = torch.tensor([0, 500, 999])
+    ref = O.dit_forward(sd, x2, t2, ctx2, heads=cfg["num_heads"], max_len=100)
+    assert O.max_rel_err(m(x2.cuda(), t2.cuda(), context=ctx2.cuda()).cpu(), ref) < 1e-2
