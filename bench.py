@@ -441,12 +441,16 @@ def main():
                         "frac": ach / peak, "traffic": None,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
                         "launches": n, "avg_launch_us": 1e3 * ms / n, "bytes_per_launch": work / n}
-        # DRAM traffic per launch of that family from the committed ncu --set full capture, when there is one
+        # DRAM traffic per launch of that family from this round's ncu --set full captures (tools/profile_r02.sh ->
+        # tools/ncu_summarise.py --traffic): for the tap-GEMM family the launch-weighted mean over its DiT members
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
-            if tr:
-                roofline["traffic"] = tr["bytes_per_launch"]
-                roofline["traffic_source"] = tr["source"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            fams = {"tap_gemm": ["tap_gemm", "rownorm"]}.get(name, [name])
+            caps = [c for f in fams if f in tj for c in tj[f]["captures"]]
+            if caps:
+                roofline["traffic"] = sum(c["dram_bytes"] for c in caps) / len(caps)
+                roofline["traffic_by_kernel"] = {c["kernel"][:60] + f" ({c['gpu_time_us']:.0f} us)": c["dram_bytes"] for c in caps}
+                roofline["traffic_source"] = "; ".join(tj[f]["source"] for f in fams if f in tj)
         except Exception:
             pass
         # secondary: the HBM-bound vocoder activation kernel the north_star singles out

@@ -26,7 +26,7 @@ cap() {  # name, kernel regex, skip, count
 }
 cap attn attn2_kernel 4 1
 cap rownorm rowgemm_norm 8 2          # wo (K=1152) and w2 (K=3072) of one block
-cap gemm "tap_gemm_kernel<\(int\)[23]" 12 2   # QKV+RoPE and w1|w3+SwiGLU of one block
+cap gemm tap_gemm_kernel 13 2          # QKV+RoPE and w1|w3+SwiGLU of one block (after the conditioning GEMMs)
 cap rms rmsnorm_modulate 2 1
 # vocoder kernels from the bench driver (graph-free)
 ncu --set full --clock-control none --import-source on -k regex:act1d_mma -s 40 -c 2 -o gpurun_out/r02_prof_act1d $BENCH > gpurun_out/r02_ncu_act1d.log 2>&1
