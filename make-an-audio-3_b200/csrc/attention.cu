@@ -19,6 +19,7 @@ constexpr int kAttnThreads = 160;
 
 struct AttnParams {
   CUtensorMap tmQ, tmK, tmVt, tmKy, tmVyt;
+  CUtensorMap tmVt2, tmVyt2;   // BKV = 80: keys 64..79 of a V^T tile (16 keys = 32-byte rows, 32B swizzle)
   int T, L, H, D;  // D = H * hd (row pitch of out)
   void* out;
   const float* gate;
@@ -494,7 +495,11 @@ __device__ __forceinline__ void rescale_cols(uint32_t tO, float alpha) {
 
 template <int HDP, int HD, int BKV>
 __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_constant__ AttnParams p) {
-  static_assert(BKV == 64, "one 64-key chunk per KV tile");
+  // BKV = 64: one 64-key chunk per KV tile.  BKV = 80: 312 latent tokens are 4 tiles instead of 5 and 154 context tokens 2
+  // instead of 3 (6 KV tiles per CTA instead of 8: the per-tile synchronisation chain is the cost, not the MMAs); the 16
+  // extra keys of V^T live in a second, 32B-swizzled chunk and each softmax thread owns 40 keys instead of 32.
+  static_assert(BKV == 64 || BKV == 80, "KV tile of 64 or 80 keys");
+  constexpr int CPT = BKV / 2;                   // S columns (keys) per softmax thread
   constexpr int HDC = HDP / 64;
   constexpr int HDO = (HD + 1 + 15) / 16 * 16;   // O columns: HD values, the row-sum column, zero padding
   constexpr int KS = (HD + 15) / 16;             // k-steps of S = Q K^T that carry data (pad columns are zero)
@@ -504,9 +509,11 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
   constexpr int NSTASH = HSPLIT / 2;
   constexpr uint32_t kQBytes = 128 * HDP * 2;
   constexpr uint32_t kKBytes = BKV * HDP * 2;
-  constexpr uint32_t kVBytes = HDO * 128;        // only the HDO rows of V^T the PV MMA reads are staged
+  constexpr uint32_t kV1Bytes = HDO * 128;       // only the HDO rows of V^T the PV MMA reads are staged (keys 0..63)
+  constexpr uint32_t kV2Bytes = BKV > 64 ? HDO * 32 : 0;   // keys 64..79
+  constexpr uint32_t kVBytes = kV1Bytes + kV2Bytes;
   constexpr uint32_t kStageBytes = kKBytes + kVBytes;
-  constexpr uint32_t kTmemCols = 256;            // S0: [0, 64)  S1: [64, 128)  O: [128, 128 + HDO)
+  constexpr uint32_t kTmemCols = 256;            // S0: [0, BKV)  S1: [BKV, 2 BKV)  O: [2 BKV, 2 BKV + HDO)
   static_assert(2 * BKV + HDO <= 256, "TMEM budget");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -573,6 +580,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
           tma_load_3d(dK + c * (BKV * 128), cross ? &p.tmKy : &p.tmK, &k_full[i], c * 64, kv0, bh);
         mbar_arrive_expect_tx(&v_full[i], kVBytes);
         tma_load_3d(dK + kKBytes, cross ? &p.tmVyt : &p.tmVt, &v_full[i], kv0, 0, bh);
+        if constexpr (BKV > 64)
+          tma_load_3d(dK + kKBytes + kV1Bytes, cross ? &p.tmVyt2 : &p.tmVt2, &v_full[i], kv0 + 64, 0, bh);
       }
     }
     __syncwarp();
@@ -605,6 +614,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
         uint8_t* dV = sKV + st * kStageBytes + kKBytes;
         mbar_arrive_expect_tx(&v_full[st], kVBytes);
         tma_load_3d(dV, cross ? &p.tmVyt : &p.tmVt, &v_full[st], kv0, 0, bh);
+        if constexpr (BKV > 64) tma_load_3d(dV + kV1Bytes, cross ? &p.tmVyt2 : &p.tmVt2, &v_full[st], kv0 + 64, 0, bh);
       };
       const uint32_t idesc_s = umma_idesc(128, BKV, p.dtype == MA3_BF16 ? 1 : 0);
       const uint32_t idesc_o = umma_idesc(128, HDO, p.dtype == MA3_BF16 ? 1 : 0);
@@ -614,6 +624,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
       const uint32_t dhi = (uint32_t)(dq0 >> 32), q_lo = (uint32_t)dq0;
       const uint32_t k_lo = (uint32_t)umma_desc_kmajor(smem_u32(sKV), 128);
       const uint32_t v_lo = (uint32_t)umma_desc_kmajor(smem_u32(sKV + kKBytes), 128);
+      const uint64_t dv2 = umma_desc_kmajor(smem_u32(sKV + kKBytes + kV1Bytes), 32);   // 32B-swizzled chunk of keys 64..79
+      const uint32_t v2_lo = (uint32_t)dv2, dhi32 = (uint32_t)(dv2 >> 32);
       auto issue_s = [&](int i) {
         const int st = i & 1;
         mbar_wait(&k_full[st], (i >> 1) & 1);
@@ -642,12 +654,14 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
         tc_fence_after();
         const uint32_t dv = v_lo + (uint32_t)st * (kStageBytes >> 4);
         const uint32_t fresh = (i == 0 || i == n_self) ? 0u : 1u;   // first tile of a segment overwrites O
-        // P(i) lives in tensor memory, packed two keys per column over the first 32 columns of S buffer st
+        // P(i) lives in tensor memory, packed two keys per column over the first BKV / 2 columns of S buffer st
         const uint32_t tP = tmem_S + st * BKV;
         umma_f16_ts(tmem_O, tP, dv, dhi, idesc_o, fresh);
         umma_f16_ts(tmem_O, tP + 8, dv + 2, dhi, idesc_o, 1u);
         umma_f16_ts(tmem_O, tP + 16, dv + 4, dhi, idesc_o, 1u);
         umma_f16_ts(tmem_O, tP + 24, dv + 6, dhi, idesc_o, 1u);
+        if constexpr (BKV > 64)
+          umma_f16_ts(tmem_O, tP + 32, v2_lo + (uint32_t)st * (kStageBytes >> 4), dhi32, idesc_o, 1u);
         umma_commit(o_full);
         umma_commit(&v_empty[st]);
         attn_trace(p, i, 10);
@@ -682,20 +696,21 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
         mbar_wait(&s_full[it & 1], (it >> 1) & 1);
         if (tr) attn_trace(p, it, 1);
         tc_fence_after();
-        uint32_t s[32];
-        tmem_ld_n<32>(tmem_S + (it & 1) * BKV + half * 32 + lane_base, s);
+        uint32_t s[CPT];
+        tmem_ld_n<32>(tmem_S + (it & 1) * BKV + half * CPT + lane_base, s);
+        if constexpr (CPT > 32) tmem_ld_n<8>(tmem_S + (it & 1) * BKV + half * CPT + 32 + lane_base, s + 32);
         tmem_ld_wait();
-        const int valid = kvlen - j * BKV - half * 32;   // keys of this thread's half that exist
-        if (valid < 32) {   // ragged last tile of a segment: keys beyond the sequence get -inf
+        const int valid = kvlen - j * BKV - half * CPT;   // keys of this thread's half that exist
+        if (valid < CPT) {   // ragged last tile of a segment: keys beyond the sequence get -inf
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
+          for (int e = 0; e < CPT; ++e)
             if (e >= valid) s[e] = 0xff800000u;
         }
         float mx4[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 4]));
 #pragma unroll
-        for (int e = 8; e < 32; e += 8) {
+        for (int e = 8; e < CPT; e += 8) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) mx4[c] = fmax3(mx4[c], __uint_as_float(s[e + c]), __uint_as_float(s[e + c + 4]));
         }
@@ -719,17 +734,17 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
           m = m_new;
         }
         if (tr) attn_trace(p, it, 3);
-        uint32_t pk[16];
+        uint32_t pk[CPT / 2];
         const float2 nm = make_float2(-m, -m);
         if (bf16) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+          for (int e = 0; e < CPT; e += 2) {
             const float2 d = fadd2(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), nm);
             pk[e >> 1] = pack_bf16(ex2_approx(d.x), ex2_approx(d.y));
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+          for (int e = 0; e < CPT; e += 2) {
             const float2 d = fadd2(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), nm);
             pk[e >> 1] = pack_f16(ex2_approx(d.x), ex2_approx(d.y));
           }
@@ -739,7 +754,9 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
         // barrier above orders the partner's S load before this store): 16 packed columns per thread, read by the PV
         // MMA as its A operand.  No shared-memory tile, no async-proxy fence; S(it+2), which overwrites this buffer,
         // is issued after PV(it) and the tensor pipe executes in issue order.
-        tmem_st16(tmem_S + (it & 1) * BKV + half * 16 + lane_base, pk);
+        tmem_st16(tmem_S + (it & 1) * BKV + half * (CPT / 2) + lane_base, *reinterpret_cast<uint32_t(*)[16]>(pk));
+        if constexpr (CPT > 32)
+          tmem_st4(tmem_S + (it & 1) * BKV + half * (CPT / 2) + 16 + lane_base, *reinterpret_cast<uint32_t(*)[4]>(pk + 16));
         tmem_st_wait();
         // Every warp observes every phase of o_full, in order, before it arrives for the next tile: a parity wait is
         // only meaningful when the waiter is at most one phase behind, and the waits of the correction path and of the
@@ -788,7 +805,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
 template <int HDP, int HD, int BKV>
 static int launch_attn2(const AttnParams& p, int NS, cudaStream_t st) {
   constexpr int HDO = (HD + 1 + 15) / 16 * 16;
-  constexpr size_t smem = 128 * HDP * 2 + 2 * (BKV * HDP * 2 + HDO * 128) + 128 + 2048;
+  constexpr size_t smem = 128 * HDP * 2 + 2 * (BKV * HDP * 2 + HDO * 128 + (BKV > 64 ? HDO * 32 : 0)) + 128 + 2048;
   static DeviceOnce configured;
   if (configured.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn2_kernel<HDP, HD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -837,7 +854,6 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
   memset(&p, 0, sizeof(p));
   p.T = T; p.L = L; p.H = H; p.D = H * hd; p.out = out; p.gate = gate; p.dtype = dtype;
   p.trace = g_trace;
-  const int BKV = 64;
   const uint64_t nbh = (uint64_t)NS * H;
   int rc;
   // v2 (O resident in TMEM, row sums through the ones row of V^T) whenever the padded head has a spare row;
@@ -846,6 +862,13 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
   const bool v2 = !force_v1 && ((hdp == 64 && (hd == 16 || hd == 24 || hd == 32 || hd == 48)) ||
                                 (hdp == 128 && (hd == 72 || hd == 96)));
   const uint32_t vrows = v2 ? (uint32_t)((hd + 1 + 15) / 16 * 16) : (uint32_t)hdp;   // V^T rows staged per tile
+  // KV tile of 80 keys when that saves tiles (the per-tile synchronisation chain is the cost): 312 + 154 tokens are
+  // 4 + 2 tiles of 80 against 5 + 3 of 64.  A tile of 80 costs ~1.1x a tile of 64.  MA3_ATTN_BKV=64|80 forces one.
+  static const int force_bkv = getenv("MA3_ATTN_BKV") ? atoi(getenv("MA3_ATTN_BKV")) : 0;
+  const int t64 = (T + 63) / 64 + (L + 63) / 64, t80 = (T + 79) / 80 + (L + 79) / 80;
+  int BKV = (v2 && 11 * t80 < 10 * t64 && 2 * 80 + (int)vrows <= 256) ? 80 : 64;
+  if (v2 && force_bkv == 64) BKV = 64;
+  if (v2 && force_bkv == 80 && 2 * 80 + (int)vrows <= 256) BKV = 80;
   {
     uint64_t dims[3] = {(uint64_t)hdp, (uint64_t)T, nbh};
     uint64_t str[2] = {(uint64_t)hdp * 2, (uint64_t)T * hdp * 2};
@@ -858,6 +881,8 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
     uint64_t str[2] = {(uint64_t)Tp * 2, (uint64_t)hdp * Tp * 2};
     uint32_t box[3] = {64, vrows, 1};
     if ((rc = encode_tmap(&p.tmVt, vt, 2, 3, dims, str, box, 128))) return rc;
+    uint32_t box2[3] = {16, vrows, 1};
+    if (BKV > 64 && (rc = encode_tmap(&p.tmVt2, vt, 2, 3, dims, str, box2, 32))) return rc;
   }
   if (L > 0) {
     uint64_t dims[3] = {(uint64_t)hdp, (uint64_t)L, nbh};
@@ -868,11 +893,21 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
     uint64_t strv[2] = {(uint64_t)Lp * 2, (uint64_t)hdp * Lp * 2};
     uint32_t boxv[3] = {64, vrows, 1};
     if ((rc = encode_tmap(&p.tmVyt, vyt, 2, 3, dimv, strv, boxv, 128))) return rc;
+    uint32_t boxv2[3] = {16, vrows, 1};
+    if (BKV > 64 && (rc = encode_tmap(&p.tmVyt2, vyt, 2, 3, dimv, strv, boxv2, 32))) return rc;
   } else {
     p.tmKy = p.tmK;
     p.tmVyt = p.tmVt;
+    p.tmVyt2 = p.tmVt2;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (v2 && BKV == 80) {
+    if (hdp == 64 && hd == 16) return launch_attn2<64, 16, 80>(p, NS, st);
+    if (hdp == 64 && hd == 24) return launch_attn2<64, 24, 80>(p, NS, st);
+    if (hdp == 64 && hd == 32) return launch_attn2<64, 32, 80>(p, NS, st);
+    if (hdp == 64 && hd == 48) return launch_attn2<64, 48, 80>(p, NS, st);
+    if (hdp == 128 && hd == 72) return launch_attn2<128, 72, 80>(p, NS, st);
+  }
   if (v2) {
     if (hdp == 64 && hd == 16) return launch_attn2<64, 16, 64>(p, NS, st);
     if (hdp == 64 && hd == 24) return launch_attn2<64, 24, 64>(p, NS, st);
