@@ -142,6 +142,9 @@ int ma3_debug_set_gemm_trace(void* buf);
  * releases stages without issuing MMAs.  Isolates the feed side from the tensor side of the mainloop; the output of
  * later ma3_gemm calls is garbage until mode 0 is restored (tools/probe_trace.py). */
 int ma3_debug_set_gemm_mode(int mode);
+/* Attention kernel generation: 0 = default, 2 / 3 = force v2 / v3 (v3: several query tiles of a head per CTA; kept as a
+ * measured alternative).  Diagnostics and tests only. */
+int ma3_debug_set_attn_version(int v);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused flash attention of one Next-DiT block: self-attention over the T latent tokens plus tanh-gated

@@ -25,6 +25,7 @@ struct AttnParams {
   const float* gate;
   int dtype;
   long long* trace;  // diagnostics (CTA 0 records clock64 at pipeline events when non-null)
+  int stagger;       // v3: clocks by which consecutive contexts start their first tile apart
 };
 
 __device__ __forceinline__ void attn_trace(const AttnParams& p, int it, int slot) {
@@ -802,6 +803,356 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ v3 kernel
+// One CTA per (sample, head, group of NCTX consecutive 128-query tiles), one CTA per SM, all of tensor memory.
+// The v2 kernel runs at a quarter of its MUFU / issue floor: a CTA is one latency chain per KV tile (S -> max ->
+// partner exchange -> exp -> P -> PV -> next S), TMEM caps an SM at two such CTAs, every CTA pays its own prologue and
+// re-loads K / V^T, and a ragged last query tile costs a whole CTA.  Here the NCTX query tiles of a head are NCTX
+// independent softmax streams inside one CTA that share every K / V^T tile (loaded once per head instead of once per
+// query tile); a softmax thread owns a whole query row of an 80-key tile (no partner exchange, no named barriers, 80
+// exponentials per ~800 clocks of per-tile synchronisation instead of 40); and every context has its own MMA-issuing
+// warp, so the PV -> next-S turnaround of one context (S is single-buffered: 3 x (80 S/P + 80 O) = 480 columns) is
+// ~400 clocks during which the other two contexts own the MUFU pipe.
+//   warps [0, 4 NCTX):        softmax, warp w <-> context w / 4, TMEM lane quarter w % 4
+//   warp 4 NCTX:              TMA producer (Q tiles, K ring, V^T ring)
+//   warps 4 NCTX + 1 + c:     MMA issue for context c (one elected lane each; the first one owns the TMEM allocation)
+// Lazy rescaling, P written back over the consumed S columns as the TMEM A operand of PV, row sums from the ones row
+// of V^T, keys 64..79 of V^T as a 32B-swizzled chunk: as in v2.  The normalised self-attention result is parked in the
+// output row (16-bit) across the cross segment and read back by the same thread at the end.
+template <int HDP, int HD, int NCTX>
+__global__ void __launch_bounds__(NCTX * 128 + 32 + NCTX * 32, 1) attn3_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int BKV = 80;
+  constexpr int NST = 3;                         // K / V^T stages
+  constexpr int HDC = HDP / 64;
+  constexpr int HDO = (HD + 1 + 15) / 16 * 16;
+  constexpr int KS = (HD + 15) / 16;
+  constexpr int CW = BKV + HDO;                  // TMEM columns of one context: S / P [0, 80)  O [80, 80 + HDO)
+  static_assert(NCTX * CW <= 512, "TMEM budget");
+  static_assert(HDO <= HDP, "needs a spare V^T row for the row sums");
+  constexpr uint32_t kQBytes = 128 * HDP * 2;
+  constexpr uint32_t kKBytes = BKV * HDP * 2;
+  constexpr uint32_t kV1Bytes = HDO * 128;       // keys 0..63 of a V^T tile (128B swizzle)
+  constexpr uint32_t kV2Bytes = HDO * 32;        // keys 64..79 (32B swizzle)
+  constexpr uint32_t kVBytes = kV1Bytes + kV2Bytes;
+  constexpr uint32_t kStageBytes = (kKBytes + kVBytes + 1023) / 1024 * 1024;
+  constexpr int kSoftWarps = 4 * NCTX;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sQ = smem_raw;
+  uint8_t* sKV = sQ + NCTX * kQBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NST * kStageBytes);
+  uint64_t* q_full = bars;                  // NCTX (one per query tile, so that context 0 starts on its own tile)
+  uint64_t* k_full = q_full + NCTX;         // NST
+  uint64_t* k_empty = k_full + NST;         // NST, one commit per active context
+  uint64_t* v_full = k_empty + NST;         // NST
+  uint64_t* v_empty = v_full + NST;         // NST, one commit per active context
+  uint64_t* s_full = v_empty + NST;         // NCTX: phase i completes with S(c, i)
+  uint64_t* p_full = s_full + NCTX;         // NCTX: P(c, i) is in TMEM (one arrival per active softmax warp)
+  uint64_t* pv_done = p_full + NCTX;        // NCTX: phase i completes with PV(c, i)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + NCTX);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt0 = blockIdx.x * NCTX, h = blockIdx.y, ns = blockIdx.z;
+  const int bh = ns * p.H + h;
+  const int n_self = (p.T + BKV - 1) / BKV, n_cross = (p.L + BKV - 1) / BKV;   // KV tiles per segment
+  const int n_tiles = n_self + n_cross;
+  const int n_ctx = min(NCTX, (p.T + 127) / 128 - qt0);   // contexts owning at least one query row
+  long long* cta_rec = nullptr;
+  if (p.trace && threadIdx.x == 0) {
+    cta_rec = p.trace + 256 + 4 * ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+    unsigned smid;
+    unsigned long long t0;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    cta_rec[0] = smid;
+    cta_rec[1] = (long long)t0;
+    cta_rec[3] = clock64();
+  }
+
+  if (warp == kSoftWarps && lane == 0) {
+    prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmVt); prefetch_tmap(&p.tmVt2);
+    prefetch_tmap(&p.tmKy); prefetch_tmap(&p.tmVyt); prefetch_tmap(&p.tmVyt2);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], n_ctx);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], n_ctx);
+    }
+    for (int c = 0; c < NCTX; ++c) {
+      const int nw = max(1, min(4, (p.T - (qt0 + c) * 128 + 31) / 32));
+      mbar_init(&q_full[c], 1);
+      mbar_init(&s_full[c], 1);
+      mbar_init(&p_full[c], nw);
+      mbar_init(&pv_done[c], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kSoftWarps + 1) tmem_alloc(tmem_slot, 512);
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == kSoftWarps) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      auto load_q = [&](int c) {
+        mbar_arrive_expect_tx(&q_full[c], kQBytes);
+#pragma unroll
+        for (int ch = 0; ch < HDC; ++ch)
+          tma_load_3d(sQ + c * kQBytes + ch * (128 * 128), &p.tmQ, &q_full[c], ch * 64, (qt0 + c) * 128, bh);
+      };
+      load_q(0);
+      int st = 0, ph = 0;   // ring position; ph = parity of the stage's current use
+      for (int g = 0; g < n_tiles; ++g) {
+        const bool cross = g >= n_self;
+        const int kv0 = (cross ? g - n_self : g) * BKV;
+        uint8_t* dK = sKV + st * kStageBytes;
+        if (g >= NST) mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], kKBytes);
+#pragma unroll
+        for (int ch = 0; ch < HDC; ++ch)
+          tma_load_3d(dK + ch * (BKV * 128), cross ? &p.tmKy : &p.tmK, &k_full[st], ch * 64, kv0, bh);
+        if (g == 0)
+          for (int c = 1; c < n_ctx; ++c) load_q(c);
+        if (g >= NST) mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], kVBytes);
+        tma_load_3d(dK + kKBytes, cross ? &p.tmVyt : &p.tmVt, &v_full[st], kv0, 0, bh);
+        tma_load_3d(dK + kKBytes + kV1Bytes, cross ? &p.tmVyt2 : &p.tmVt2, &v_full[st], kv0 + 64, 0, bh);
+        if (++st == NST) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp > kSoftWarps) {
+    // ---------------------------------------------------------------- MMA issue, one warp (one elected lane) per context
+    // (A single thread polling all contexts reacted ~1000 clocks late: a lone warp runs its dependent instruction stream at
+    // a fraction of an instruction per clock.  Per context the events come in a fixed order, so each issuing thread
+    // simply blocks on the next one.)
+    const int c = warp - kSoftWarps - 1;
+    if (c < n_ctx && elect_one()) {
+      const uint32_t idesc_s = umma_idesc(128, BKV, p.dtype == MA3_BF16 ? 1 : 0);
+      const uint32_t idesc_o = umma_idesc(128, HDO, p.dtype == MA3_BF16 ? 1 : 0);
+      const uint64_t dq0 = umma_desc_kmajor(smem_u32(sQ + c * kQBytes), 128);
+      const uint32_t dhi = (uint32_t)(dq0 >> 32), a_lo = (uint32_t)dq0;
+      const uint32_t k_lo = (uint32_t)umma_desc_kmajor(smem_u32(sKV), 128);
+      const uint32_t v_lo = (uint32_t)umma_desc_kmajor(smem_u32(sKV + kKBytes), 128);
+      const uint64_t dv2 = umma_desc_kmajor(smem_u32(sKV + kKBytes + kV1Bytes), 32);
+      const uint32_t v2_lo = (uint32_t)dv2, dhi32 = (uint32_t)(dv2 >> 32);
+      const uint32_t tS = tmem_base + c * CW, tO = tS + BKV;
+      const bool trm = p.trace && n_tiles <= 16 && (c == 0 || c == 2) && blockIdx.x + blockIdx.y + blockIdx.z == 0;
+      auto issue_s = [&](int it, int st, int ph) {
+        mbar_wait(&k_full[st], ph);
+        tc_fence_after();
+        const uint32_t b_lo = k_lo + (uint32_t)st * (kStageBytes >> 4);
+#pragma unroll
+        for (int k = 0; k < KS; ++k)
+          umma_f16_lohi<1>(tS, a_lo + (uint32_t)((k / 4) * (128 * 128 / 16) + (k % 4) * 2),
+                           b_lo + (uint32_t)((k / 4) * (BKV * 128 / 16) + (k % 4) * 2), dhi, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[c]);
+        umma_commit(&k_empty[st]);
+        if (trm) p.trace[it * 16 + 8 + c] = clock64();
+      };
+      mbar_wait(&q_full[c], 0);
+      issue_s(0, 0, 0);
+      int st = 0, ph = 0;          // ring stage of tile it and the parity of that use
+      for (int it = 0; it < n_tiles; ++it) {
+        mbar_wait(&p_full[c], it & 1);     // P(c, it) written over the S columns
+        mbar_wait(&v_full[st], ph);
+        tc_fence_after();
+        const uint32_t dv = v_lo + (uint32_t)st * (kStageBytes >> 4);
+        const uint32_t fresh = (it == 0 || it == n_self) ? 0u : 1u;   // first tile of a segment overwrites O
+        umma_f16_ts(tO, tS, dv, dhi, idesc_o, fresh);
+        umma_f16_ts(tO, tS + 8, dv + 2, dhi, idesc_o, 1u);
+        umma_f16_ts(tO, tS + 16, dv + 4, dhi, idesc_o, 1u);
+        umma_f16_ts(tO, tS + 24, dv + 6, dhi, idesc_o, 1u);
+        umma_f16_ts(tO, tS + 32, v2_lo + (uint32_t)st * (kStageBytes >> 4), dhi32, idesc_o, 1u);
+        umma_commit(&pv_done[c]);
+        umma_commit(&v_empty[st]);
+        if (trm) p.trace[it * 16 + 9 + c] = clock64();
+        if (++st == NST) { st = 0; ph ^= 1; }
+        if (it + 1 < n_tiles) {
+          // S(c, it + 1) overwrites the columns PV(c, it) reads P from, and the tensor pipe does not order those TMEM
+          // A-operand reads against a later MMA: wait for the completion
+          mbar_wait(&pv_done[c], it & 1);
+          issue_s(it + 1, st, ph);
+        }
+      }
+    }
+  } else if (warp < 4 * n_ctx && (warp & 3) * 32 < p.T - (qt0 + (warp >> 2)) * 128) {
+    // ---------------------------------------------------------------- softmax: thread <-> query row
+    const int c = warp >> 2, qw = warp & 3;
+    const int q0 = (qt0 + c) * 128;
+    const int row = qw * 32 + lane;
+    const uint32_t tS = tmem_base + c * CW + ((uint32_t)(qw * 32) << 16);
+    const uint32_t tO = tS + BKV;
+    const bool bf16 = p.dtype == MA3_BF16;
+    const bool tr = p.trace != nullptr && n_tiles <= 16 && warp == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 &&
+                    blockIdx.z == 0;
+    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + ((long long)ns * p.T + q0 + row) * p.D + (long long)h * HD;
+    const bool row_ok = q0 + row < p.T;
+    float m = 0.f;
+    for (int it = 0; it < n_tiles; ++it) {
+      const bool cross = it >= n_self;
+      const int j = cross ? it - n_self : it;
+      const int valid = (cross ? p.L : p.T) - j * BKV;   // keys of this tile that exist
+      if (tr) p.trace[it * 16 + 0] = clock64();
+      mbar_wait(&s_full[c], it & 1);
+      if (it == 0 && c > 0 && p.stagger > 0) {
+        const long long t_go = clock64() + (long long)c * p.stagger;
+        while (clock64() < t_go) {
+        }
+      }
+      tc_fence_after();
+      if (tr) p.trace[it * 16 + 1] = clock64();
+      uint32_t s[BKV];
+      tmem_ld_n<32>(tS, s);
+      tmem_ld_n<32>(tS + 32, s + 32);
+      tmem_ld_n<16>(tS + 64, s + 64);
+      // every phase of pv_done is observed in order (a parity wait is only meaningful one phase back); S(c, it) was
+      // issued after PV(c, it - 1) completed, so this never spins
+      if (it > 0) mbar_wait(&pv_done[c], (it - 1) & 1);
+      if (cross && j == 0 && n_self > 0) {
+        // segment switch: the self-attention O is final.  Park it, normalised, in the output row (16-bit, as it is
+        // rounded on output anyway) before PV(c, it) overwrites O; the same thread adds the cross part at the end.
+        uint32_t rl[8];
+        tmem_ld8(tO + (HD / 8) * 8, rl);
+        tmem_ld_wait();
+        const float f = __fdividef(1.f, __uint_as_float(rl[HD % 8]));
+#pragma unroll
+        for (int c0 = 0; c0 < HD; c0 += 8) {
+          uint32_t r[8];
+          tmem_ld8(tO + c0, r);
+          tmem_ld_wait();
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[e]) * f;
+          const uint4 u = bf16 ? make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]))
+                               : make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
+          if (row_ok) *reinterpret_cast<uint4*>(orow + c0) = u;
+        }
+      }
+      tmem_ld_wait();
+      if (valid < BKV) {
+#pragma unroll
+        for (int e = 0; e < BKV; ++e)
+          if (e >= valid) s[e] = 0xff800000u;
+      }
+      float mx4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mx4[q] = fmaxf(__uint_as_float(s[q]), __uint_as_float(s[q + 4]));
+#pragma unroll
+      for (int e = 8; e < BKV; e += 8) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mx4[q] = fmax3(mx4[q], __uint_as_float(s[e + q]), __uint_as_float(s[e + q + 4]));
+      }
+      const float mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]);
+      if (tr) p.trace[it * 16 + 2] = clock64();
+      if (j == 0) {
+        m = mx;
+      } else if (__any_sync(0xffffffffu, mx > m + 8.f)) {
+        // PV(c, it - 1) has completed (see above): O may be modified in place
+        const float m_new = fmaxf(m, mx);
+        rescale_cols<0, HDO>(tO, ex2_approx(m - m_new));
+        tmem_st_wait();
+        m = m_new;
+      }
+      if (tr) p.trace[it * 16 + 3] = clock64();
+      // p = 2^(s - m), 16 keys (8 packed columns) at a time, written back over the S columns this thread has consumed:
+      // the TMEM A operand of PV(c, it).  16-key groups beyond the sequence cost no exponentials.
+      const float2 nm = make_float2(-m, -m);
+#pragma unroll
+      for (int g = 0; g < BKV; g += 16) {
+        uint32_t pk[8];
+        if (g < valid) {
+          if (bf16) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const float2 d = fadd2(make_float2(__uint_as_float(s[g + e]), __uint_as_float(s[g + e + 1])), nm);
+              pk[e >> 1] = pack_bf16(ex2_approx(d.x), ex2_approx(d.y));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const float2 d = fadd2(make_float2(__uint_as_float(s[g + e]), __uint_as_float(s[g + e + 1])), nm);
+              pk[e >> 1] = pack_f16(ex2_approx(d.x), ex2_approx(d.y));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pk[e] = 0u;
+        }
+        tmem_st8(tS + g / 2, pk);
+      }
+      if (tr) p.trace[it * 16 + 4] = clock64();
+      tmem_st_wait();
+      if (tr) p.trace[it * 16 + 5] = clock64();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[c]);
+      if (tr) p.trace[it * 16 + 6] = clock64();
+    }
+    // epilogue: out = parked self part + tanh(gate) * cross part / its row sum
+    uint4 prev[HD / 8];
+    const bool two = n_self > 0 && n_cross > 0;
+#pragma unroll
+    for (int e = 0; e < HD / 8; ++e) prev[e] = (two && row_ok) ? *reinterpret_cast<const uint4*>(orow + 8 * e) : make_uint4(0u, 0u, 0u, 0u);
+    mbar_wait(&pv_done[c], (n_tiles - 1) & 1);
+    tc_fence_after();
+    uint32_t rl[8];
+    tmem_ld8(tO + (HD / 8) * 8, rl);
+    tmem_ld_wait();
+    const float f = __fdividef(n_cross > 0 ? tanhf(p.gate[h]) : 1.f, __uint_as_float(rl[HD % 8]));
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 8) {
+      uint32_t r[8];
+      tmem_ld8(tO + c0, r);
+      tmem_ld_wait();
+      const uint32_t pw[4] = {prev[c0 / 8].x, prev[c0 / 8].y, prev[c0 / 8].z, prev[c0 / 8].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 sv;
+        if (bf16) sv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[e]));
+        else sv = __half22float2(*reinterpret_cast<const __half2*>(&pw[e]));
+        const float v0 = fmaf(__uint_as_float(r[2 * e]), f, sv.x), v1 = fmaf(__uint_as_float(r[2 * e + 1]), f, sv.y);
+        o[e] = bf16 ? pack_bf16(v0, v1) : pack_f16(v0, v1);
+      }
+      if (row_ok) *reinterpret_cast<uint4*>(orow + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (cta_rec) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    cta_rec[2] = (long long)t1;
+    cta_rec[3] = clock64() - cta_rec[3];
+  }
+  if (warp == kSoftWarps + 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int HDP, int HD, int NCTX>
+static int launch_attn3(const AttnParams& p, int NS, cudaStream_t st) {
+  constexpr int HDO = (HD + 1 + 15) / 16 * 16;
+  constexpr size_t stage = ((size_t)80 * HDP * 2 + HDO * 160 + 1023) / 1024 * 1024;
+  constexpr size_t smem = (size_t)NCTX * 128 * HDP * 2 + 3 * stage + (12 + 4 * NCTX) * 8 + 16;
+  static DeviceOnce configured;
+  if (configured.pending()) {
+    cudaError_t e = cudaFuncSetAttribute(attn3_kernel<HDP, HD, NCTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(attn3): %s", cudaGetErrorString(e));
+    configured.mark();
+  }
+  const int nq = (p.T + 127) / 128;
+  dim3 grid((unsigned)((nq + NCTX - 1) / NCTX), (unsigned)p.H, (unsigned)NS);
+  cudaError_t le = launch_pdl(attn3_kernel<HDP, HD, NCTX>, grid, dim3(NCTX * 128 + 32 + NCTX * 32), smem, st, 1, p);
+  if (le != cudaSuccess) MA3_FAIL((int)le, "attention launch: %s", cudaGetErrorString(le));
+  MA3_LAUNCH_CHECK("attention");
+  return 0;
+}
+
 template <int HDP, int HD, int BKV>
 static int launch_attn2(const AttnParams& p, int NS, cudaStream_t st) {
   constexpr int HDO = (HD + 1 + 15) / 16 * 16;
@@ -839,6 +1190,12 @@ static int launch_attn(const AttnParams& p, int NS, cudaStream_t st) {
 
 using namespace ma3;
 
+static int g_attn_version = 0;   // 0 = default (v2 where eligible), 2 / 3 = forced (diagnostics, tests)
+extern "C" int ma3_debug_set_attn_version(int v) {
+  g_attn_version = v;
+  return 0;
+}
+
 // q, k: [NS*H, T, hdp]; vt: [NS*H, hdp, Tp]; ky: [NS*H, L, hdp]; vyt: [NS*H, hdp, Lp]; gate: [H] fp32 (raw, tanh is
 // applied here); out: [NS, T, H*hd] (16-bit, same dtype as the operands).
 extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const void* ky, const void* vyt,
@@ -854,6 +1211,8 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
   memset(&p, 0, sizeof(p));
   p.T = T; p.L = L; p.H = H; p.D = H * hd; p.out = out; p.gate = gate; p.dtype = dtype;
   p.trace = g_trace;
+  static const int stagger = getenv("MA3_ATTN_STAGGER") ? atoi(getenv("MA3_ATTN_STAGGER")) : 0;
+  p.stagger = stagger;
   const uint64_t nbh = (uint64_t)NS * H;
   int rc;
   // v2 (O resident in TMEM, row sums through the ones row of V^T) whenever the padded head has a spare row;
@@ -869,6 +1228,13 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
   int BKV = (v2 && 11 * t80 < 10 * t64 && 2 * 80 + (int)vrows <= 256) ? 80 : 64;
   if (v2 && force_bkv == 64) BKV = 64;
   if (v2 && force_bkv == 80 && 2 * 80 + (int)vrows <= 256) BKV = 80;
+  // v3 (several query tiles of a head per CTA, one softmax thread per row) is opt-in: MA3_ATTN_VER=3 or
+  // ma3_debug_set_attn_version(3).  Measured equal to v2 at the XL shape: its single-buffered S puts
+  // the PV -> S turnaround of the tensor pipe (~1400 clocks) on every context's critical path.
+  static const int env_ver = getenv("MA3_ATTN_VER") ? atoi(getenv("MA3_ATTN_VER")) : 0;
+  const int force_ver = g_attn_version ? g_attn_version : env_ver;
+  const bool v3 = v2 && force_ver == 3;
+  if (v3) BKV = 80;
   {
     uint64_t dims[3] = {(uint64_t)hdp, (uint64_t)T, nbh};
     uint64_t str[2] = {(uint64_t)hdp * 2, (uint64_t)T * hdp * 2};
@@ -901,6 +1267,14 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
     p.tmVyt2 = p.tmVt2;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (v3) {
+    if (hdp == 64 && hd == 16) return launch_attn3<64, 16, 3>(p, NS, st);
+    if (hdp == 64 && hd == 24) return launch_attn3<64, 24, 3>(p, NS, st);
+    if (hdp == 64 && hd == 32) return launch_attn3<64, 32, 3>(p, NS, st);
+    if (hdp == 64 && hd == 48) return launch_attn3<64, 48, 3>(p, NS, st);
+    if (hdp == 128 && hd == 72) return launch_attn3<128, 72, 3>(p, NS, st);
+    if (hdp == 128 && hd == 96) return launch_attn3<128, 96, 2>(p, NS, st);
+  }
   if (v2 && BKV == 80) {
     if (hdp == 64 && hd == 16) return launch_attn2<64, 16, 80>(p, NS, st);
     if (hdp == 64 && hd == 24) return launch_attn2<64, 24, 80>(p, NS, st);

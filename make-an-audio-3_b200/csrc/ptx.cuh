@@ -54,6 +54,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar_addr, uint32_t parity
       : "memory");
   return ok != 0;
 }
+// Non-blocking phase test for polling loops: try_wait may suspend the thread for a system-dependent time when the phase
+// is not complete, which stalls a loop that serves several barriers.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   while (!mbar_try_wait(addr, parity)) {

@@ -6,6 +6,9 @@ through numpy, txt2audio_for_2cap_flow.py:181-188).
 Multi-GPU: prompts are independent, so `shard_prompts` gives rank r the prompts r::world and `gather_waveforms` is the
 only collective (one NCCL all-gather of the finished waveforms).
 """
+import contextlib
+import os
+
 import torch
 
 from . import lib as L
@@ -25,6 +28,24 @@ MODEL_CONFIGS = {
 # first_stage_config.params.ddconfig of every shipped config (configs/txt2audio-cfm-cfg.yaml:50-66)
 VAE_DDCONFIG = dict(double_z=True, in_channels=80, out_ch=80, z_channels=20, kernel_size=5, ch=384, ch_mult=[1, 2, 4],
                     num_res_blocks=2, attn_layers=[3], down_layers=[0], dropout=0.0)
+
+
+_NVTX = os.environ.get("MA3_NVTX", "0") == "1"
+
+
+@contextlib.contextmanager
+def stage_range(name):
+    """NVTX range around one stage of the path (the reference has no tracing; MA3_NVTX=1 marks
+    sample_cfg / decode_first_stage / vocode so that a timeline shows the stages by name).  Off by default: a range
+    push / pop is a host call per stage, harmless, but the graph replays need none."""
+    if not _NVTX:
+        yield
+        return
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 class Txt2AudioPipeline:
@@ -104,8 +125,10 @@ class Txt2AudioPipeline:
     def generate(self, cond, uncond, x0, scale=3.0, timesteps=25):
         """cond/uncond [B, L, Cd], x0 [B, 20, T] (device tensors) -> waveforms [B, 2T*hop] on the device."""
         B = x0.shape[0]
-        z, _ = self.sample_cfg(cond, scale, uncond, B, timesteps=timesteps, x_latent=x0)
-        return self.decode_and_vocode(z)
+        with stage_range("ma3.sample_cfg"):
+            z, _ = self.sample_cfg(cond, scale, uncond, B, timesteps=timesteps, x_latent=x0)
+        with stage_range("ma3.decode_first_stage+vocode"):
+            return self.decode_and_vocode(z)
 
     @torch.no_grad()
     def decode_and_vocode(self, z):
@@ -113,7 +136,10 @@ class Txt2AudioPipeline:
         launches of the two stages are captured once per latent shape and replayed (as the sampler does for its step
         loop), so no host launch latency sits between the short kernels of the VAE and of the early vocoder stages."""
         if not self.use_graph:
-            return self.vocoder.vocode_tensor(self.decode_first_stage(z))
+            with stage_range("ma3.decode_first_stage"):
+                mel = self.decode_first_stage(z)
+            with stage_range("ma3.vocode"):
+                return self.vocoder.vocode_tensor(mel)
         key = (tuple(z.shape), id(self.first_stage_model), id(self.vocoder))
         st = self._tail.get(key)
         if st is None:

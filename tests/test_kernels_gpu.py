@@ -257,6 +257,20 @@ def test_qkv_rope_attention(ops, D, H, T, L, Ns):
     assert _qkv_attention_case(ops, D, H, T, L, Ns, seed=20) < 2e-2
 
 
+@pytest.mark.parametrize("D,H,T,L,Ns", [(1152, 16, 312, 154, 2), (768, 16, 936, 154, 1), (768, 32, 256, 40, 2),
+                                        (128, 2, 130, 77, 1), (1536, 16, 312, 154, 1)])
+def test_qkv_rope_attention_v3(ops, D, H, T, L, Ns):
+    """The opt-in third-generation attention kernel (query tiles of a head as contexts of one CTA, one softmax thread per
+    row, per-context MMA warps) against the same oracle; forced through ma3_debug_set_attn_version."""
+    from ma3_b200 import lib as L_
+    lib = L_.require_device()
+    lib.ma3_debug_set_attn_version(3)
+    try:
+        assert _qkv_attention_case(ops, D, H, T, L, Ns, seed=22) < 2e-2
+    finally:
+        lib.ma3_debug_set_attn_version(0)
+
+
 @pytest.mark.parametrize("Ns,H,hd,hdp,reps", [(2, 4, 72, 128, 1), (2, 32, 24, 64, 25)])
 def test_attention_lazy_rescale_large_logits(ops, Ns, H, hd, hdp, reps):
     """Logits with a large, growing spread across KV tiles force the in-TMEM rescale of O (running maximum raised by
