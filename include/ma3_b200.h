@@ -61,7 +61,7 @@ const char* ma3_last_error(void);
  * Epilogues (`epi`):
  *   MA3_EPI_STORE      v = acc (+ bias[n] or bias[m]) (+ res[z,m,n]) ; v = act(alpha*v) ; (+ out_old if accumulate) -> out
  *                      out row = m*out_row_mul + out_row_off (strided rows: transposed-conv phases)
- *   MA3_EPI_GATE_RES   out(f32)[m,n] += gate[(m / rows_per_sample), n] * acc        (flag_large_dit.py:83-91)
+ *   MA3_EPI_GATE_RES   out(f32)[z,m,n] += gate[(m / rows_per_sample), z*gate_batch_stride + n] * acc   (flag_large_dit.py:83-91)
  *   MA3_EPI_SWIGLU     out[m, n/2] = silu(acc[m, n]) * acc[m, n+1], n even         (flag_large_dit_moe.py:484-489;
  *                      w1 rows interleaved with w3 rows in B)
  *   MA3_EPI_QKV_ROPE   columns [0,D) q, [D,2D) k, [2D,3D) v of one fused projection; rotary embedding on q,k
@@ -105,6 +105,8 @@ typedef struct ma3_gemm {
   /* GATE_RES */
   const float* gate;      /* [samples][gate_ld] fp32 */
   int64_t gate_ld;
+  int64_t gate_batch_stride; /* elements added to the gate COLUMN per z (batched column slices of one residual stream:
+                              * the frequency experts of flag_large_dit_moe.py:516-538 as one launch) */
   int32_t rows_per_sample;
   /* QKV_ROPE */
   void* q_out; void* k_out; void* vt_out;   /* operand dtype */

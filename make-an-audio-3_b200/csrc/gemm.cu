@@ -40,7 +40,7 @@ struct GemmKParams {
   int accumulate;
   int vec_ok;
   const float* gate;
-  long long gate_ld;
+  long long gate_ld, gate_batch_stride;
   int rows_per_sample;
   void *q_out, *k_out, *vt_out;
   const float* rope;
@@ -219,14 +219,14 @@ __device__ __forceinline__ void make_row_ctx(const GemmKParams& p, int z, int m0
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
       const int m = m0 + pass * 4 + (lane >> 3);
-      rc.off[pass] = m < p.M ? (long long)m * p.out_ld : -1;
-      rc.aux[pass] = m < p.M ? (long long)fast_div(m, p.inv_rows_per_sample) * p.gate_ld : 0;
+      rc.off[pass] = m < p.M ? (long long)z * p.out_batch_stride + (long long)m * p.out_ld : -1;
+      rc.aux[pass] = m < p.M ? (long long)z * p.gate_batch_stride + (long long)fast_div(m, p.inv_rows_per_sample) * p.gate_ld : 0;
     }
   } else if constexpr (EPI == MA3_EPI_SWIGLU) {
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       const int m = m0 + pass * 16 + (lane >> 1);
-      rc.off[pass] = m < p.M ? (long long)m * p.out_ld : -1;
+      rc.off[pass] = m < p.M ? (long long)z * p.out_batch_stride + (long long)m * p.out_ld : -1;
     }
   } else if constexpr (EPI == MA3_EPI_STORE) {
 #pragma unroll
@@ -1343,7 +1343,7 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   kp.bias = g->bias; kp.bias_per_row = g->bias_per_row;
   kp.res = g->res; kp.res_dtype = g->res_dtype; kp.res_ld = g->res_ld; kp.res_batch_stride = g->res_batch_stride;
   kp.alpha = g->alpha; kp.accumulate = g->accumulate; kp.act = g->act; kp.first_section = g->first_section;
-  kp.gate = g->gate; kp.gate_ld = g->gate_ld; kp.rows_per_sample = g->rows_per_sample;
+  kp.gate = g->gate; kp.gate_ld = g->gate_ld; kp.gate_batch_stride = g->gate_batch_stride; kp.rows_per_sample = g->rows_per_sample;
   kp.q_out = g->q_out; kp.k_out = g->k_out; kp.vt_out = g->vt_out; kp.rope = g->rope;
   kp.model_dim = g->model_dim; kp.head_dim = g->head_dim; kp.head_dim_pad = g->head_dim_pad;
   kp.heads = g->head_dim > 0 ? g->model_dim / g->head_dim : 0;
@@ -1390,7 +1390,10 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
     }
     case MA3_EPI_GATE_RES:
       MA3_REQUIRE(g->out && g->gate && g->rows_per_sample > 0, "gemm/gate_res: out, gate, rows_per_sample required");
-      MA3_REQUIRE(g->batch == 1, "gemm/gate_res: batch must be 1 (flatten samples into M)");
+      // batch > 1: z selects a column slice of the same residual stream (out_batch_stride / gate_batch_stride columns)
+      MA3_REQUIRE(g->batch >= 1 && g->out_batch_stride % 4 == 0 && g->gate_batch_stride % 4 == 0,
+                  "gemm/gate_res: batch strides of out and gate must be multiples of 4");
+      MA3_REQUIRE(g->batch == 1 || g->stream_k != 1, "gemm/gate_res: stream-K is not available with batch > 1");
       MA3_REQUIRE(g->N % 4 == 0 && g->out_ld % 4 == 0 && g->gate_ld % 4 == 0 && aligned16(g->out) && aligned16(g->gate),
                   "gemm/gate_res: N, out_ld, gate_ld must be multiples of 4 and pointers 16-byte aligned");
       MA3_REQUIRE(g->stream_k >= -1 && g->stream_k <= 1, "gemm/gate_res: stream_k must be -1, 0 or 1");
@@ -1409,9 +1412,10 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
       }
       return launch<MA3_EPI_GATE_RES>(kp, smem, grid, CG, st);
     case MA3_EPI_SWIGLU:
-      MA3_REQUIRE(g->out && g->batch == 1, "gemm/swiglu: out required, batch must be 1");
-      MA3_REQUIRE(g->N % 16 == 0 && g->out_ld % 8 == 0 && aligned16(g->out) && g->out_dtype != MA3_F32,
-                  "gemm/swiglu: N %% 16, out_ld %% 8, 16-bit out required");
+      MA3_REQUIRE(g->out && g->batch >= 1, "gemm/swiglu: out required");
+      MA3_REQUIRE(g->N % 16 == 0 && g->out_ld % 8 == 0 && g->out_batch_stride % 8 == 0 && aligned16(g->out) &&
+                      g->out_dtype != MA3_F32,
+                  "gemm/swiglu: N %% 16, out_ld %% 8, out_batch_stride %% 8, 16-bit out required");
       return launch<MA3_EPI_SWIGLU>(kp, smem, grid, CG, st);
     case MA3_EPI_QKV_ROPE:
       MA3_REQUIRE(g->q_out && g->k_out && g->vt_out, "gemm/qkv_rope: q_out, k_out, vt_out required");

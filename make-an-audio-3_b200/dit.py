@@ -245,10 +245,12 @@ class TxtFlagLargeDiT(nn.Module):
                 band = D // self.num_experts
                 q["t_w13"] = [b16(il(e.w1.weight, e.w3.weight)) for e in ff.time_experts.values()]
                 q["t_w2"] = [b16(e.w2.weight) for e in ff.time_experts.values()]
-                # frequency expert j only sees / produces band j: slice the weights once (exact)
-                q["f_w13"] = [b16(il(e.w1.weight[:, j * band:(j + 1) * band], e.w3.weight[:, j * band:(j + 1) * band]))
-                              for j, e in enumerate(ff.freq_experts.values())]
-                q["f_w2"] = [b16(e.w2.weight[j * band:(j + 1) * band, :]) for j, e in enumerate(ff.freq_experts.values())]
+                # frequency expert j only sees / produces band j: slice the weights once (exact), stacked
+                # [E][...] so that the E band GEMMs of a block are ONE batched launch per projection
+                q["f_w13"] = torch.stack([b16(il(e.w1.weight[:, j * band:(j + 1) * band], e.w3.weight[:, j * band:(j + 1) * band]))
+                                          for j, e in enumerate(ff.freq_experts.values())]).contiguous()
+                q["f_w2"] = torch.stack([b16(e.w2.weight[j * band:(j + 1) * band, :])
+                                         for j, e in enumerate(ff.freq_experts.values())]).contiguous()
             else:
                 q["w13"] = b16(il(ff.w1.weight, ff.w3.weight))
                 q["w2"] = b16(ff.w2.weight)
@@ -312,6 +314,7 @@ class TxtFlagLargeDiT(nn.Module):
                 w.qkv_raw = torch.empty(N * T, 3 * D, device=dev, dtype=torch.float32)
             if self.num_experts:
                 w.y1 = torch.empty(N * T, D, device=dev, dtype=bf)
+                w.mid_e = torch.empty(self.num_experts, N * T, F, device=dev, dtype=bf)   # one SwiGLU buffer per band expert
             self._work[key] = w
             self.generation += 1
         return w
@@ -493,12 +496,15 @@ class TxtFlagLargeDiT(nn.Module):
             else:
                 w.y1[rows].zero_()
             n = m
+        # The E band experts as two batched launches (z = band): operand / output column slices of y1, h and the gate are
+        # batch strides of `band` columns.  (One launch per expert and projection was 8 of the block's 14 launches, and
+        # at batch 2 every one of them is latency-bound.)
         M = N * T
-        for j in range(E):
-            ops.gemm(w.y1[:, j * band:], q["f_w13"][j], M=M, N=2 * F, K=band, a_ld=D, epi=L.EPI_SWIGLU, out=w.mid,
-                     out_ld=F)
-            ops.gemm(w.mid, q["f_w2"][j], M=M, N=band, K=F, epi=L.EPI_GATE_RES, out=w.h[:, j * band:], out_ld=D,
-                     gate=gate2[:, j * band:(j + 1) * band], rows_per_sample=T)
+        ops.gemm(w.y1, q["f_w13"], M=M, N=2 * F, K=band, batch=E, a_ld=D, a_batch_stride=band, b_rows=2 * F,
+                 b_batch_stride=2 * F * band, epi=L.EPI_SWIGLU, out=w.mid_e, out_ld=F, out_batch_stride=M * F)
+        ops.gemm(w.mid_e, q["f_w2"], M=M, N=band, K=F, batch=E, a_batch_stride=M * F, b_rows=band, b_batch_stride=band * F,
+                 epi=L.EPI_GATE_RES, out=w.h, out_ld=D, out_batch_stride=band, gate=gate2, gate_batch_stride=band,
+                 rows_per_sample=T)
 
 
 class TxtFlagLargeImprovedDiTV2(TxtFlagLargeDiT):

@@ -37,7 +37,7 @@ class GemmDesc(C.Structure):
         ("res", C.c_void_p), ("res_dtype", C.c_int32),
         ("res_ld", C.c_int64), ("res_batch_stride", C.c_int64),
         ("alpha", C.c_float), ("act", C.c_int32), ("accumulate", C.c_int32),
-        ("gate", C.c_void_p), ("gate_ld", C.c_int64), ("rows_per_sample", C.c_int32),
+        ("gate", C.c_void_p), ("gate_ld", C.c_int64), ("gate_batch_stride", C.c_int64), ("rows_per_sample", C.c_int32),
         ("q_out", C.c_void_p), ("k_out", C.c_void_p), ("vt_out", C.c_void_p),
         ("rope", C.c_void_p),
         ("model_dim", C.c_int32), ("head_dim", C.c_int32), ("head_dim_pad", C.c_int32),

@@ -77,7 +77,7 @@ def declare(lib):
 def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_rows=None, b_ld=None,
          b_batch_stride=0, taps=((0, 0),), epi=L.EPI_STORE, out=None, out_ld=None, out_batch_stride=0,
          out_row_mul=1, out_row_off=0, bias=None, bias_per_row=False, res=None, res_ld=None, res_batch_stride=0,
-         alpha=1.0, accumulate=False, gate=None, rows_per_sample=0, q_out=None, k_out=None, vt_out=None, rope=None,
+         alpha=1.0, accumulate=False, gate=None, gate_batch_stride=0, rows_per_sample=0, q_out=None, k_out=None, vt_out=None, rope=None,
          model_dim=0, head_dim=0, head_dim_pad=0, tokens=0, tokens_pad=0, q_scale=1.0, first_section=0, act=0,
          tile_n=0, cta_group=0, stream_k=0):
     """acc[z,m,n] = sum_taps sum_k A[z, m + a_shift, k] * B[z, n + b_row, k]; see include/ma3_b200.h."""
@@ -120,6 +120,7 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
         assert gate.dtype == torch.float32
         d.gate = gate.data_ptr()
         d.gate_ld = gate.stride(0)
+        d.gate_batch_stride = gate_batch_stride
     d.rows_per_sample = rows_per_sample
     if q_out is not None:
         d.q_out, d.k_out, d.vt_out = q_out.data_ptr(), k_out.data_ptr(), vt_out.data_ptr()
