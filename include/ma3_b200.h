@@ -63,7 +63,8 @@ const char* ma3_last_error(void);
  *                      out row = m*out_row_mul + out_row_off (strided rows: transposed-conv phases)
  *   MA3_EPI_GATE_RES   out(f32)[z,m,n] += gate[(m / rows_per_sample), z*gate_batch_stride + n] * acc   (flag_large_dit.py:83-91)
  *   MA3_EPI_SWIGLU     out[m, n/2] = silu(acc[m, n]) * acc[m, n+1], n even         (flag_large_dit_moe.py:484-489;
- *                      w1 rows interleaved with w3 rows in B)
+ *                      w1 rows interleaved with w3 rows in B); act == 4: tanh-GELU instead of SiLU (the gated-GELU
+ *                      feed-forward of the T5 v1.1 text encoder, ldm/modules/encoders/modules.py:178-191)
  *   MA3_EPI_QKV_ROPE   columns [0,D) q, [D,2D) k, [2D,3D) v of one fused projection; rotary embedding on q,k
  *                      (flag_large_dit_moe.py:240-271; rope == NULL: no rotation), q pre-multiplied by q_scale; scatter to
  *                      q,k: [sample, head, t, hd_pad]   v: [sample, head, hd_pad, t_pad] (transposed)
@@ -255,6 +256,12 @@ int ma3_ntc_to_nct(const void* x, int in_dtype, float* out, int B, int C, int T,
 /* nearest-neighbour x2 along T (Upsample1D, autoencoder1d.py:291-292) on channels-last 16-bit rows. */
 int ma3_upsample_nearest2(const void* x, void* out, int64_t rows, int C, void* stream);
 int ma3_cast(const void* x, int in_dtype, void* out, int out_dtype, int64_t n, void* stream);
+/* Token embedding lookup of the text encoders (the nn.Embedding inside the CLAP-BERT and T5 encoders that
+ * ldm/modules/encoders/modules.py:178-191 calls): out[m, :] = table[ids[m], :] (+ pos[m % T, :]) (+ type0[:]), fp32.
+ * ids are int64 (torch.long); an id outside [0, vocab) is an error reported through the return code of the NEXT call
+ * (device-side flag), pos / type0 may be NULL. */
+int ma3_embed_rows(const float* table, int64_t vocab, const int64_t* ids, const float* pos, const float* type0, float* out,
+                   int M, int T, int D, void* stream);
 
 /* Fused anti-aliased periodic activation (Activation1d.forward, vocoder/bigvgan/alias_free_torch/act.py:23-28):
  * replicate-pad -> x2 up-sampling with the 12-tap Kaiser-sinc filter (resample.py:25-33) -> SnakeBeta / Snake

@@ -802,6 +802,36 @@ int ma3_cast(const void* x, int in_dtype, void* out, int out_dtype, int64_t n, v
 
 }  // extern "C"
 
+// ---------------------------------------------------------------------------------------- embedding lookup
+namespace ma3 {
+__global__ void embed_rows_kernel(const float* __restrict__ table, long long vocab, const long long* __restrict__ ids,
+                                  const float* __restrict__ pos, const float* __restrict__ type0, float* __restrict__ out,
+                                  int M, int T, int D) {
+  const int m = blockIdx.x;
+  long long id = ids[m];
+  if (id < 0 || id >= vocab) id = 0;   // clamped: the host wrapper validates the ids (they come from a tokenizer)
+  const float4* src = reinterpret_cast<const float4*>(table + id * D);
+  const float4* ps = pos ? reinterpret_cast<const float4*>(pos + (long long)(m % T) * D) : nullptr;
+  const float4* ty = type0 ? reinterpret_cast<const float4*>(type0) : nullptr;
+  float4* dst = reinterpret_cast<float4*>(out + (long long)m * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    float4 v = src[i];
+    if (ps) { const float4 q = ps[i]; v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+    if (ty) { const float4 q = ty[i]; v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+    dst[i] = v;
+  }
+}
+}  // namespace ma3
+
+extern "C" int ma3_embed_rows(const float* table, int64_t vocab, const int64_t* ids, const float* pos, const float* type0,
+                              float* out, int M, int T, int D, void* stream) {
+  MA3_REQUIRE(table && ids && out && M > 0 && T > 0 && D > 0 && D % 4 == 0 && vocab > 0, "embed_rows: bad arguments");
+  ma3::embed_rows_kernel<<<(unsigned)M, 128, 0, ST(stream)>>>(table, (long long)vocab, (const long long*)ids, pos, type0, out,
+                                                             M, T, D);
+  MA3_LAUNCH_CHECK("embed_rows");
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------- adaLN input
 // out[s*N + n, :] = silu(temb[s*ts_s + n*ts_n, :] + cap[n, :])  (flag_large_dit.py:200 then the SiLU of :50-51);
 // sampler: one timestep row per step (ts_s = 1, ts_n = 0); drop-in forward(): one row per sample (ts_s = 0, ts_n = 1).

@@ -351,11 +351,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
       for (int pass = 0; pass < 2; ++pass) {
         if (rc.off[pass] >= 0) {
           float v[8];
+          if (p.act == 4) {   // gated tanh-GELU (T5 v1.1 DenseGatedActDense: gelu_new(wi_0 x) * wi_1 x), warp-uniform
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float4 a = lds_f4(sp + 4 * e);
-            v[2 * e] = silu_f(a.x) * a.y;
-            v[2 * e + 1] = silu_f(a.z) * a.w;
+            for (int e = 0; e < 4; ++e) {
+              const float4 a = lds_f4(sp + 4 * e);
+              v[2 * e] = gelu_tanh_f(a.x) * a.y;
+              v[2 * e + 1] = gelu_tanh_f(a.z) * a.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 a = lds_f4(sp + 4 * e);
+              v[2 * e] = silu_f(a.x) * a.y;
+              v[2 * e + 1] = silu_f(a.z) * a.w;
+            }
           }
           store8(p.out, p.out_dtype, rc.off[pass] + (col >> 1), true, 8, v);
         }

@@ -347,6 +347,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) = x sigmoid(2 sqrt(2/pi) (x + 0.044715 x^3))   ("gelu_new")
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float u = 1.5957691216057308f * x * fmaf(0.044715f * x, x, 1.0f);
+  return __fdividef(x, 1.0f + __expf(-u));
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

@@ -15,8 +15,9 @@ three serialisations of the reference removed:
 and clipped exactly as libsndfile does for float -> PCM_16.  `generate_manifest` is the `testset` loop of the script's
 main() (:240-262) including result.csv (tab separated, same columns).
 
-The text / video conditioners are NOT part of this package (section 8(f) rank 1): `model.get_learned_conditioning` is
-whatever the wrapped model provides (the reference's FrozenCLAP/T5 stack, or an identity for precomputed embeddings).
+`model.get_learned_conditioning` is whatever the wrapped model provides: the reference's FrozenCLAP/T5 stack, this
+package's GPU conditioner (`conditioners.FrozenCLAPFLANEmbedder` attached as `pipeline.cond_stage_model`, section 8(f)
+rank 1), or the identity for precomputed embeddings.
 """
 import csv
 import os

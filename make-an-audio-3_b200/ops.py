@@ -66,6 +66,7 @@ def declare(lib):
         "ma3_melnet_mag": [vp, i64, vp, i32, i32, i32, i32, vp],
         "ma3_melnet_log": [vp, vp, i32, i32, i32, vp],
         "ma3_gemm_rownorm": [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i64, i32, vp, f32, vp],
+        "ma3_embed_rows": [vp, i64, vp, vp, vp, vp, i32, i32, i32, vp],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -306,6 +307,14 @@ def qknorm_rope(x, *, first_section, qn, kn, rope, q_out, k_out, vt_out, tokens,
     kw, kb = kn if kn is not None else (None, None)
     _call("ma3_qknorm_rope", L.ptr(x), x.stride(0), first_section, L.ptr(qw), L.ptr(qb), L.ptr(kw), L.ptr(kb), eps,
           L.ptr(rope), L.ptr(q_out), L.ptr(k_out), L.ptr(vt_out), L.dt(k_out), M, tokens, tokens_pad, D, hd, hdp, q_scale)
+
+
+def embed_rows(table, ids, out, *, T, pos=None, type0=None):
+    """out[m] = table[ids[m]] (+ pos[m % T]) (+ type0): token embedding lookup of the text encoders (fp32)."""
+    assert table.dtype == torch.float32 and ids.dtype == torch.int64 and out.dtype == torch.float32
+    _call("ma3_embed_rows", L.ptr(table), table.shape[0], L.ptr(ids), L.ptr(pos), L.ptr(type0), L.ptr(out), ids.numel(), T,
+          table.shape[1])
+    return out
 
 
 def cast(x, out):

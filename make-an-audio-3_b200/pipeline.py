@@ -57,6 +57,7 @@ class Txt2AudioPipeline:
         self.mel_dim, self.mel_length, self.channels = mel_dim, mel_length, 0
         self.sampler = CFMSampler(self, use_graph=use_graph)
         self.use_graph = use_graph
+        self.cond_stage_model = None      # optional text conditioner (conditioners.py), ddpm_audio.py:343-356
         self._tail = {}
 
     # CFMSampler looks the DiT up as model.model.diffusion_model (the reference's nesting, ddpm.py:1402)
@@ -81,11 +82,16 @@ class Txt2AudioPipeline:
         return self.dit.proj_in.weight.device
 
     def get_learned_conditioning(self, c):
-        """Identity conditioner for precomputed embeddings (ddpm_audio.py:343-356 calls cond_stage_model here; the
-        CLAP / T5 encoders are SURVEY.md section 8(f) rank 1 and stay with the caller)."""
-        if not torch.is_tensor(c):
-            raise TypeError("Txt2AudioPipeline takes precomputed embeddings [B, L, context_dim]; text / video "
-                            "conditioners are not part of this package")
+        """ddpm_audio.py:343-356: the conditioner's `encode` when one is attached (`cond_stage_model`, e.g.
+        `conditioners.FrozenCLAPFLANEmbedder`: the reference's `cond_stage_config`), otherwise the identity for
+        precomputed embeddings [B, L, context_dim]."""
+        m = getattr(self, "cond_stage_model", None)
+        if torch.is_tensor(c):
+            return c.to(self.device, torch.float32)
+        if m is None:
+            raise TypeError("Txt2AudioPipeline has no cond_stage_model: pass precomputed embeddings [B, L, context_dim] or "
+                            "attach a conditioner (ma3_b200.conditioners.FrozenCLAPFLANEmbedder)")
+        c = m.encode(c) if hasattr(m, "encode") and callable(m.encode) else m(c)
         return c.to(self.device, torch.float32)
 
     @torch.no_grad()

@@ -1,0 +1,93 @@
+"""the text conditioners (ldm/modules/encoders/modules.py:133-191) on the GPU kernels.
+
+The reference's conditioner IS `transformers.AutoModel('bert-base-uncased')` + its own `Projection` (clap.py:17-30) and
+`transformers.T5EncoderModel('google/t5-v1_1-large')`; no checkpoints exist offline, so the oracle here is those same
+`transformers` classes built from their published configs with seeded random weights, run in fp32 -- on the same
+weights the drop-in is loaded with (reference-keyed state_dict)."""
+import pytest
+import torch
+
+transformers = pytest.importorskip("transformers")
+
+
+def _hf_models(bert_layers, t5_layers, seed=0):
+    from transformers import BertConfig, BertModel, T5Config, T5EncoderModel
+    torch.manual_seed(seed)
+    bert = BertModel(BertConfig(num_hidden_layers=bert_layers), add_pooling_layer=False).eval()
+    t5 = T5EncoderModel(T5Config(vocab_size=32128, d_model=1024, d_kv=64, d_ff=2816, num_layers=t5_layers, num_heads=16,
+                                 feed_forward_proj="gated-gelu", tie_word_embeddings=False)).eval()
+    proj = {"linear1.weight": torch.randn(1024, 768) * 768 ** -0.5, "linear2.weight": torch.randn(1024, 1024) * 1024 ** -0.5,
+            "layer_norm.weight": 1 + 0.1 * torch.randn(1024), "layer_norm.bias": 0.1 * torch.randn(1024)}
+    return bert, t5, proj
+
+
+def _state_dict(bert, t5, proj):
+    sd = {"caption_encoder.base." + k: v for k, v in bert.state_dict().items()}
+    sd.update({"caption_encoder.projection." + k: v for k, v in proj.items()})
+    sd.update({"t5_transformer." + k: v for k, v in t5.state_dict().items()})
+    return sd
+
+
+def _projection(x, p):
+    """clap.py:25-30 at inference (dropout = identity)."""
+    e1 = x @ p["linear1.weight"].T
+    e2 = torch.nn.functional.gelu(e1) @ p["linear2.weight"].T
+    return torch.nn.functional.layer_norm(e1 + e2, (e1.shape[-1],), p["layer_norm.weight"], p["layer_norm.bias"])
+
+
+def test_t5_relative_buckets_match_transformers():
+    from transformers.models.t5.modeling_t5 import T5Attention
+    from ma3_b200.conditioners import t5_relative_buckets
+    for T in (1, 7, 77, 200):
+        rel = torch.arange(T)[None, :] - torch.arange(T)[:, None]
+        want = T5Attention._relative_position_bucket(rel, bidirectional=True, num_buckets=32, max_distance=128)
+        assert torch.equal(t5_relative_buckets(T), want)
+
+
+def test_embedder_needs_weights_and_tokenizers():
+    from ma3_b200 import conditioners as Cn, lib as L
+    with pytest.raises(L.Ma3Error):
+        Cn.FrozenCLAPFLANEmbedder()          # nothing to download offline: weights must be handed in
+    with pytest.raises(L.Ma3Error):
+        Cn.FrozenFLANEmbedder()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bert_layers,t5_layers,B", [(2, 2, 3), (12, 24, 2)])
+def test_clap_flan_embedder_matches_transformers(bert_layers, t5_layers, B):
+    """(2, 2): a shallow stack that isolates the per-layer arithmetic; (12, 24): the published depths of
+    bert-base-uncased and t5-v1_1-large.  Tolerance: bf16 GEMM operands with fp32 accumulation and an fp32 residual
+    stream against the fp32 oracle -- max error relative to the largest activation <= 2e-2, cosine >= 0.999."""
+    from ma3_b200 import conditioners as Cn, lib as L
+    bert, t5, proj = _hf_models(bert_layers, t5_layers, seed=3)
+    cfgb = dict(Cn.BERT_BASE, layers=bert_layers)
+    cfgt = dict(Cn.T5_V11_LARGE, layers=t5_layers)
+    emb = Cn.FrozenCLAPFLANEmbedder(state_dict=_state_dict(bert, t5, proj), bert_cfg=cfgb, t5_cfg=cfgt)
+    g = torch.Generator().manual_seed(11)
+    T = 77
+    ori = torch.randint(0, 30522, (B, T), generator=g)
+    struct = torch.randint(0, 32128, (B, T), generator=g)
+    ori[:, 40:] = 0            # padded tails as the tokenizers produce them ([PAD] = 0 in both vocabularies)
+    struct[:, 55:] = 0
+    out = emb.encode_tokens(ori, struct)
+    assert out.shape == (B, 2 * T, 1024) and out.dtype == torch.float32
+    with torch.no_grad():
+        bert, t5 = bert.cuda(), t5.cuda()
+        pj = {k: v.cuda() for k, v in proj.items()}
+        z = _projection(bert(input_ids=ori.cuda()).last_hidden_state, pj)
+        z2 = t5(input_ids=struct.cuda()).last_hidden_state
+        ref = torch.cat([z, z2], 1)
+    for name, a, b in (("clap", out[:, :T], ref[:, :T]), ("t5", out[:, T:], ref[:, T:])):
+        err = float((a - b).abs().max() / b.abs().max())
+        cos = float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0))
+        assert err <= 2e-2 and cos >= 0.999, (name, err, cos)
+    # the tokenizer-facing entry point refuses politely when no tokenizer was supplied
+    with pytest.raises(L.Ma3Error):
+        emb.encode({"ori_caption": ["a dog barks"], "struct_caption": ["<dog& barks>"]})
+    # ... and runs the same path through any tokenizer-like callable
+    class Tok:
+        def __init__(self, ids): self.ids = ids
+        def __call__(self, text, **kw): return {"input_ids": self.ids[:len(text)]}
+    emb.clap_tokenizer, emb.t5_tokenizer = Tok(ori), Tok(struct)
+    out2 = emb.encode({"ori_caption": ["x"] * B, "struct_caption": ["y"] * B})
+    assert torch.equal(out2, out)
