@@ -258,8 +258,7 @@ int ma3_upsample_nearest2(const void* x, void* out, int64_t rows, int C, void* s
 int ma3_cast(const void* x, int in_dtype, void* out, int out_dtype, int64_t n, void* stream);
 /* Token embedding lookup of the text encoders (the nn.Embedding inside the CLAP-BERT and T5 encoders that
  * ldm/modules/encoders/modules.py:178-191 calls): out[m, :] = table[ids[m], :] (+ pos[m % T, :]) (+ type0[:]), fp32.
- * ids are int64 (torch.long); an id outside [0, vocab) is an error reported through the return code of the NEXT call
- * (device-side flag), pos / type0 may be NULL. */
+ * ids are int64 (torch.long); the caller validates them (an id outside [0, vocab) reads row 0); pos / type0 may be NULL. */
 int ma3_embed_rows(const float* table, int64_t vocab, const int64_t* ids, const float* pos, const float* type0, float* out,
                    int M, int T, int D, void* stream);
 

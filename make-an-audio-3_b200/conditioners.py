@@ -137,8 +137,10 @@ class BertTextEncoder:
         B, T = tokens.shape
         D, H, F = c["hidden"], c["heads"], c["ffn"]
         hd, M, Tp = D // H, B * T, (T + 15) // 16 * 16
-        if T > c["max_pos"] or int(tokens.min()) < 0 or int(tokens.max()) >= c["vocab"]:
-            raise L.Ma3Error(f"BERT tokens out of range (T={T}, vocab {c['vocab']}, max positions {c['max_pos']})")
+        if T > c["max_pos"]:
+            raise L.Ma3Error(f"BERT: {T} tokens exceed the {c['max_pos']} learned positions")
+        if not torch.cuda.is_current_stream_capturing() and (int(tokens.min()) < 0 or int(tokens.max()) >= c["vocab"]):
+            raise L.Ma3Error(f"BERT token id outside [0, {c['vocab']})")
         buf = self._buf.get
         ids = tokens.to(self.device).reshape(-1).contiguous()
         tmp = ops.embed_rows(self.word, ids, buf("tmp", (M, D), f32), T=T, pos=self.pos, type0=self.type0)
@@ -215,8 +217,8 @@ class T5TextEncoder:
         B, T = tokens.shape
         D, H, hd, F = c["d_model"], c["heads"], c["d_kv"], c["d_ff"]
         inner, M, Tp = H * hd, B * T, (T + 15) // 16 * 16
-        if int(tokens.min()) < 0 or int(tokens.max()) >= self.embed.shape[0]:
-            raise L.Ma3Error(f"T5 tokens out of range (vocab {self.embed.shape[0]})")
+        if not torch.cuda.is_current_stream_capturing() and (int(tokens.min()) < 0 or int(tokens.max()) >= self.embed.shape[0]):
+            raise L.Ma3Error(f"T5 token id outside [0, {self.embed.shape[0]})")
         buf = self._buf.get
         ids = tokens.to(self.device).reshape(-1).contiguous()
         h = ops.embed_rows(self.embed, ids, buf("h", (M, D), f32), T=T)
@@ -248,7 +250,8 @@ class FrozenCLAPFLANEmbedder:
     the reference's own recipe when given (modules.py:140-145)."""
 
     def __init__(self, weights_path=None, t5version="google/t5-v1_1-large", freeze=True, device="cuda", max_length=77,
-                 state_dict=None, clap_tokenizer=None, t5_tokenizer=None, bert_cfg=None, t5_cfg=None):
+                 state_dict=None, clap_tokenizer=None, t5_tokenizer=None, bert_cfg=None, t5_cfg=None, use_graph=True):
+        self.use_graph, self._plans = use_graph, {}
         if state_dict is None:
             if weights_path is None:
                 raise L.Ma3Error("FrozenCLAPFLANEmbedder: pass `state_dict` (reference-keyed) or `weights_path`; there is no "
@@ -274,10 +277,34 @@ class FrozenCLAPFLANEmbedder:
 
     @torch.no_grad()
     def encode_tokens(self, ori_tokens, struct_tokens):
-        """int64 [B, T] token ids of the two captions -> fp32 [B, 2T, 1024] (CLAP part first, modules.py:187-191)."""
-        z = self.caption_encoder(ori_tokens)
-        z2 = self.t5_transformer(struct_tokens)
-        return torch.cat([z, z2], dim=1)
+        """int64 [B, T] token ids of the two captions -> fp32 [B, 2T, 1024] (CLAP part first, modules.py:187-191).
+        The ~1100 short launches of the two encoders are captured into one CUDA graph per (B, T) and replayed (the
+        kernels are microseconds long; issued eagerly the host launch latency is the whole cost)."""
+        if ori_tokens.shape != struct_tokens.shape or ori_tokens.dim() != 2:
+            raise L.Ma3Error("encode_tokens: ori_tokens and struct_tokens must both be [B, T]")
+        for name, t, vocab in (("CLAP", ori_tokens, self.caption_encoder.cfg["vocab"]),
+                               ("T5", struct_tokens, self.t5_transformer.embed.shape[0])):
+            if int(t.min()) < 0 or int(t.max()) >= vocab:
+                raise L.Ma3Error(f"encode_tokens: {name} token id outside [0, {vocab})")
+        if not self.use_graph:
+            return torch.cat([self.caption_encoder(ori_tokens), self.t5_transformer(struct_tokens)], dim=1)
+        key = tuple(ori_tokens.shape)
+        st = self._plans.get(key)
+        if st is None:
+            ids_o = ori_tokens.to(self.device).clone()
+            ids_s = struct_tokens.to(self.device).clone()
+            run = lambda: torch.cat([self.caption_encoder(ids_o), self.t5_transformer(ids_s)], dim=1)
+            run()                                    # eager pass: allocates the scratch buffers, packs the position bias
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = run()
+            st = {"ids_o": ids_o, "ids_s": ids_s, "graph": g, "out": out}
+            self._plans = {key: st}                  # one plan: the scratch buffers are shared between shapes
+        st["ids_o"].copy_(ori_tokens)
+        st["ids_s"].copy_(struct_tokens)
+        st["graph"].replay()
+        return st["out"].clone()
 
     def _tokenize(self, tok, text, which):
         if tok is None:
@@ -292,6 +319,54 @@ class FrozenCLAPFLANEmbedder:
                                   self._tokenize(self.t5_tokenizer, text["struct_caption"], "T5"))
 
     __call__ = encode
+
+
+class Video_Feat_Encoder_NoPosembed:
+    """Drop-in for ldm.modules.encoders.modules.Video_Feat_Encoder_NoPosembed (modules.py:16-27; the
+    cond_stage_config of configs/video2audio-cfm-cfg-moe.yaml:70-75): x [B, L, origin_dim] -> Linear -> [B, L, embed_dim].
+    state_dict keys `embedder.0.weight / .bias`.  The fp32 input is carried through the bf16 tensor cores as a hi / lo
+    pair against hi / lo weights (three products, ~16 mantissa bits), like the DiT's own conditioning path."""
+
+    def __init__(self, origin_dim, embed_dim, seq_len=40, state_dict=None, device="cuda"):
+        self.origin_dim, self.embed_dim, self.seq_len, self.device = origin_dim, embed_dim, seq_len, torch.device(device)
+        if state_dict is None:
+            lin = torch.nn.Linear(origin_dim, embed_dim)
+            state_dict = {"embedder.0.weight": lin.weight.detach(), "embedder.0.bias": lin.bias.detach()}
+        self.load_state_dict(state_dict)
+
+    def load_state_dict(self, sd, strict=True):
+        want = {"embedder.0.weight", "embedder.0.bias"}
+        if strict and set(sd) != want:
+            raise RuntimeError(f"Video_Feat_Encoder_NoPosembed: state_dict keys {sorted(sd)} != {sorted(want)}")
+        self.weight = sd["embedder.0.weight"].detach().to(self.device, torch.float32).contiguous()
+        self.bias = sd["embedder.0.bias"].detach().to(self.device, torch.float32).contiguous()
+        self._w2 = None
+
+    def state_dict(self):
+        return {"embedder.0.weight": self.weight, "embedder.0.bias": self.bias}
+
+    @torch.no_grad()
+    def forward(self, x):
+        L.require_device()
+        lead, K = x.shape[:-1], x.shape[-1]
+        x2 = x.to(self.device, torch.float32).reshape(-1, K).contiguous()
+        if self._w2 is None:
+            self._w2 = ops.split_weight(self.weight)
+        out = torch.empty(x2.shape[0], self.embed_dim, device=self.device, dtype=torch.float32)
+        ops.gemm_split(x2, self._w2, M=x2.shape[0], N=self.embed_dim, K=K, out=out, bias=self.bias)
+        return out.view(*lead, self.embed_dim)
+
+    __call__ = encode = forward
+
+
+class Video_Feat_Encoder_NoPosembed_inpaint(Video_Feat_Encoder_NoPosembed):
+    """modules.py:31-39: {'mix_video_feat', 'mix_spec'} -> (Linear(video), spec)."""
+
+    @torch.no_grad()
+    def forward(self, x):
+        return super().forward(x["mix_video_feat"]), x["mix_spec"]
+
+    __call__ = encode = forward
 
 
 class FrozenFLANEmbedder:

@@ -91,3 +91,23 @@ def test_clap_flan_embedder_matches_transformers(bert_layers, t5_layers, B):
     emb.clap_tokenizer, emb.t5_tokenizer = Tok(ori), Tok(struct)
     out2 = emb.encode({"ori_caption": ["x"] * B, "struct_caption": ["y"] * B})
     assert torch.equal(out2, out)
+
+
+@pytest.mark.gpu
+def test_video_feat_encoder():
+    """modules.py:16-39 (cond_stage_config of the video/MoE config): Linear 512 -> 768 on 40 video tokens."""
+    from ma3_b200 import conditioners as Cn
+    torch.manual_seed(5)
+    lin = torch.nn.Linear(512, 768)
+    sd = {"embedder.0.weight": lin.weight.detach(), "embedder.0.bias": lin.bias.detach()}
+    x = torch.randn(3, 40, 512)
+    ref = lin(x).detach()
+    enc = Cn.Video_Feat_Encoder_NoPosembed(512, 768, seq_len=40, state_dict=sd)
+    out = enc(x.cuda())
+    assert out.shape == (3, 40, 768)
+    assert float((out.cpu() - ref).abs().max() / ref.abs().max()) <= 1e-4      # split-bf16 products: ~fp32
+    assert set(enc.state_dict()) == set(sd)
+    v, spec = Cn.Video_Feat_Encoder_NoPosembed_inpaint(512, 768, state_dict=sd)({"mix_video_feat": x.cuda(), "mix_spec": x})
+    assert torch.equal(v, out) and spec is x
+    with pytest.raises(RuntimeError):
+        enc.load_state_dict({"embedder.0.weight": lin.weight})
