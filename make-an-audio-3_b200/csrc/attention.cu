@@ -16,6 +16,9 @@
 namespace ma3 {
 
 constexpr int kAttnThreads = 160;
+#ifndef MA3_ATTN_POLY_PAIRS
+#define MA3_ATTN_POLY_PAIRS 0
+#endif
 
 struct AttnParams {
   CUtensorMap tmQ, tmK, tmVt, tmKy, tmVyt;
@@ -381,6 +384,23 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+// 2^x for a pair of logits on the FMA pipe (x <= ~8; clamped below at -120): round-to-nearest split x = i + f with the
+// 1.5 * 2^23 trick, degree-3 minimax of 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the 16-bit rounding of
+// P), and i added into the exponent field.  Takes a quarter of a tile's exponentials off the MUFU pipe, which three
+// softmax warps per scheduler otherwise saturate.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float kM = 12582912.f;
+  x.x = fmaxf(x.x, -120.f);
+  x.y = fmaxf(x.y, -120.f);
+  const float2 t = fadd2(x, make_float2(kM, kM));
+  const float2 xi = fadd2(t, make_float2(-kM, -kM));
+  const float2 f = __ffma2_rn(xi, make_float2(-1.f, -1.f), x);
+  float2 q = __ffma2_rn(f, make_float2(0.05517165f, 0.05517165f), make_float2(0.24261112f, 0.24261112f));
+  q = __ffma2_rn(q, f, make_float2(0.69326099f, 0.69326099f));
+  q = __ffma2_rn(q, f, make_float2(0.99992807f, 0.99992807f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
 
 // O[:, 0..HDO) *= alpha, in place in TMEM (thread <-> row)
 template <int HDO>
@@ -810,23 +830,26 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) attn2_kernel(const __grid_co
 // re-loads K / V^T, and a ragged last query tile costs a whole CTA.  Here the NCTX query tiles of a head are NCTX
 // independent softmax streams inside one CTA that share every K / V^T tile (loaded once per head instead of once per
 // query tile); a softmax thread owns a whole query row of an 80-key tile (no partner exchange, no named barriers, 80
-// exponentials per ~800 clocks of per-tile synchronisation instead of 40); and every context has its own MMA-issuing
-// warp, so the PV -> next-S turnaround of one context (S is single-buffered: 3 x (80 S/P + 80 O) = 480 columns) is
-// ~400 clocks during which the other two contexts own the MUFU pipe.
+// exponentials per ~800 clocks of per-tile synchronisation instead of 40); every context has its own MMA-issuing warp;
+// and P goes to the PV MMA through SHARED memory (128B / 32B-swizzled K-major tile written by the softmax threads), not
+// over the S columns: S (single-buffered: 3 x (80 S + 80 O) = 480 TMEM columns) is handed back to the tensor core as
+// soon as the softmax warps hold it in registers, so S(c, i+1) is computed under the exponentials of tile i and the
+// PV -> next-S turnaround of the tensor pipe (~1400 clocks) leaves the critical path.
 //   warps [0, 4 NCTX):        softmax, warp w <-> context w / 4, TMEM lane quarter w % 4
 //   warp 4 NCTX:              TMA producer (Q tiles, K ring, V^T ring)
 //   warps 4 NCTX + 1 + c:     MMA issue for context c (one elected lane each; the first one owns the TMEM allocation)
-// Lazy rescaling, P written back over the consumed S columns as the TMEM A operand of PV, row sums from the ones row
-// of V^T, keys 64..79 of V^T as a 32B-swizzled chunk: as in v2.  The normalised self-attention result is parked in the
+// Lazy rescaling, row sums from the ones row of V^T, keys 64..79 of V^T (and of P) as a 32B-swizzled chunk: as in v2.  The normalised self-attention result is parked in the
 // output row (16-bit) across the cross segment and read back by the same thread at the end.
 template <int HDP, int HD, int NCTX>
 __global__ void __launch_bounds__(NCTX * 128 + 32 + NCTX * 32, 1) attn3_kernel(const __grid_constant__ AttnParams p) {
   constexpr int BKV = 80;
-  constexpr int NST = 3;                         // K / V^T stages
+  constexpr int NST = 2;                         // K / V^T stages (K and V^T halves are released separately)
   constexpr int HDC = HDP / 64;
   constexpr int HDO = (HD + 1 + 15) / 16 * 16;
   constexpr int KS = (HD + 15) / 16;
-  constexpr int CW = BKV + HDO;                  // TMEM columns of one context: S / P [0, 80)  O [80, 80 + HDO)
+  constexpr int CW = BKV + HDO;                  // TMEM columns of one context: S [0, 80)  O [80, 80 + HDO)
+  constexpr uint32_t kP1Bytes = 128 * 128;       // P, keys 0..63: 128 rows x 128 B, 128B swizzle
+  constexpr uint32_t kPBytes = kP1Bytes + 128 * 32;   // + keys 64..79: 128 rows x 32 B, 32B swizzle
   static_assert(NCTX * CW <= 512, "TMEM budget");
   static_assert(HDO <= HDP, "needs a spare V^T row for the row sums");
   constexpr uint32_t kQBytes = 128 * HDP * 2;
@@ -836,18 +859,21 @@ __global__ void __launch_bounds__(NCTX * 128 + 32 + NCTX * 32, 1) attn3_kernel(c
   constexpr uint32_t kVBytes = kV1Bytes + kV2Bytes;
   constexpr uint32_t kStageBytes = (kKBytes + kVBytes + 1023) / 1024 * 1024;
   constexpr int kSoftWarps = 4 * NCTX;
+  constexpr int kPolyPairs = MA3_ATTN_POLY_PAIRS;   // of the 8 key pairs of a 16-key group
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sQ = smem_raw;
   uint8_t* sKV = sQ + NCTX * kQBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NST * kStageBytes);
+  uint8_t* sP = sKV + NST * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NCTX * kPBytes);
   uint64_t* q_full = bars;                  // NCTX (one per query tile, so that context 0 starts on its own tile)
   uint64_t* k_full = q_full + NCTX;         // NST
   uint64_t* k_empty = k_full + NST;         // NST, one commit per active context
   uint64_t* v_full = k_empty + NST;         // NST
   uint64_t* v_empty = v_full + NST;         // NST, one commit per active context
   uint64_t* s_full = v_empty + NST;         // NCTX: phase i completes with S(c, i)
-  uint64_t* p_full = s_full + NCTX;         // NCTX: P(c, i) is in TMEM (one arrival per active softmax warp)
+  uint64_t* s_free = s_full + NCTX;         // NCTX: S(c, i) is in registers (one arrival per active softmax warp)
+  uint64_t* p_full = s_free + NCTX;         // NCTX: P(c, i) is in shared memory (one arrival per active softmax warp)
   uint64_t* pv_done = p_full + NCTX;        // NCTX: phase i completes with PV(c, i)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + NCTX);
 
@@ -880,6 +906,7 @@ __global__ void __launch_bounds__(NCTX * 128 + 32 + NCTX * 32, 1) attn3_kernel(c
       const int nw = max(1, min(4, (p.T - (qt0 + c) * 128 + 31) / 32));
       mbar_init(&q_full[c], 1);
       mbar_init(&s_full[c], 1);
+      mbar_init(&s_free[c], nw);
       mbar_init(&p_full[c], nw);
       mbar_init(&pv_done[c], 1);
     }
@@ -938,6 +965,8 @@ __global__ void __launch_bounds__(NCTX * 128 + 32 + NCTX * 32, 1) attn3_kernel(c
       const uint64_t dv2 = umma_desc_kmajor(smem_u32(sKV + kKBytes + kV1Bytes), 32);
       const uint32_t v2_lo = (uint32_t)dv2, dhi32 = (uint32_t)(dv2 >> 32);
       const uint32_t tS = tmem_base + c * CW, tO = tS + BKV;
+      const uint32_t p_lo = (uint32_t)umma_desc_kmajor(smem_u32(sP + c * kPBytes), 128);
+      const uint32_t p2_lo = (uint32_t)umma_desc_kmajor(smem_u32(sP + c * kPBytes + kP1Bytes), 32);
       const bool trm = p.trace && n_tiles <= 16 && (c == 0 || c == 2) && blockIdx.x + blockIdx.y + blockIdx.z == 0;
       auto issue_s = [&](int it, int st, int ph) {
         mbar_wait(&k_full[st], ph);
@@ -955,26 +984,26 @@ __global__ void __launch_bounds__(NCTX * 128 + 32 + NCTX * 32, 1) attn3_kernel(c
       issue_s(0, 0, 0);
       int st = 0, ph = 0;          // ring stage of tile it and the parity of that use
       for (int it = 0; it < n_tiles; ++it) {
-        mbar_wait(&p_full[c], it & 1);     // P(c, it) written over the S columns
+        int st1 = st + 1, ph1 = ph;
+        if (st1 == NST) { st1 = 0; ph1 ^= 1; }
+        if (it + 1 < n_tiles) {
+          mbar_wait(&s_free[c], it & 1);   // S(c, it) is in registers: its columns may be overwritten
+          issue_s(it + 1, st1, ph1);
+        }
+        mbar_wait(&p_full[c], it & 1);     // P(c, it) is in shared memory (its writers waited for PV(c, it - 1))
         mbar_wait(&v_full[st], ph);
         tc_fence_after();
         const uint32_t dv = v_lo + (uint32_t)st * (kStageBytes >> 4);
         const uint32_t fresh = (it == 0 || it == n_self) ? 0u : 1u;   // first tile of a segment overwrites O
-        umma_f16_ts(tO, tS, dv, dhi, idesc_o, fresh);
-        umma_f16_ts(tO, tS + 8, dv + 2, dhi, idesc_o, 1u);
-        umma_f16_ts(tO, tS + 16, dv + 4, dhi, idesc_o, 1u);
-        umma_f16_ts(tO, tS + 24, dv + 6, dhi, idesc_o, 1u);
-        umma_f16_ts(tO, tS + 32, v2_lo + (uint32_t)st * (kStageBytes >> 4), dhi32, idesc_o, 1u);
+        umma_f16_lohi<1>(tO, p_lo, dv, dhi, idesc_o, fresh);
+        umma_f16_lohi<1>(tO, p_lo + 2, dv + 2, dhi, idesc_o, 1u);
+        umma_f16_lohi<1>(tO, p_lo + 4, dv + 4, dhi, idesc_o, 1u);
+        umma_f16_lohi<1>(tO, p_lo + 6, dv + 6, dhi, idesc_o, 1u);
+        umma_f16_lohi<1>(tO, p2_lo, v2_lo + (uint32_t)st * (kStageBytes >> 4), dhi32, idesc_o, 1u);
         umma_commit(&pv_done[c]);
         umma_commit(&v_empty[st]);
         if (trm) p.trace[it * 16 + 9 + c] = clock64();
-        if (++st == NST) { st = 0; ph ^= 1; }
-        if (it + 1 < n_tiles) {
-          // S(c, it + 1) overwrites the columns PV(c, it) reads P from, and the tensor pipe does not order those TMEM
-          // A-operand reads against a later MMA: wait for the completion
-          mbar_wait(&pv_done[c], it & 1);
-          issue_s(it + 1, st, ph);
-        }
+        st = st1; ph = ph1;
       }
     }
   } else if (warp < 4 * n_ctx && (warp & 3) * 32 < p.T - (qt0 + (warp >> 2)) * 128) {
@@ -1007,9 +1036,83 @@ __global__ void __launch_bounds__(NCTX * 128 + 32 + NCTX * 32, 1) attn3_kernel(c
       tmem_ld_n<32>(tS, s);
       tmem_ld_n<32>(tS + 32, s + 32);
       tmem_ld_n<16>(tS + 64, s + 64);
-      // every phase of pv_done is observed in order (a parity wait is only meaningful one phase back); S(c, it) was
-      // issued after PV(c, it - 1) completed, so this never spins
-      if (it > 0) mbar_wait(&pv_done[c], (it - 1) & 1);
+      tmem_ld_wait();
+      // S(c, it) is in registers: hand the columns back so that S(c, it + 1) runs under this tile's exponentials
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(&s_free[c]);
+      if (tr) p.trace[it * 16 + 7] = clock64();
+      if (valid < BKV) {
+#pragma unroll
+        for (int e = 0; e < BKV; ++e)
+          if (e >= valid) s[e] = 0xff800000u;
+      }
+      float mx4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mx4[q] = fmaxf(__uint_as_float(s[q]), __uint_as_float(s[q + 4]));
+#pragma unroll
+      for (int e = 8; e < BKV; e += 8) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mx4[q] = fmax3(mx4[q], __uint_as_float(s[e + q]), __uint_as_float(s[e + q + 4]));
+      }
+      const float mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]);
+      if (tr) p.trace[it * 16 + 2] = clock64();
+      if (j == 0) {
+        m = mx;
+      } else if (__any_sync(0xffffffffu, mx > m + 8.f)) {
+        mbar_wait(&pv_done[c], (it - 1) & 1);   // PV(c, it - 1) complete: O may be modified in place
+        tc_fence_after();
+        const float m_new = fmaxf(m, mx);
+        rescale_cols<0, HDO>(tO, ex2_approx(m - m_new));
+        tmem_st_wait();
+        tc_fence_before();
+        m = m_new;
+      }
+      if (tr) p.trace[it * 16 + 3] = clock64();
+      // p = 2^(s - m) for the 80 keys, packed to 16-bit pairs; 16-key groups beyond the sequence cost no exponentials
+      uint32_t pk[BKV / 2];
+      const float2 nm = make_float2(-m, -m);
+#pragma unroll
+      for (int g = 0; g < BKV; g += 16) {
+        if (g + 16 <= valid && bf16) {
+          // full group: the first kPolyPairs key pairs through the FMA-pipe polynomial, the rest through MUFU
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float2 d = fadd2(make_float2(__uint_as_float(s[g + e]), __uint_as_float(s[g + e + 1])), nm);
+            if (e < 2 * kPolyPairs) {
+              const float2 r = ex2_poly2(d);
+              pk[(g + e) >> 1] = pack_bf16(r.x, r.y);
+            } else {
+              pk[(g + e) >> 1] = pack_bf16(ex2_approx(d.x), ex2_approx(d.y));
+            }
+          }
+        } else if (g < valid) {
+          if (bf16) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const float2 d = fadd2(make_float2(__uint_as_float(s[g + e]), __uint_as_float(s[g + e + 1])), nm);
+              pk[(g + e) >> 1] = pack_bf16(ex2_approx(d.x), ex2_approx(d.y));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              const float2 d = fadd2(make_float2(__uint_as_float(s[g + e]), __uint_as_float(s[g + e + 1])), nm);
+              pk[(g + e) >> 1] = pack_f16(ex2_approx(d.x), ex2_approx(d.y));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pk[(g >> 1) + e] = 0u;
+        }
+      }
+      if (tr) p.trace[it * 16 + 4] = clock64();
+      // PV(c, it - 1) reads the shared-memory P tile and (first cross tile) leaves the final self-attention O: it must
+      // have completed.  Every phase of pv_done is observed in order (a parity wait is only meaningful one phase back);
+      // that PV was issued a whole tile ago, so this is normally already satisfied.
+      if (it > 0) {
+        mbar_wait(&pv_done[c], (it - 1) & 1);
+        tc_fence_after();
+      }
       if (cross && j == 0 && n_self > 0) {
         // segment switch: the self-attention O is final.  Park it, normalised, in the output row (16-bit, as it is
         // rounded on output anyway) before PV(c, it) overwrites O; the same thread adds the cross part at the end.
@@ -1030,60 +1133,20 @@ __global__ void __launch_bounds__(NCTX * 128 + 32 + NCTX * 32, 1) attn3_kernel(c
           if (row_ok) *reinterpret_cast<uint4*>(orow + c0) = u;
         }
       }
-      tmem_ld_wait();
-      if (valid < BKV) {
+      // P row -> the K-major operand tile of PV(c, it): 16-byte units, XOR-swizzled like a TMA write would
+      // (128B swizzle: unit ^= row & 7 in 128-byte rows; 32B swizzle: unit ^= (row >> 2) & 1 in 32-byte rows)
+      {
+        uint8_t* prow = sP + c * kPBytes + row * 128;
 #pragma unroll
-        for (int e = 0; e < BKV; ++e)
-          if (e >= valid) s[e] = 0xff800000u;
+        for (int u = 0; u < 8; ++u)
+          *reinterpret_cast<uint4*>(prow + ((u ^ (row & 7)) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        uint8_t* prow2 = sP + c * kPBytes + kP1Bytes + row * 32;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          *reinterpret_cast<uint4*>(prow2 + ((u ^ ((row >> 2) & 1)) << 4)) =
+              make_uint4(pk[32 + 4 * u], pk[33 + 4 * u], pk[34 + 4 * u], pk[35 + 4 * u]);
       }
-      float mx4[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) mx4[q] = fmaxf(__uint_as_float(s[q]), __uint_as_float(s[q + 4]));
-#pragma unroll
-      for (int e = 8; e < BKV; e += 8) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) mx4[q] = fmax3(mx4[q], __uint_as_float(s[e + q]), __uint_as_float(s[e + q + 4]));
-      }
-      const float mx = fmaxf(fmax3(mx4[0], mx4[1], mx4[2]), mx4[3]);
-      if (tr) p.trace[it * 16 + 2] = clock64();
-      if (j == 0) {
-        m = mx;
-      } else if (__any_sync(0xffffffffu, mx > m + 8.f)) {
-        // PV(c, it - 1) has completed (see above): O may be modified in place
-        const float m_new = fmaxf(m, mx);
-        rescale_cols<0, HDO>(tO, ex2_approx(m - m_new));
-        tmem_st_wait();
-        m = m_new;
-      }
-      if (tr) p.trace[it * 16 + 3] = clock64();
-      // p = 2^(s - m), 16 keys (8 packed columns) at a time, written back over the S columns this thread has consumed:
-      // the TMEM A operand of PV(c, it).  16-key groups beyond the sequence cost no exponentials.
-      const float2 nm = make_float2(-m, -m);
-#pragma unroll
-      for (int g = 0; g < BKV; g += 16) {
-        uint32_t pk[8];
-        if (g < valid) {
-          if (bf16) {
-#pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              const float2 d = fadd2(make_float2(__uint_as_float(s[g + e]), __uint_as_float(s[g + e + 1])), nm);
-              pk[e >> 1] = pack_bf16(ex2_approx(d.x), ex2_approx(d.y));
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              const float2 d = fadd2(make_float2(__uint_as_float(s[g + e]), __uint_as_float(s[g + e + 1])), nm);
-              pk[e >> 1] = pack_f16(ex2_approx(d.x), ex2_approx(d.y));
-            }
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) pk[e] = 0u;
-        }
-        tmem_st8(tS + g / 2, pk);
-      }
-      if (tr) p.trace[it * 16 + 4] = clock64();
-      tmem_st_wait();
+      fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's shared-memory reads
       if (tr) p.trace[it * 16 + 5] = clock64();
       tc_fence_before();
       __syncwarp();
@@ -1138,7 +1201,7 @@ template <int HDP, int HD, int NCTX>
 static int launch_attn3(const AttnParams& p, int NS, cudaStream_t st) {
   constexpr int HDO = (HD + 1 + 15) / 16 * 16;
   constexpr size_t stage = ((size_t)80 * HDP * 2 + HDO * 160 + 1023) / 1024 * 1024;
-  constexpr size_t smem = (size_t)NCTX * 128 * HDP * 2 + 3 * stage + (12 + 4 * NCTX) * 8 + 16;
+  constexpr size_t smem = (size_t)NCTX * 128 * HDP * 2 + 2 * stage + (size_t)NCTX * (128 * 160) + (8 + 6 * NCTX) * 8 + 16;
   static DeviceOnce configured;
   if (configured.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn3_kernel<HDP, HD, NCTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1228,9 +1291,9 @@ extern "C" int ma3_attention(const void* q, const void* k, const void* vt, const
   int BKV = (v2 && 11 * t80 < 10 * t64 && 2 * 80 + (int)vrows <= 256) ? 80 : 64;
   if (v2 && force_bkv == 64) BKV = 64;
   if (v2 && force_bkv == 80 && 2 * 80 + (int)vrows <= 256) BKV = 80;
-  // v3 (several query tiles of a head per CTA, one softmax thread per row) is opt-in: MA3_ATTN_VER=3 or
-  // ma3_debug_set_attn_version(3).  Measured equal to v2 at the XL shape: its single-buffered S puts
-  // the PV -> S turnaround of the tensor pipe (~1400 clocks) on every context's critical path.
+  // v3 (several query tiles of a head per CTA, one softmax thread per row, P through shared memory) is opt-in:
+  // MA3_ATTN_VER=3 or ma3_debug_set_attn_version(3).  Measured equal to v2 at the XL shape (41-42 us against 40 us;
+  // DESIGN section 7b has the timeline): per-CTA fixed costs and the work granularity bound both the same way.
   static const int env_ver = getenv("MA3_ATTN_VER") ? atoi(getenv("MA3_ATTN_VER")) : 0;
   const int force_ver = g_attn_version ? g_attn_version : env_ver;
   const bool v3 = v2 && force_ver == 3;
