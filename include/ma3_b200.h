@@ -37,6 +37,10 @@ int ma3_version(void);
 int ma3_check_device(void);
 /* number of kernel launches enqueued by this library in this process so far (bench.py reports the delta). */
 int64_t ma3_launch_count(void);
+/* Programmatic dependent launch for the launches that follow (kernel attribute, baked into captured graph nodes): 1 on,
+ * 0 off, -1 back to the default (off).  The environment variable MA3_PDL=0|1 overrides every request.  On = each kernel's
+ * prologue overlaps its predecessor's tail: worth 3-5 % on single-clip workloads, -1..2 % on power-capped large batches. */
+int ma3_set_pdl(int on);
 /* L2 access-policy window for launches on `stream` (persisting hits on [ptr, ptr+bytes), streaming elsewhere); NULL
  * removes the stream's window.  Used for the DiT's fp32 residual stream, which every block reads twice and reduces
  * into twice.  NOTE: this is the one entry point with a device-wide side effect: it sizes the device's persisting-L2

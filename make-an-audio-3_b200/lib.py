@@ -98,6 +98,15 @@ def launch_count():
     return int(load().ma3_launch_count())
 
 
+PDL_MAX_ROWS = 2048   # token rows (batch x latent frames) up to which programmatic dependent launch pays (see ma3_set_pdl)
+
+
+def auto_pdl(rows):
+    """Switch programmatic dependent launch for the launches (and graph captures) that follow: on for small, latency-bound
+    batches, off for the power-capped large ones (measured both ways).  MA3_PDL=0|1 overrides."""
+    load().ma3_set_pdl(1 if rows <= PDL_MAX_ROWS else 0)
+
+
 def dt(t):
     return _DT[t.dtype]
 

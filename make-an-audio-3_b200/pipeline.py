@@ -141,6 +141,7 @@ class Txt2AudioPipeline:
         """decode_first_stage + vocode of latents z [B, 20, T] -> waveforms [B, 2T*hop].  With use_graph the ~450
         launches of the two stages are captured once per latent shape and replayed (as the sampler does for its step
         loop), so no host launch latency sits between the short kernels of the VAE and of the early vocoder stages."""
+        L.auto_pdl(2 * z.shape[0] * z.shape[-1])   # same rule as the sampler (whose batch is CFG-doubled)
         if not self.use_graph:
             with stage_range("ma3.decode_first_stage"):
                 mel = self.decode_first_stage(z)

@@ -117,6 +117,7 @@ class CFMSampler:
         ints, dts = euler_schedule(timesteps, t_start)
         S = len(ints)
 
+        L.auto_pdl(N * T)   # kernel attribute, baked into the captured nodes: chosen per workload before anything is launched
         cbuf = dit.prepare_context(ctx)
         work = dit._workspace(N, T)
         # The plan (buffers + captured graph) is valid for these shapes and this schedule, and only as long as none of
