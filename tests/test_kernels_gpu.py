@@ -159,6 +159,37 @@ def test_gemm_gate_residual_and_swiglu(ops):
     assert rel(o, ref) < 8e-3
 
 
+@pytest.mark.parametrize("M,T,E,band,F", [(512, 256, 4, 192, 2048), (300, 100, 3, 64, 256)])
+def test_gemm_batched_band_experts(ops, M, T, E, band, F):
+    """The frequency experts of the MoE feed-forward as two batched launches (flag_large_dit_moe.py:516-538): z selects a
+    band of `band` columns of the input, of the fp32 residual stream and of the gate (a/out/gate_batch_stride), its own
+    stacked weights and its own SwiGLU buffer.  Against the per-band fp32 expression, and the gated-GELU variant (act=4)
+    of the same epilogue against torch's tanh-GELU."""
+    from ma3_b200 import lib as L
+    D = E * band
+    y = torch.randn(M, D, generator=g(50)).bfloat16().cuda()
+    w13 = (torch.randn(E, 2 * F, band, generator=g(51)) / band ** .5).bfloat16().cuda()   # rows interleaved: w1_0, w3_0, w1_1, ...
+    w2 = (torch.randn(E, band, F, generator=g(52)) / F ** .5).bfloat16().cuda()
+    gate = torch.randn(M // T, 3 * D, generator=g(53)).cuda()[:, D:2 * D]                 # a strided slice, like the adaLN table
+    h0 = torch.randn(M, D, generator=g(54)).cuda()
+    for act, fn in ((0, torch.nn.functional.silu), (4, lambda t: torch.nn.functional.gelu(t, approximate="tanh"))):
+        mid = torch.empty(E, M, F, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(y, w13, M=M, N=2 * F, K=band, batch=E, a_ld=D, a_batch_stride=band, b_rows=2 * F, b_batch_stride=2 * F * band,
+                 epi=L.EPI_SWIGLU, act=act, out=mid, out_ld=F, out_batch_stride=M * F)
+        h = h0.clone()
+        ops.gemm(mid, w2, M=M, N=band, K=F, batch=E, a_batch_stride=M * F, b_rows=band, b_batch_stride=band * F,
+                 epi=L.EPI_GATE_RES, out=h, out_ld=D, out_batch_stride=band, gate=gate, gate_batch_stride=band, rows_per_sample=T)
+        ref = h0.clone()
+        for j in range(E):
+            x = y[:, j * band:(j + 1) * band].float()
+            w = w13[j].float()
+            m_ref = (fn(x @ w[0::2].t()) * (x @ w[1::2].t()))
+            assert rel(mid[j], m_ref) < 8e-3
+            ref[:, j * band:(j + 1) * band] += gate[:, j * band:(j + 1) * band].repeat_interleave(T, 0) * \
+                (mid[j].float() @ w2[j].float().t())
+        assert rel(h, ref) < 1e-4
+
+
 @pytest.mark.parametrize("M,N,K,cg", [(4992, 1152, 1152, 1), (4992, 1152, 3072, 2), (624, 768, 2048, 1), (1000, 192, 512, 2)])
 def test_gemm_gate_residual_stream_k(ops, M, N, K, cg):
     """Stream-K work split (equal k-iteration ranges per SM, partial products added by separate reductions) against
