@@ -111,3 +111,38 @@ def test_video_feat_encoder():
     assert torch.equal(v, out) and spec is x
     with pytest.raises(RuntimeError):
         enc.load_state_dict({"embedder.0.weight": lin.weight})
+
+
+@pytest.mark.gpu
+def test_token_ids_to_waveform_end_to_end():
+    """The widened path in one piece: token ids -> FrozenCLAPFLANEmbedder (attached as the pipeline's cond_stage_model,
+    ddpm_audio.py:343-356) -> sample_cfg -> decode_first_stage -> vocode.  The conditioner's output is the [B, 154, 1024]
+    context the txt2audio DiT expects; the waveform equals the one generated from the same embeddings handed in
+    precomputed."""
+    from ma3_b200 import conditioners as Cn
+    from ma3_b200.pipeline import build_random_pipeline
+    bert, t5, proj = _hf_models(2, 2, seed=9)
+    emb = Cn.FrozenCLAPFLANEmbedder(state_dict=_state_dict(bert, t5, proj), bert_cfg=dict(Cn.BERT_BASE, layers=2),
+                                    t5_cfg=dict(Cn.T5_V11_LARGE, layers=2))
+    B, T = 2, 77
+    g = torch.Generator().manual_seed(2)
+    ori, struct = torch.randint(0, 30522, (B, T), generator=g), torch.randint(0, 32128, (B, T), generator=g)
+
+    class Tok:   # stands in for the two tokenizers (no vocabulary files offline): caption i -> row i of a fixed id table
+        def __init__(self, ids): self.ids = ids
+        def __call__(self, text, **kw): return {"input_ids": torch.zeros_like(self.ids[:len(text)]) if text[0] == "" else self.ids[:len(text)]}
+    emb.clap_tokenizer, emb.t5_tokenizer = Tok(ori), Tok(struct)
+    from oracle.cases import BIGVGAN_TINY      # the vocoder layout with a narrow first stage: a small, fast generator
+    pipe = build_random_pipeline("M", vocoder_h=dict(BIGVGAN_TINY), seed=4)
+    pipe.cond_stage_model = emb
+    c = pipe.get_learned_conditioning({"ori_caption": ["a dog barks"] * B, "struct_caption": ["<dog& barks& all>"] * B})
+    uc = pipe.get_learned_conditioning({"ori_caption": [""] * B, "struct_caption": [""] * B})
+    assert c.shape == uc.shape == (B, 2 * T, 1024) and not torch.equal(c, uc)
+    x0 = torch.randn(B, 20, 312, generator=torch.Generator().manual_seed(3)).cuda()
+    wav = pipe.generate(c, uc, x0, scale=3.0, timesteps=5)
+    assert wav.shape == (B, 2 * 312 * 256) and bool(torch.isfinite(wav).all())
+    wav2 = pipe.generate(emb.encode_tokens(ori, struct), emb.encode_tokens(torch.zeros_like(ori), torch.zeros_like(struct)),
+                         x0, scale=3.0, timesteps=5)
+    assert torch.equal(wav, wav2)
+    with pytest.raises(TypeError):
+        build_random_pipeline("M", vocoder_h=dict(BIGVGAN_TINY), seed=4).get_learned_conditioning(["no conditioner attached"])
