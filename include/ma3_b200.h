@@ -66,6 +66,7 @@ const char* ma3_last_error(void);
  *   MA3_EPI_STORE      v = acc (+ bias[n] or bias[m]) (+ res[z,m,n]) ; v = act(alpha*v) ; (+ out_old if accumulate) -> out
  *                      out row = m*out_row_mul + out_row_off (strided rows: transposed-conv phases)
  *   MA3_EPI_GATE_RES   out(f32)[z,m,n] += gate[(m / rows_per_sample), z*gate_batch_stride + n] * acc   (flag_large_dit.py:83-91)
+ *                      (+ the fused-RMSNorm producer outputs described at norm_out below)
  *   MA3_EPI_SWIGLU     out[m, n/2] = silu(acc[m, n]) * acc[m, n+1], n even         (flag_large_dit_moe.py:484-489;
  *                      w1 rows interleaved with w3 rows in B); act == 4: tanh-GELU instead of SiLU (the gated-GELU
  *                      feed-forward of the T5 v1.1 text encoder, ldm/modules/encoders/modules.py:178-191)
@@ -125,6 +126,23 @@ typedef struct ma3_gemm {
   int32_t stream_k;       /* MA3_EPI_GATE_RES only.  0: library heuristic; 1: split the tiles x k-iterations space evenly
                            * over the SMs (partial products are added by separate reductions: fp32 sums may differ in the
                            * last bit from run to run); -1: whole tiles only (bit-reproducible) */
+  /* Fused RMSNorm + adaLN modulate (flag_large_dit.py:79-91, flag_large_dit_moe.py:63-81) -- the stand-alone
+   * normalisation pass between a gated-residual GEMM and the GEMM that consumes the normalised rows is removed by
+   * splitting  u = rms(h) * w * (1 + scale_s) + shift_s  into a row scalar and a per-sample bias:
+   *     u W^T = rstd[m] * ((h * wn_s) W^T) + (shift_s W^T),      wn_s = w * (1 + scale_s),  rstd = rsqrt(mean(h^2) + eps)
+   * Producer (MA3_EPI_GATE_RES with norm_out != NULL; whole tiles, N % 32 == 0): the epilogue owns its elements
+   * (no atomics): h_new = h_old + gate * acc -> out (fp32);  norm_out[m, n] = 16-bit(h_new * norm_w[sample, n]);
+   * ss_out[m, n / 32] = sum over the 32-column chunk of h_new^2 (deterministic per-chunk partial sums). */
+  void* norm_out;         /* [M][out_ld], operand dtype */
+  const float* norm_w;    /* [samples][gate_ld] fp32 (same row pitch as gate) */
+  float* ss_out;          /* [M][ss_cols] fp32, ss_cols >= N / 32 and a multiple of 4 (pad columns must hold zeros) */
+  /* Consumer (MA3_EPI_QKV_ROPE / MA3_EPI_SWIGLU; N % 32 == 0, rows_per_sample > 0): before the epilogue proper
+   *     acc[m, n] <- acc[m, n] * rsqrt(sum_j row_ss[m, j] / ss_dim + ss_eps) + col_bias2[m / rows_per_sample, n] */
+  const float* row_ss;    /* [M][ss_cols] fp32 partial sums of squares (a producer's ss_out); NULL = off */
+  int32_t ss_cols, ss_dim;
+  float ss_eps;
+  const float* col_bias2; /* [samples][col_bias2_ld] fp32 = shift_s W^T */
+  int64_t col_bias2_ld;
 } ma3_gemm_t;
 
 int ma3_gemm(const ma3_gemm_t* g, void* stream);
@@ -218,7 +236,8 @@ int ma3_adaln_input(const float* temb, const float* cap, void* out, int out_dtyp
  * out[b] = [2*rows][cols] bf16 with rows [0, rows) = bf16(x) and rows [rows, 2*rows) = bf16(x - bf16(x)).  A tap-GEMM
  * over (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) then carries ~16 mantissa bits through the bf16 tensor cores.  Used for
  * the step-invariant conditioning path: TimestepEmbedder (flag_large_dit_moe.py:96-133), cap_embedder
- * (flag_large_dit.py:171-174,198) and every adaLN_modulation Linear (flag_large_dit.py:50-51,120-124). */
+ * (flag_large_dit.py:171-174,198), every adaLN_modulation Linear (flag_large_dit.py:50-51,120-124) and the shift_s W^T
+ * bias tables of the fused RMSNorm (ma3_gemm_t.col_bias2). */
 int ma3_split_bf16(const float* x, int64_t ld, int col0, int col_step, int nb, int rows, int cols, void* out,
                    void* stream);
 
@@ -242,7 +261,7 @@ int ma3_melnet_log(const float* mel, float* out, int B, int F, int n_mels, void*
 
 /* mod[r, tail_off + (2i+j)*D + d] = norm_w[i][j][d] * (1 + mod[r, 6*D*i + (j ? 4*D : D) + d]) for r < rows, i < depth,
  * j in {0: attention_norm, 1: ffn_norm}: wn_s = w * (1 + scale_s) of flag_large_dit.py:83-91, written behind the
- * modulation columns of the same row so that it shares their row pitch (the `wn` operand of ma3_gemm_rownorm). */
+ * modulation columns of the same row (ma3_gemm_t.norm_w). */
 int ma3_norm_weights(float* mod, int64_t ld, const float* norm_w, int rows, int depth, int D, int tail_off, void* stream);
 
 /* GroupNorm(groups, eps, affine) optionally followed by swish on channels-last x [B, T, C]

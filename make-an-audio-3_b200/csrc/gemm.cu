@@ -53,6 +53,15 @@ struct GemmKParams {
   int debug_mode;    // diagnostics: 1 = no TMA loads, 2 = no MMAs
   // narrow-conv kernel (conv_narrow_kernel): rows of the staged A tile, smallest tap shift, padded N, A stages
   int cn_rows_a, cn_min_shift, cn_bnp, cn_stages;
+  // fused RMSNorm (see ma3_gemm_t): producer outputs of GATE_RES, consumer pre-op of any epilogue
+  void* norm_out;
+  const float* norm_w;
+  float* ss_out;
+  const float* row_ss;
+  int ss_cols;
+  float ss_inv_dim, ss_eps;
+  const float* col_bias2;
+  long long col_bias2_ld;
   int stream_k;      // GATE_RES only: workers take equal contiguous ranges of (tile, k-iteration) instead of whole tiles
   long long* trace;  // diagnostics: when non-null, CTA 0 records clock64() at pipeline events (tools/probe_trace.py)
 };
@@ -215,7 +224,8 @@ struct RowCtx {
 
 template <int EPI>
 __device__ __forceinline__ void make_row_ctx(const GemmKParams& p, int z, int m0, int lane, RowCtx& rc) {
-  if constexpr (EPI == MA3_EPI_GATE_RES) {
+  if constexpr (EPI == 4) {   // MA3_EPI_GATE_RES_NORM keeps no per-row table (see norm_pre_issue)
+  } else if constexpr (EPI == MA3_EPI_GATE_RES) {
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
       const int m = m0 + pass * 4 + (lane >> 3);
@@ -278,6 +288,96 @@ __device__ __forceinline__ void res_pre_issue(const GemmKParams& p, int n0, int 
   for (int pass = 0; pass < 4; ++pass)
     if (rc.off[pass] >= 0) rp.v[pass] = *reinterpret_cast<const uint4*>(res + rc.aux[pass] + col);
 }
+// Fused-RMSNorm producer (GATE_RES with norm_out; instantiated as its own epilogue kind so that the row bookkeeping of
+// the reduction path does not occupy registers here).  Row-wise mapping as GATE_RES: 8 lanes x float4 cover the 32
+// columns of a row, 4 rows per pass, 8 passes; lane rows are rbase + 4 * pass.  NormPre holds everything a lane needs
+// from global memory for one chunk; it is requested BEFORE the accumulator chunk is loaded and staged so that the L2
+// latency overlaps that work.  The 32 rows of a warp lie in at most two samples (rows_per_sample >= 32, host check),
+// so the per-sample gate and wn vectors are two float4 each instead of one per row.
+constexpr int MA3_EPI_GATE_RES_NORM = 4;   // internal: MA3_EPI_GATE_RES with norm_out != NULL
+
+struct NormPre {
+  float4 h[8];
+  float4 g0, w0, g1, w1;
+  int nvalid;   // passes [0, nvalid) are rows inside M
+  int split;    // passes >= split belong to the lane's second sample
+};
+__device__ __forceinline__ void norm_pre_issue(const GemmKParams& p, int m0, int n0, int lane, NormPre& pf) {
+  const int col = n0 + (lane & 7) * 4;
+  const int rbase = m0 + (lane >> 3);
+  const float* hp = reinterpret_cast<const float*>(p.out) + (long long)rbase * p.out_ld + col;
+  const int left = p.M - rbase;
+  pf.nvalid = left <= 0 ? 0 : (left >= 29 ? 8 : (left + 3) >> 2);
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass)
+    if (pass < pf.nvalid) pf.h[pass] = *reinterpret_cast<const float4*>(hp + (long long)pass * 4 * p.out_ld);
+  const int rb = rbase < p.M ? rbase : p.M - 1;
+  const int s0 = fast_div(rb, p.inv_rows_per_sample);
+  const int to_next = (s0 + 1) * p.rows_per_sample - rbase;      // rows until the next sample starts (>= 1)
+  pf.split = to_next >= 29 ? 8 : (to_next + 3) >> 2;
+  const bool two = __any_sync(0xffffffffu, pf.split < pf.nvalid);
+  const float* gp = p.gate + (long long)s0 * p.gate_ld + col;
+  const float* wp = p.norm_w + (long long)s0 * p.gate_ld + col;
+  pf.g0 = *reinterpret_cast<const float4*>(gp);
+  pf.w0 = *reinterpret_cast<const float4*>(wp);
+  if (two) {
+    const long long o1 = pf.split < pf.nvalid ? p.gate_ld : 0;   // lanes without a second sample re-read the first
+    pf.g1 = *reinterpret_cast<const float4*>(gp + o1);
+    pf.w1 = *reinterpret_cast<const float4*>(wp + o1);
+  } else {
+    pf.g1 = pf.g0;
+    pf.w1 = pf.w0;
+  }
+}
+
+// This tile owns its elements of h (no split-K): the update is a plain load-add-store, and the same pass emits the next
+// GEMM's 16-bit operand h_new * wn_s and the chunk's per-row sum of squares (the 8 lanes of a row reduce by shuffles;
+// one store per row and chunk, so the partial sums are deterministic).
+__device__ __forceinline__ void gate_res_norm_chunk(const GemmKParams& p, int m0, int n0, const uint32_t* r, float* stg,
+                                                    int lane, const NormPre& pf) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) sts_u4(stg + lane * kStagePitch + e, r[e], r[e + 1], r[e + 2], r[e + 3]);
+  __syncwarp();
+  const int cg = (lane & 7) * 4, col = n0 + cg;
+  const int rbase = m0 + (lane >> 3);
+  float* hp = reinterpret_cast<float*>(p.out) + (long long)rbase * p.out_ld + col;
+  uint16_t* gp = reinterpret_cast<uint16_t*>(p.norm_out) + (long long)rbase * p.out_ld + col;
+  float* ssp = p.ss_out + (long long)rbase * p.ss_cols + (n0 >> 5);
+  const long long step = 4 * p.out_ld, ss_step = 4LL * p.ss_cols;
+  const float* sp = stg + (lane >> 3) * kStagePitch + cg;
+  const bool bf16 = p.op_dtype == MA3_BF16;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    float ss = 0.f;
+    const bool ok = pass < pf.nvalid;
+    if (ok) {
+      const bool first = pass < pf.split;
+      const float4 gv = first ? pf.g0 : pf.g1;
+      const float4 wv = first ? pf.w0 : pf.w1;
+      const float4 a = lds_f4(sp);
+      float4 hn;
+      hn.x = fmaf(gv.x, a.x, pf.h[pass].x); hn.y = fmaf(gv.y, a.y, pf.h[pass].y);
+      hn.z = fmaf(gv.z, a.z, pf.h[pass].z); hn.w = fmaf(gv.w, a.w, pf.h[pass].w);
+      *reinterpret_cast<float4*>(hp) = hn;
+      uint2 u;
+      if (bf16) {
+        u.x = pack_bf16(hn.x * wv.x, hn.y * wv.y); u.y = pack_bf16(hn.z * wv.z, hn.w * wv.w);
+      } else {
+        u.x = pack_f16(hn.x * wv.x, hn.y * wv.y); u.y = pack_f16(hn.z * wv.z, hn.w * wv.w);
+      }
+      *reinterpret_cast<uint2*>(gp) = u;
+      ss = fmaf(hn.x, hn.x, fmaf(hn.y, hn.y, fmaf(hn.z, hn.z, hn.w * hn.w)));
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    if ((lane & 7) == 0 && ok) *ssp = ss;
+    hp += step; gp += step; ssp += ss_step;
+    sp += 4 * kStagePitch;
+  }
+  __syncwarp();
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int n0, int w, const uint32_t* r,
                                                float* stg, int lane, const RowCtx& rc, const ResPre* rp = nullptr) {
@@ -728,7 +828,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* staging = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);  // kEpiWarps x 32 x 33 floats
+  float* staging = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);  // kEpiWarps x 32 x kStagePitch floats
+  float* bias_stage = staging + kEpiWarps * 32 * kStagePitch;            // kEpiWarps x 256 floats (fused-norm consumer)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -916,6 +1017,44 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
         continue;
       }
       float* stg = staging + ew * (32 * kStagePitch);
+      // fused-RMSNorm consumer: this thread's accumulator row (TMEM lane) is m0 + lane; its rstd comes from the
+      // producer's per-chunk sums of squares, its bias row from the row's sample (computed while the mainloop runs)
+      // (done while the mainloop of the tile runs).  The bias values of the warp's own column chunks -- for the at most
+      // two samples its 32 rows lie in -- are staged in a private 1 KB patch of shared memory, so the chunk loop reads
+      // them with broadcast LDS instead of L2-latency loads on its critical path.
+      float pre_rstd = 0.f;
+      const float* pre_bias = nullptr;   // this lane's sample row of the staged patch
+      constexpr bool kPreOp = EPI == MA3_EPI_QKV_ROPE || EPI == MA3_EPI_SWIGLU;   // the two consumers of a norm in the DiT
+      if (kPreOp && p.row_ss != nullptr) {
+        const int m = m0 + lane;
+        const int mc = m < p.M ? m : p.M - 1;
+        // every load of this prologue is issued before the first use (fully unrolled, predicated): a rolled loop would
+        // pay one L2 round trip per iteration and delay the warp's start on the tile by more than a mainloop
+        const float4* ssr = reinterpret_cast<const float4*>(p.row_ss + (long long)mc * p.ss_cols);
+        const int n4 = p.ss_cols >> 2;   // <= 16 (host check)
+        float4 sv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sv[j] = j < n4 ? __ldg(ssr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int s_first = fast_div(m0 < p.M ? m0 : p.M - 1, p.inv_rows_per_sample);
+        const int s_mine = fast_div(mc, p.inv_rows_per_sample);
+        const int s_last = __shfl_sync(0xffffffffu, s_mine, 31);
+        float* bs = bias_stage + ew * 256;               // [2 samples][4 chunks][32 columns]
+        // lane l stages float4 #(l & 7) of chunk (l >> 3) for both samples
+        const int bcol = n_t * p.BN + half * 32 + (lane >> 3) * 64 + (lane & 7) * 4;
+        float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0;
+        if (bcol < p.N && (lane >> 3) * 64 + half * 32 < p.BN) {
+          bv0 = __ldg(reinterpret_cast<const float4*>(p.col_bias2 + (long long)s_first * p.col_bias2_ld + bcol));
+          bv1 = __ldg(reinterpret_cast<const float4*>(p.col_bias2 + (long long)s_last * p.col_bias2_ld + bcol));
+        }
+        float s4 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s4 += (sv[j].x + sv[j].y) + (sv[j].z + sv[j].w);
+        pre_rstd = rsqrtf(s4 * p.ss_inv_dim + p.ss_eps);
+        *reinterpret_cast<float4*>(bs + lane * 4) = bv0;
+        *reinterpret_cast<float4*>(bs + 128 + lane * 4) = bv1;
+        __syncwarp();
+        pre_bias = bs + (s_mine == s_first ? 0 : 128);
+      }
       RowCtx rc;
       make_row_ctx<EPI>(p, z, m0, lane, rc);
       if (ew == 0 && lane == 0) trace_evt(p, lt, 4);
@@ -933,6 +1072,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
         ResPre rp;
         // (the same trick for the accumulate operand was measured slower: 16 more live registers spill)
         if constexpr (EPI == MA3_EPI_STORE) res_pre_issue(p, n_t * p.BN + c0, w, lane, rc, rp);
+        NormPre pf;
+        if constexpr (EPI == MA3_EPI_GATE_RES_NORM) {
+          if (n_t * p.BN + c0 >= p.N) continue;   // chunk of a ragged last column tile wholly beyond N
+          norm_pre_issue(p, m0, n_t * p.BN + c0, lane, pf);
+        }
         if (w == 32) {
           tmem_ld32(taddr + c0, r);
         } else {
@@ -943,6 +1087,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
         }
         tmem_ld_wait();
         if (tr0) trace_evt(p, lt, 9);
+        if (kPreOp && pre_bias != nullptr) {   // acc <- acc * rstd[row] + (shift_s W^T)[n]  (staged: zero beyond N)
+          const float* b4 = pre_bias + ((c0 - half * 32) >> 6) * 32;
+          const float2 rs2 = make_float2(pre_rstd, pre_rstd);
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 b = lds_f4(b4 + e);   // same address in every lane of a sample: broadcast
+            const float2 lo = ffma2(make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), rs2, make_float2(b.x, b.y));
+            const float2 hi = ffma2(make_float2(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])), rs2, make_float2(b.z, b.w));
+            r[e] = __float_as_uint(lo.x); r[e + 1] = __float_as_uint(lo.y);
+            r[e + 2] = __float_as_uint(hi.x); r[e + 3] = __float_as_uint(hi.y);
+          }
+        }
         if constexpr (EPI == MA3_EPI_STORE) {
           epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc, &rp);
         } else if constexpr (EPI == MA3_EPI_QKV_ROPE) {
@@ -955,6 +1111,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
           } else {
             epilogue_chunk<EPI>(p, m0, n0, w, r, stg, lane, rc);
           }
+        } else if constexpr (EPI == MA3_EPI_GATE_RES_NORM) {
+          gate_res_norm_chunk(p, m0, n_t * p.BN + c0, r, stg, lane, pf);
         } else {
           epilogue_chunk<EPI>(p, m0, n_t * p.BN + c0, w, r, stg, lane, rc);
         }
@@ -1313,7 +1471,8 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   MA3_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm: tile_n=%d must be a multiple of 16 in [16,256]", BN);
   if (CG == 2) MA3_REQUIRE(BN % 32 == 0, "gemm: cta_group 2 needs tile_n %% 32 == 0 (got %d)", BN);
   const size_t stage_bytes = (size_t)(kBM + BN / CG) * BK * 2;   // per CTA
-  const size_t kTail = 256 + kEpiWarps * 32 * kStagePitch * sizeof(float);  // barriers + epilogue staging
+  // barriers + epilogue staging + per-warp bias patches of the fused-norm consumer
+  const size_t kTail = 256 + kEpiWarps * 32 * kStagePitch * sizeof(float) + kEpiWarps * 256 * sizeof(float);
   const size_t budget = 232448 - 1024 - kTail;
   int stages = (int)(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -1366,6 +1525,18 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
   }
   kp.trace = g_trace;
   kp.debug_mode = g_gemm_debug_mode;
+  if (g->row_ss != nullptr) {
+    MA3_REQUIRE(g->col_bias2 && g->rows_per_sample >= 32 && g->ss_dim > 0 && g->ss_cols > 0 && g->ss_cols % 4 == 0 &&
+                    g->ss_cols <= 64,
+                "gemm/fused-norm consumer: col_bias2, rows_per_sample >= 32, ss_dim, ss_cols %% 4 == 0 (<= 64) required");
+    MA3_REQUIRE(g->N % 32 == 0 && BN % 32 == 0 && g->batch == 1 && aligned16(g->row_ss) && aligned16(g->col_bias2) &&
+                    g->col_bias2_ld % 4 == 0,
+                "gemm/fused-norm consumer: N and tile_n must be multiples of 32, batch 1, 16-byte aligned tables");
+    MA3_REQUIRE(g->epi == MA3_EPI_QKV_ROPE || g->epi == MA3_EPI_SWIGLU,
+                "gemm/fused-norm consumer: only the QKV_ROPE and SWIGLU epilogues take a normalised input in the DiT");
+    kp.row_ss = g->row_ss; kp.ss_cols = g->ss_cols; kp.ss_inv_dim = 1.0f / (float)g->ss_dim; kp.ss_eps = g->ss_eps;
+    kp.col_bias2 = g->col_bias2; kp.col_bias2_ld = g->col_bias2_ld;
+  }
 
   const int total_tiles = kp.tiles_m * kp.tiles_n * kp.batch;
   const int workers = num_sms() / CG;   // CTAs (CG = 1) or CTA pairs (CG = 2)
@@ -1406,6 +1577,17 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
       MA3_REQUIRE(g->N % 4 == 0 && g->out_ld % 4 == 0 && g->gate_ld % 4 == 0 && aligned16(g->out) && aligned16(g->gate),
                   "gemm/gate_res: N, out_ld, gate_ld must be multiples of 4 and pointers 16-byte aligned");
       MA3_REQUIRE(g->stream_k >= -1 && g->stream_k <= 1, "gemm/gate_res: stream_k must be -1, 0 or 1");
+      if (g->norm_out != nullptr) {
+        MA3_REQUIRE(g->norm_w && g->ss_out && g->N % 32 == 0 && BN % 32 == 0 && g->stream_k != 1,
+                    "gemm/gate_res fused norm: norm_w, ss_out, N %% 32 == 0, tile_n %% 32 == 0, no stream-K");
+        MA3_REQUIRE(g->ss_cols >= g->N / 32 && g->ss_cols % 4 == 0, "gemm/gate_res fused norm: ss_cols >= N/32, %% 4 == 0");
+        MA3_REQUIRE(g->rows_per_sample >= 32, "gemm/gate_res fused norm: rows_per_sample must be >= 32");
+        kp.ss_cols = g->ss_cols;
+        MA3_REQUIRE(aligned16(g->norm_out) && aligned16(g->norm_w) && aligned16(g->ss_out) && g->out_ld % 8 == 0,
+                    "gemm/gate_res fused norm: 16-byte aligned pointers, out_ld %% 8 == 0");
+        kp.norm_out = g->norm_out; kp.norm_w = g->norm_w; kp.ss_out = g->ss_out;
+        return launch<MA3_EPI_GATE_RES_NORM>(kp, smem, grid, CG, st);
+      }
       {
         // stream-K when whole tiles would leave a large part of the last wave idle and every worker still gets a
         // reasonable run of k-iterations

@@ -105,6 +105,7 @@ class _Final(nn.Module):
 
 
 _ROWNORM_MIN_CTAS = 100
+_EPI_NORM_MAX_ROWS = 1024
 
 
 class _Work:
@@ -224,13 +225,26 @@ class TxtFlagLargeDiT(nn.Module):
         # normalised, modulated operand of the next projection (ma3_gemm_rownorm): 5 launches per block, no stand-alone
         # RMSNorm pass.  MA3_ROWNORM=0 restores the 7-launch form.
         fused = not self.num_experts and D % 384 == 0 and D // 384 <= 4 and os.environ.get("MA3_ROWNORM", "1") != "0"
+        # Batches too small to fill the row-owning GEMM's single wave fold the norm into the epilogues of the tiled GEMMs
+        # instead (ma3_gemm_t.norm_out / row_ss: the wo / w2 epilogue emits h_new, g = 16-bit(h_new * wn_s) and partial
+        # sums of squares; the QKV / w1|w3 GEMM scales its accumulator rows by rstd and adds shift_s W^T): also 5 launches
+        # per block, which is what counts when every launch is latency-bound.  MA3_EPI_NORM=0 switches it off.
+        epi = fused and not self.qk_norm and D % 32 == 0 and os.environ.get("MA3_EPI_NORM", "1") != "0"
         if fused:
             p["norm_w"] = torch.stack([torch.stack([f32(b_.attention_norm.weight), f32(b_.ffn_norm.weight)])
                                        for b_ in self.blocks]).contiguous()          # [depth, 2, D]
+        if epi:
+            # one contiguous tensor per weight kind, so that the per-block shift_s W^T tables are ONE batched GEMM
+            p["wqkv_all"] = torch.empty(self.depth, 3 * D, D, device=dev, dtype=bf)
+            p["w13_all"] = torch.empty(self.depth, 2 * F, D, device=dev, dtype=bf)
         for bi, blk in enumerate(self.blocks):
             a = blk.attention
             q = {}
-            q["wqkv"] = b16(torch.cat([a.wq.weight, a.wk.weight, a.wv.weight]))
+            if epi:
+                p["wqkv_all"][bi].copy_(torch.cat([a.wq.weight, a.wk.weight, a.wv.weight]).detach())
+                q["wqkv"] = p["wqkv_all"][bi]
+            else:
+                q["wqkv"] = b16(torch.cat([a.wq.weight, a.wk.weight, a.wv.weight]))
             yw = blk.attention_y_norm.weight.detach()[None, :]  # RMSNorm_y scale folded into the projections
             q["wkv_y"] = b16(torch.cat([a.wk_y.weight.detach() * yw, a.wv_y.weight.detach() * yw]))
             q["wo"] = b16(a.wo.weight)
@@ -252,7 +266,11 @@ class TxtFlagLargeDiT(nn.Module):
                 q["f_w2"] = torch.stack([b16(e.w2.weight[j * band:(j + 1) * band, :])
                                          for j, e in enumerate(ff.freq_experts.values())]).contiguous()
             else:
-                q["w13"] = b16(il(ff.w1.weight, ff.w3.weight))
+                if epi:
+                    p["w13_all"][bi].copy_(il(ff.w1.weight, ff.w3.weight))
+                    q["w13"] = p["w13_all"][bi]
+                else:
+                    q["w13"] = b16(il(ff.w1.weight, ff.w3.weight))
                 q["w2"] = b16(ff.w2.weight)
             blocks.append(q)
             ada_w.append(getattr(blk.adaLN_modulation, "1").weight.detach())
@@ -265,6 +283,7 @@ class TxtFlagLargeDiT(nn.Module):
         p["mod_cols"] = 6 * D * self.depth + 2 * D
         # row pitch of the modulation buffer: dense models append wn_s = w * (1 + scale_s) of both norms of every block
         p["fused"] = fused
+        p["epi"] = epi
         p["wn_off"] = p["mod_cols"]
         p["mod_ld"] = p["mod_cols"] + (2 * D * self.depth if fused else 0)
         p["final_w"], p["final_b"] = f32(fl.linear.weight), f32(fl.linear.bias)
@@ -310,6 +329,10 @@ class TxtFlagLargeDiT(nn.Module):
             w.vt = ops.alloc_vt(N, H, hd=hd, hdp=hdp, tokens_pad=Tp, device=dev, dtype=bf)
             w.att = torch.empty(N * T, D, device=dev, dtype=bf)
             w.mid = torch.empty(N * T, F, device=dev, dtype=bf)
+            if self._ensure()["epi"]:
+                w.g = torch.empty(N * T, D, device=dev, dtype=bf)                       # h * wn_s (epilogue-fused RMSNorm operand)
+                # per-chunk sums of squares of h (row pitch padded to 4 floats; the pad columns stay zero)
+                w.ss = torch.zeros(N * T, (D // 32 + 3) // 4 * 4, device=dev, dtype=torch.float32)
             if self.qk_norm:
                 w.qkv_raw = torch.empty(N * T, 3 * D, device=dev, dtype=torch.float32)
             if self.num_experts:
@@ -371,12 +394,35 @@ class TxtFlagLargeDiT(nn.Module):
                      tokens=Lc, tokens_pad=Lp, first_section=1)
         return c
 
-    def cond_buffers(self, S, N):
+    def _norm_mode(self, N, T):
+        """How the RMSNorm + modulate between two projections is realised for a batch of N x T token rows: 'row' = the
+        row-owning cluster GEMM (its single wave of ceil(M / 128) * D / 384 CTAs must fill most of the GPU: XL x 8 prompts =
+        117 of 148 SMs), 'epi' = folded into the epilogues of the tiled GEMMs (small batches), 'plain' = stand-alone pass."""
+        p = self._ensure()
+        if not p["fused"]:
+            return "plain"
+        n_cta = (N * T + 127) // 128 * (self.hidden_size // 384)
+        if _ROWNORM_MIN_CTAS <= n_cta <= ops.sm_count() or os.environ.get("MA3_ROWNORM") == "force":
+            return "row"
+        # Epilogue-fused norms pay while every launch is latency-bound (M x 1 prompt, 624 rows: 28.2 -> 27.1 ms per clip); at
+        # XXL / T = 936 (1872 rows) the heavier epilogues cost more than the two saved launches (137.1 -> 140.5 ms).
+        # A warp's 32 accumulator rows must lie in at most two samples (T >= 32).
+        return "epi" if p["epi"] and T >= 32 and N * T <= _EPI_NORM_MAX_ROWS else "plain"
+
+    def cond_buffers(self, S, N, T=None):
         """Device buffers of one (steps, batch) conditioning: `mod` fp32 [S, N, mod_ld] = the adaLN modulation of every
-        block and of the final layer; fused models append wn_s = w * (1 + scale_s) of both norms of every block."""
+        block and of the final layer; fused models append wn_s = w * (1 + scale_s) of both norms of every block.  When the
+        batch (N x T rows, T given) will run the epilogue-fused norm, also its per-block bias tables
+        b2q [depth, S*N, 3D] = shift_1 Wqkv^T and b2f [depth, S*N, 2F] = shift_2 W13^T."""
         p = self._ensure()
         dev = self.proj_in.weight.device
-        return {"S": S, "N": N, "mod": torch.empty(S, N, p["mod_ld"], device=dev, dtype=torch.float32)}
+        D, F = self.hidden_size, self.ffn_hidden
+        c = {"S": S, "N": N, "mod": torch.empty(S, N, p["mod_ld"], device=dev, dtype=torch.float32)}
+        if T is not None and self._norm_mode(N, T) == "epi":
+            c["b2q"] = torch.empty(self.depth, S * N, 3 * D, device=dev, dtype=torch.float32)
+            c["b2f"] = torch.empty(self.depth, S * N, 2 * F, device=dev, dtype=torch.float32)
+            c["sh2"] = torch.empty(2 * self.depth, 2 * S * N, D, device=dev, dtype=torch.bfloat16)
+        return c
 
     @torch.no_grad()
     def prepare_timesteps(self, t, per_sample=False, out=None):
@@ -409,7 +455,20 @@ class TxtFlagLargeDiT(nn.Module):
         R = S * N
         ops.gemm_split(a, p["ada_w"], M=R, N=p["mod_cols"], K=D, out=mod, out_ld=p["mod_ld"], bias=p["ada_b"])
         if p["fused"]:
-            ops.norm_weights(mod.view(R, p["mod_ld"]), p["norm_w"], self.depth, D, p["wn_off"])
+            m2 = mod.view(R, p["mod_ld"])
+            ops.norm_weights(m2, p["norm_w"], self.depth, D, p["wn_off"])
+            if "b2q" in cb:
+                # shift_s W^T with W the bf16 weights the main GEMMs use: A = (hi, lo) halves of the fp32 shift vectors
+                sh = cb["sh2"]
+                ops.split_bf16(m2, sh[:self.depth], col0=0, col_step=6 * D, nb=self.depth, cols=D)            # shift_1
+                ops.split_bf16(m2, sh[self.depth:], col0=3 * D, col_step=6 * D, nb=self.depth, cols=D)        # shift_2
+                taps = ((0, 0), (R, 0))
+                ops.gemm(sh[:self.depth], p["wqkv_all"], M=R, N=3 * D, K=D, batch=self.depth, a_rows=2 * R,
+                         a_batch_stride=2 * R * D, b_rows=3 * D, b_batch_stride=3 * D * D, taps=taps, out=cb["b2q"],
+                         out_batch_stride=R * 3 * D)
+                ops.gemm(sh[self.depth:], p["w13_all"], M=R, N=2 * F, K=D, batch=self.depth, a_rows=2 * R,
+                         a_batch_stride=2 * R * D, b_rows=2 * F, b_batch_stride=2 * F * D, taps=taps, out=cb["b2f"],
+                         out_batch_stride=R * 2 * F)
         return cb
 
     # ---------------------------------------------------------------- per-step work
@@ -431,10 +490,10 @@ class TxtFlagLargeDiT(nn.Module):
         w = self._workspace(N, T)
         M = N * T
         mod = cond["mod"][k]
-        # the row-owning GEMM is ONE wave of ceil(M / 128) * D / 384 CTAs with an exposed epilogue: it pays when that wave
-        # fills most of the GPU (XL x 8 prompts: 117 of 148 SMs); small batches keep the tiled GEMM + stand-alone norm
-        n_cta = (M + 127) // 128 * (D // 384) if p["fused"] else 0
-        fused = p["fused"] and (_ROWNORM_MIN_CTAS <= n_cta <= ops.sm_count() or os.environ.get("MA3_ROWNORM") == "force")
+        mode = self._norm_mode(N, T)
+        if mode == "epi" and "b2q" not in cond:
+            mode = "plain"                       # conditioning prepared without the bias tables (cond_buffers(S, N) without T)
+        fused = mode == "row"
         qs = math.log2(math.e) / math.sqrt(hd)
         eps = self.norm_eps
         if T > p["rope"].shape[0]:
@@ -443,6 +502,30 @@ class TxtFlagLargeDiT(nn.Module):
         for i, q in enumerate(p["blocks"]):
             o = 6 * D * i
             gate1, gate2 = mod[:, o + 2 * D:o + 3 * D], mod[:, o + 5 * D:o + 6 * D]
+            if mode == "epi":
+                # 5 launches per block with the norms folded into the tiled GEMMs' epilogues (small batches)
+                qkv_kw = dict(M=M, N=3 * D, K=D, epi=L.EPI_QKV_ROPE, q_out=w.q, k_out=w.k, vt_out=w.vt, rope=p["rope"],
+                              model_dim=D, head_dim=hd, head_dim_pad=w.hdp, tokens=T, tokens_pad=w.Tp, q_scale=qs)
+                if i > 0:   # attention_norm of this block was folded into the previous block's w2 epilogue (w.g, w.ss)
+                    ops.gemm(w.g, q["wqkv"], rows_per_sample=T, row_ss=w.ss, ss_dim=D, ss_eps=eps,
+                             col_bias2=cond["b2q"][i, k * N:(k + 1) * N], **qkv_kw)
+                else:
+                    ops.rmsnorm_modulate(w.h, q["attn_norm"], w.u, mod=mod, shift_off=o, scale_off=o + D,
+                                         rows_per_sample=T, eps=eps)
+                    ops.gemm(w.u, q["wqkv"], **qkv_kw)
+                ops.attention(w.q, w.k, w.vt, c["ky"][i] if Lc else None, c["vyt"][i] if Lc else None, q["gate"], w.att,
+                              hd=hd)
+                wn = p["wn_off"] + 2 * D * i
+                ops.gemm(w.att, q["wo"], M=M, N=D, K=D, epi=L.EPI_GATE_RES, out=w.h, gate=gate1, rows_per_sample=T,
+                         norm_out=w.g, norm_w=mod[:, wn + D:wn + 2 * D], ss_out=w.ss)            # -> ffn_norm
+                ops.gemm(w.g, q["w13"], M=M, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=w.mid, out_ld=F, rows_per_sample=T,
+                         row_ss=w.ss, ss_dim=D, ss_eps=eps, col_bias2=cond["b2f"][i, k * N:(k + 1) * N])
+                if i + 1 < self.depth:
+                    ops.gemm(w.mid, q["w2"], M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=w.h, gate=gate2, rows_per_sample=T,
+                             norm_out=w.g, norm_w=mod[:, wn + 2 * D:wn + 3 * D], ss_out=w.ss)    # -> next attention_norm
+                else:
+                    ops.gemm(w.mid, q["w2"], M=M, N=D, K=F, epi=L.EPI_GATE_RES, out=w.h, gate=gate2, rows_per_sample=T)
+                continue
             if not fused or i == 0:
                 ops.rmsnorm_modulate(w.h, q["attn_norm"], w.u, mod=mod, shift_off=o, scale_off=o + D, rows_per_sample=T,
                                      eps=eps)

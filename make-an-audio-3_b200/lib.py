@@ -44,6 +44,9 @@ class GemmDesc(C.Structure):
         ("tokens", C.c_int32), ("tokens_pad", C.c_int32),
         ("q_scale", C.c_float), ("first_section", C.c_int32),
         ("tile_n", C.c_int32), ("cta_group", C.c_int32), ("stream_k", C.c_int32),
+        ("norm_out", C.c_void_p), ("norm_w", C.c_void_p), ("ss_out", C.c_void_p),
+        ("row_ss", C.c_void_p), ("ss_cols", C.c_int32), ("ss_dim", C.c_int32), ("ss_eps", C.c_float),
+        ("col_bias2", C.c_void_p), ("col_bias2_ld", C.c_int64),
     ]
 
 

@@ -80,7 +80,8 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
          out_row_mul=1, out_row_off=0, bias=None, bias_per_row=False, res=None, res_ld=None, res_batch_stride=0,
          alpha=1.0, accumulate=False, gate=None, gate_batch_stride=0, rows_per_sample=0, q_out=None, k_out=None, vt_out=None, rope=None,
          model_dim=0, head_dim=0, head_dim_pad=0, tokens=0, tokens_pad=0, q_scale=1.0, first_section=0, act=0,
-         tile_n=0, cta_group=0, stream_k=0):
+         tile_n=0, cta_group=0, stream_k=0, norm_out=None, norm_w=None, ss_out=None, row_ss=None, ss_dim=0,
+         ss_eps=1e-5, col_bias2=None):
     """acc[z,m,n] = sum_taps sum_k A[z, m + a_shift, k] * B[z, n + b_row, k]; see include/ma3_b200.h."""
     lib = L.require_device()
     assert a.dtype == b.dtype and a.dtype in (torch.bfloat16, torch.float16)
@@ -134,6 +135,16 @@ def gemm(a, b, *, M, N, K, batch=1, a_rows=None, a_ld=None, a_batch_stride=0, b_
     d.tile_n = tile_n
     d.cta_group = cta_group
     d.stream_k = stream_k
+    if norm_out is not None:   # fused-RMSNorm producer (GATE_RES): see include/ma3_b200.h
+        assert norm_w.dtype == torch.float32 and norm_w.stride(0) == gate.stride(0) and ss_out.dtype == torch.float32
+        assert norm_out.dtype == a.dtype and N % 32 == 0 and ss_out.shape[-1] >= N // 32 and ss_out.shape[-1] % 4 == 0
+        d.norm_out, d.norm_w, d.ss_out = norm_out.data_ptr(), norm_w.data_ptr(), ss_out.data_ptr()
+        d.ss_cols = ss_out.shape[-1]
+        d.stream_k = -1
+    if row_ss is not None:     # fused-RMSNorm consumer
+        assert row_ss.dtype == torch.float32 and col_bias2.dtype == torch.float32 and rows_per_sample > 0
+        d.row_ss, d.ss_cols, d.ss_dim, d.ss_eps = row_ss.data_ptr(), row_ss.shape[-1], ss_dim, ss_eps
+        d.col_bias2, d.col_bias2_ld = col_bias2.data_ptr(), col_bias2.stride(0)
     with _Span(f"tap_gemm/{_EPI_NAMES[epi]}/M{M} N{N} K{K} taps{len(taps)} batch{batch}", 2.0 * M * N * K * len(taps) * batch):
         L.check(lib.ma3_gemm(C.byref(d), L.stream_ptr()), "ma3_gemm")
     return out

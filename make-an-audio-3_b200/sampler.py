@@ -128,7 +128,7 @@ class CFMSampler:
         st = self._graphs.get(key)
         if st is None:
             st = {"traj": torch.empty(S + 1, B, C, T, device=dev, dtype=torch.float32),
-                  "cond": dit.cond_buffers(S, N),
+                  "cond": dit.cond_buffers(S, N, T),
                   "v": torch.empty(N, C, T, device=dev, dtype=torch.float32), "graph": None,
                   "keep": (dit._packed, cbuf, work)}
             self._graphs = {key: st}          # keep one plan: buffers are large

@@ -470,6 +470,97 @@ def test_errors(ops):
 
 
 # ------------------------------------------------------------------------------------------------ fused RMSNorm
+@pytest.mark.parametrize("samples,T,D,K", [(3, 104, 1152, 256), (2, 312, 768, 2048), (2, 40, 64, 64), (16, 312, 1152, 1152)])
+def test_fused_rmsnorm_producer(ops, samples, T, D, K):
+    """GATE_RES with norm_out: h_new = h + gate*acc (plain load-add-store), g = bf16(h_new * wn_s), per-chunk sums of
+    squares of h_new -- against the fp32 expression on the same 16-bit operands."""
+    from ma3_b200 import lib as L
+    M = samples * T
+    a = torch.randn(M, K, generator=g(1)).bfloat16().cuda()
+    b = (torch.randn(D, K, generator=g(2)) / K ** 0.5).bfloat16().cuda()
+    h = torch.randn(M, D, generator=g(3)).cuda()
+    mod = torch.randn(samples, 2 * D + 8, generator=g(4)).cuda()           # [gate | wn | pad]
+    gate, wn = mod[:, :D], mod[:, D:2 * D]
+    sc = (D // 32 + 3) // 4 * 4
+    ss = torch.zeros(M, sc, device="cuda")
+    gout = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    acc = a.float() @ b.float().t()
+    rows = torch.arange(M, device="cuda") // T
+    h_ref = h + gate[rows] * acc
+    hh = h.clone()
+    ops.gemm(a, b, M=M, N=D, K=K, epi=L.EPI_GATE_RES, out=hh, gate=gate, rows_per_sample=T, norm_out=gout, norm_w=wn,
+             ss_out=ss)
+    assert rel(hh, h_ref) < 1e-5
+    assert rel(gout, (h_ref * wn[rows])) < 5e-3                           # bf16 rounding of the operand
+    assert rel(ss.sum(1), h_ref.pow(2).sum(1)) < 1e-5
+    assert torch.equal(ss[:, D // 32:], torch.zeros_like(ss[:, D // 32:]))
+    # bit-reproducible (no atomics) and identical to the reduction path's h
+    h2, h3 = h.clone(), h.clone()
+    ops.gemm(a, b, M=M, N=D, K=K, epi=L.EPI_GATE_RES, out=h2, gate=gate, rows_per_sample=T, norm_out=gout, norm_w=wn,
+             ss_out=ss)
+    assert torch.equal(h2, hh)
+    ops.gemm(a, b, M=M, N=D, K=K, epi=L.EPI_GATE_RES, out=h3, gate=gate, rows_per_sample=T)
+    assert rel(h3, hh) < 1e-6
+
+
+@pytest.mark.parametrize("samples,T,D,F", [(3, 104, 1152, 512), (2, 312, 768, 2048), (2, 40, 64, 256)])
+def test_fused_rmsnorm_consumer_swiglu(ops, samples, T, D, F):
+    """SWIGLU with row_ss / col_bias2: acc <- acc * rstd[m] + (shift_s W^T)[n] before the gate."""
+    from ma3_b200 import lib as L
+    M = samples * T
+    gop = torch.randn(M, D, generator=g(5)).bfloat16().cuda()            # h * wn (un-normalised operand)
+    w13 = (torch.randn(2 * F, D, generator=g(6)) / D ** 0.5).bfloat16().cuda()
+    sc = (D // 32 + 3) // 4 * 4
+    ss = torch.zeros(M, sc, device="cuda")
+    ss[:, :D // 32] = torch.rand(M, D // 32, generator=g(7)).cuda() * 40
+    b2 = torch.randn(samples, 2 * F, generator=g(8)).cuda()
+    out = torch.empty(M, F, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(gop, w13, M=M, N=2 * F, K=D, epi=L.EPI_SWIGLU, out=out, out_ld=F, rows_per_sample=T, row_ss=ss, ss_dim=D,
+             ss_eps=1e-5, col_bias2=b2)
+    rstd = torch.rsqrt(ss.sum(1) / D + 1e-5)
+    v = (gop.float() @ w13.float().t()) * rstd[:, None] + b2[torch.arange(M, device="cuda") // T]
+    ref = torch.nn.functional.silu(v[:, 0::2]) * v[:, 1::2]
+    assert rel(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("N,T,D,H", [(2, 312, 1152, 16), (4, 40, 192, 8)])
+def test_fused_rmsnorm_qkv_matches_unfused(ops, N, T, D, H):
+    """The fused chain (producer epilogue -> QKV GEMM with row scale + bias table) against rmsnorm_modulate + QKV GEMM."""
+    from ma3_b200 import lib as L
+    hd = D // H
+    hdp = 64 if hd <= 64 else 128
+    M = N * T
+    h = torch.randn(M, D, generator=g(11)).cuda() * 3
+    w = torch.randn(D, generator=g(12)).cuda() * 0.1 + 1
+    mod = torch.randn(N, 3 * D, generator=g(13)).cuda() * 0.3           # [shift | scale | wn]
+    mod[:, 2 * D:] = w * (1 + mod[:, D:2 * D])
+    wqkv = (torch.randn(3 * D, D, generator=g(14)) / D ** 0.5).bfloat16().cuda()
+    rope = torch.view_as_real(torch.polar(torch.ones(T, hd // 2), torch.outer(torch.arange(T).float(),
+                                                                             1.0 / 10000 ** (torch.arange(0, hd, 2).float() / hd)))).contiguous().cuda()
+    kw = dict(M=M, N=3 * D, K=D, epi=L.EPI_QKV_ROPE, rope=rope, model_dim=D, head_dim=hd, head_dim_pad=hdp, tokens=T,
+              tokens_pad=(T + 7) // 8 * 8, q_scale=0.17)
+    def outs():
+        return (torch.zeros(N, H, T, hdp, device="cuda", dtype=torch.bfloat16),
+                torch.zeros(N, H, T, hdp, device="cuda", dtype=torch.bfloat16),
+                torch.zeros(N, H, hdp, (T + 7) // 8 * 8, device="cuda", dtype=torch.bfloat16))
+    u = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    ops.rmsnorm_modulate(h, w, u, mod=mod, shift_off=0, scale_off=D, rows_per_sample=T)
+    q0, k0, v0 = outs()
+    ops.gemm(u, wqkv, q_out=q0, k_out=k0, vt_out=v0, **kw)
+    # fused: operand g = bf16(h * wn), sums of squares per 32-column chunk, bias table shift W^T (fp32 here)
+    rows = torch.arange(M, device="cuda") // T
+    gop = (h * mod[rows, 2 * D:]).bfloat16()
+    sc = (D // 32 + 3) // 4 * 4
+    ss = torch.zeros(M, sc, device="cuda")
+    ss[:, :D // 32] = h.pow(2).view(M, D // 32, 32).sum(-1)
+    b2 = mod[:, :D] @ wqkv.float().t()
+    q1, k1, v1 = outs()
+    ops.gemm(gop, wqkv, q_out=q1, k_out=k1, vt_out=v1, rows_per_sample=T, row_ss=ss, ss_dim=D, ss_eps=1e-5, col_bias2=b2,
+             **kw)
+    for x0, x1 in ((q0, q1), (k0, k1), (v0, v1)):
+        assert rel(x1, x0) < 1.5e-2 and O.cosine(x1.float().cpu(), x0.float().cpu()) > 0.9999
+
+
 def test_split_bf16_strided_and_norm_weights(ops):
     depth, D, R = 3, 64, 10
     ld = 6 * D * depth + 2 * D + 2 * D * depth
