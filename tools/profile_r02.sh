@@ -22,11 +22,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * N)) -c $N --
 STEP="python tools/repro_step.py 2 8 3"
 $STEP > gpurun_out/r02_plain_step.log 2>&1 || { echo "plain step failed"; tail gpurun_out/r02_plain_step.log; exit 1; }
 cap() {  # name, kernel regex, skip, count
-  ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -o gpurun_out/r02_prof_$1 $STEP > gpurun_out/r02_ncu_$1.log 2>&1
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c $4 -o gpurun_out/r02_prof_$1 $STEP > gpurun_out/r02_ncu_$1.log 2>&1
 }
 cap attn attn2_kernel 4 1
 cap rownorm rowgemm_norm 8 2          # wo (K=1152) and w2 (K=3072) of one block
-cap gemm tap_gemm_kernel 13 2          # QKV+RoPE and w1|w3+SwiGLU of one block (after the conditioning GEMMs)
+cap gemm_qkv 'tap_gemm_kernel<\(int\)3, \(int\)2' 2 1   # QKV+RoPE of one block (EPI 3), third launch of that kind
+cap gemm_swiglu 'tap_gemm_kernel<\(int\)2' 2 1   # w1|w3+SwiGLU of one block (EPI 2)
 cap rms rmsnorm_modulate 2 1
 # vocoder kernels from the bench driver (graph-free)
 ncu --set full --clock-control none --import-source on -k regex:act1d_mma -s 40 -c 2 -o gpurun_out/r02_prof_act1d $BENCH > gpurun_out/r02_ncu_act1d.log 2>&1
