@@ -105,7 +105,7 @@ class _Final(nn.Module):
 
 
 _ROWNORM_MIN_CTAS = 100
-_EPI_NORM_MAX_ROWS = 1024
+_EPI_NORM_MAX_ROWS = int(os.environ.get("MA3_EPI_NORM_ROWS", "1024"))
 
 
 class _Work:
