@@ -293,6 +293,9 @@ int ma3_embed_rows(const float* table, int64_t vocab, const int64_t* ids, const 
 int ma3_act1d_set_filter(const float* taps12, void* stream);
 int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float* alpha, const float* beta, int B,
               int T, int C, int logscale, void* stream);
+/* Activation1d kernel generation for fp16 -> fp16, T % 8 == 0: 0 = default (tiles staged by TMA loads / stores, a warp
+ * per 16 channels x 128 outputs), 1 = the first-generation kernel (cp.async staging).  Diagnostics and tests only. */
+int ma3_debug_set_act_version(int v);
 
 #ifdef __cplusplus
 }

@@ -454,13 +454,255 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __ha
   }
 }
 
+// ------------------------------------------------------------------------------------- tensor-core variant, TMA-staged
+// Same mathematics as act1d_mma_kernel; what changed is everything around the MMAs, which is where that kernel spent
+// two thirds of its issue slots (profiles/r02_ncu_full_act1d_summary.txt: 34.9 M warp-instructions, 0.63 IPC):
+//   * tiles move with TMA in both directions (3-D tensor maps over [B, T, C], 128/64/32-byte swizzle = one tile row):
+//     no per-thread staging loops, no index clamping (rows outside the sequence arrive as zeros and the three rows the
+//     replicate padding of x really needs are patched by the one warp that reads them), no output copy loop;
+//   * a warp owns 16 channels x 128 outputs (17 sample blocks for 16 output groups: 6 % redundant work, was 12.5 %);
+//   * Snake runs on the accumulator register pairs as the MMA delivers them (two samples of one channel per packed
+//     fp32 instruction: no register shuffling), and the sequence-end handling is peeled out of the steady-state loop.
+// Per 16 channels x 16 samples the loop is 1 ldmatrix + 4 MMAs + 8 MUFU.SIN (+ 8 range-reduction FMULs) + 12 packed
+// fp32 + 6 packs + 1 stmatrix; MUFU (16 results / clk / SM) then bounds the kernel at ~0.75 of the HBM time.
+constexpr int kTmaWarps = 4;
+constexpr int kTmaSeg = 128;               // outputs per warp and tile
+
+struct Act1dTmaParams {
+  CUtensorMap tin, tout;                   // [B, T, C] fp16, box {CT, load rows | 128, 1}
+  const float* alpha;
+  const float* beta;
+  int B, T, C, tiles_c, tiles_t, logscale;
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One sample block: 16 channels x 16 activated 2x-rate samples as the fp16 A fragment of the low-pass MMAs.
+// EDGE 1: first block of a sequence (samples 0..5 lie before m = 0 and take s[0] = local sample 6);
+// EDGE 2: last block of a sequence (samples 6..15 lie beyond m = 2T-1 = local sample 5).
+template <int EDGE>
+__device__ __forceinline__ void act_sample_block(uint32_t xaddr, const uint32_t (&bu)[2][2], float2 a0, float2 a1,
+                                                 float2 ib0, float2 ib1, int lane, uint32_t (&sc)[4]) {
+  uint32_t xa[4];
+  ldmatrix_x4_trans(xa, xaddr);
+  float ul[4] = {0.f, 0.f, 0.f, 0.f}, uh[4] = {0.f, 0.f, 0.f, 0.f};
+  mma_f16(ul, xa, bu[0][0], bu[0][1]);     // samples 0..7:  [0],[1] = channel g, samples 2tq, 2tq+1; [2],[3] = channel g+8
+  mma_f16(uh, xa, bu[1][0], bu[1][1]);     // samples 8..15
+  float2 p0 = snake2(make_float2(ul[0], ul[1]), a0, ib0);
+  float2 p1 = snake2(make_float2(ul[2], ul[3]), a1, ib1);
+  float2 p2 = snake2(make_float2(uh[0], uh[1]), a0, ib0);
+  float2 p3 = snake2(make_float2(uh[2], uh[3]), a1, ib1);
+  if constexpr (EDGE == 1) {
+    const float v0 = __shfl_sync(0xffffffffu, p0.x, (lane & ~3) | 3);
+    const float v1 = __shfl_sync(0xffffffffu, p1.x, (lane & ~3) | 3);
+    if ((lane & 3) < 3) { p0 = make_float2(v0, v0); p1 = make_float2(v1, v1); }
+  }
+  if constexpr (EDGE == 2) {
+    const float v0 = __shfl_sync(0xffffffffu, p0.y, (lane & ~3) | 2);
+    const float v1 = __shfl_sync(0xffffffffu, p1.y, (lane & ~3) | 2);
+    if ((lane & 3) == 3) { p0 = make_float2(v0, v0); p1 = make_float2(v1, v1); }
+    p2 = make_float2(v0, v0);
+    p3 = make_float2(v1, v1);
+  }
+  sc[0] = pack_f16(p0.x, p0.y);
+  sc[1] = pack_f16(p1.x, p1.y);
+  sc[2] = pack_f16(p2.x, p2.y);
+  sc[3] = pack_f16(p3.x, p3.y);
+}
+
+__device__ __forceinline__ void act_out_group(uint32_t oaddr, const uint32_t (&lo)[4], const uint32_t (&hi)[4],
+                                              const uint32_t (&bd)[2][2]) {
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  mma_f16(o, lo, bd[0][0], bd[0][1]);
+  mma_f16(o, hi, bd[1][0], bd[1][1]);
+  stmatrix_x2_trans(oaddr, pack_f16(o[0], o[1]), pack_f16(o[2], o[3]));
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kTmaWarps * 32, 4) act1d_tma_kernel(const __grid_constant__ Act1dTmaParams p) {
+  constexpr int CGS = CT / 16;                       // 16-channel groups per tile
+  constexpr int TSPLIT = kTmaWarps / CGS;            // 128-output time segments per tile
+  constexpr int S = kTmaSeg;
+  constexpr int TB = TSPLIT * S;
+  constexpr uint32_t PITCH = CT * 2;                 // bytes per tile row = the swizzle span of the tensor maps
+  constexpr int BOXR = CT == 16 ? 160 : 144;         // rows per load box: S + 16 halo rows, rounded up so that a box is
+                                                     // a multiple of 1024 bytes (swizzle pattern period x 8 rows)
+  constexpr int IN_ROWS = (TSPLIT - 1) * S + BOXR;
+  constexpr uint32_t IN_BYTES = IN_ROWS * PITCH;
+  constexpr uint32_t OUT_BYTES = TB * PITCH;
+  constexpr uint32_t SWZ = CT == 64 ? 0x70u : (CT == 32 ? 0x30u : 0x10u);
+  static_assert(IN_BYTES % 1024 == 0 && OUT_BYTES % 1024 == 0 && (S * PITCH) % 1024 == 0, "tile alignment");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle patterns are functions of the address bits
+  const uint32_t out_base = base + 2 * IN_BYTES;
+  const uint32_t bar0 = out_base + OUT_BYTES;                    // two 8-byte "tile landed" barriers
+  auto swz = [](uint32_t off) { return off ^ ((off >> 3) & SWZ); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int cgi = warp % CGS, seg = warp / CGS;
+  const int total = p.tiles_c * p.tiles_t * p.B;
+  const int T = p.T;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    fence_barrier_init();
+    prefetch_tmap(&p.tin);
+    prefetch_tmap(&p.tout);
+  }
+  // constant B fragments: G^T (two 8-sample halves) and F^T (two 16-sample k-steps)
+  uint32_t bu[2][2], bd[2][2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int k = 2 * tq + 8 * r;
+      bu[hh][r] = pack_f16(up_coef(8 * hh + g, k), up_coef(8 * hh + g, k + 1));
+      bd[hh][r] = pack_f16(dn_coef(16 * hh + k, g), dn_coef(16 * hh + k + 1, g));
+    }
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+
+  auto decode = [&](int item, int& b, int& tb0, int& c0) {
+    const int tile_c = item % p.tiles_c;
+    const int rest = item / p.tiles_c;
+    c0 = tile_c * CT;
+    tb0 = (rest % p.tiles_t) * TB;
+    b = rest / p.tiles_t;
+  };
+  // rows [tb0 - 6, tb0 - 6 + IN_ROWS) x CT of sequence b; rows outside [0, T) arrive as zeros
+  auto issue_load = [&](int item, int buf) {
+    int b, tb0, c0;
+    decode(item, b, tb0, c0);
+    const uint32_t bar = bar0 + 8 * buf;
+    mbar_arrive_expect_tx_u32(bar, (uint32_t)TSPLIT * BOXR * PITCH);
+#pragma unroll
+    for (int i = 0; i < TSPLIT; ++i)
+      tma_load_3d_u32(base + buf * IN_BYTES + i * (S * PITCH), &p.tin, bar, c0, tb0 - 6 + i * S, b);
+  };
+
+  if (tid == 0 && (int)blockIdx.x < total) issue_load(blockIdx.x, 0);
+  int it = 0;
+  for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (tid == 0) {
+      // the other buffer was released by the barrier that closed the previous iteration
+      if (item + (int)gridDim.x < total) {
+        fence_proxy_async_smem();
+        issue_load(item + gridDim.x, buf ^ 1);
+      }
+      bulk_wait_read0();                       // the previous tile's store has drained the output tile
+    }
+    int b, tb0, c0;
+    decode(item, b, tb0, c0);
+    const int cw = c0 + cgi * 16;              // first channel of this warp
+    float al0 = p.alpha[cw + g], al1 = p.alpha[cw + g + 8];
+    float be0 = p.beta ? p.beta[cw + g] : al0, be1 = p.beta ? p.beta[cw + g + 8] : al1;
+    if (p.logscale) { al0 = __expf(al0); al1 = __expf(al1); be0 = __expf(be0); be1 = __expf(be1); }
+    const float i0 = 1.f / (be0 + 1e-9f), i1 = 1.f / (be1 + 1e-9f);
+    const float2 a0 = make_float2(al0, al0), a1 = make_float2(al1, al1);
+    const float2 ib0 = make_float2(i0, i0), ib1 = make_float2(i1, i1);
+    while (!mbar_try_wait(bar0 + 8 * buf, (uint32_t)((it >> 1) & 1))) {
+    }
+    __syncthreads();                           // nobody writes the output tile before its previous store has read it
+    const int tw0 = tb0 + seg * S;             // first output of this warp's segment
+    if (tw0 < T) {
+      const uint32_t in0 = base + buf * IN_BYTES;
+      const int ng = min(S, T - tw0) >> 3;     // output groups of 8; sample blocks 0 .. ng
+      const bool at_start = tw0 == 0, at_end = tw0 + 8 * ng == T;
+      // replicate padding of x: the first / last sample block of a sequence reads three rows beyond it (t = -3..-1,
+      // t = T..T+2).  Only this warp reads them in its 16 channels, so it patches them itself.
+      if (at_start && lane < 6) {
+        const uint32_t col = (uint32_t)(cgi * 32 + (lane & 1) * 16);
+        sts128(in0 + swz((3 + (lane >> 1)) * PITCH + col), lds128(in0 + swz(6 * PITCH + col)));
+      }
+      if (at_end && lane >= 8 && lane < 14) {
+        const int l = lane - 8;
+        const uint32_t col = (uint32_t)(cgi * 32 + (l & 1) * 16);
+        const uint32_t rlast = (uint32_t)(T - 1 - tb0 + 6);
+        sts128(in0 + swz((rlast + 1 + (l >> 1)) * PITCH + col), lds128(in0 + swz(rlast * PITCH + col)));
+      }
+      __syncwarp();
+      // ldmatrix / stmatrix row addresses of this lane for block / group 0: matrix mi = lane / 8 -> rows (mi / 2) * 8 +
+      // lane % 8, channels (mi % 2) * 8 of the warp's group.  Later blocks are 8 rows on: the swizzle term is unchanged.
+      const uint32_t xaddr0 =
+          in0 + swz((uint32_t)(seg * S + ((lane >> 4) << 3) + (lane & 7)) * PITCH + (uint32_t)(cgi * 32 + ((lane >> 3) & 1) * 16));
+      const uint32_t oaddr0 =
+          out_base + swz((uint32_t)(seg * S + (lane & 7)) * PITCH + (uint32_t)(cgi * 32 + ((lane >> 3) & 1) * 16));
+      uint32_t sp[4];
+      if (at_start) act_sample_block<1>(xaddr0, bu, a0, a1, ib0, ib1, lane, sp);
+      else act_sample_block<0>(xaddr0, bu, a0, a1, ib0, ib1, lane, sp);
+      int j = 1;
+#pragma unroll 2
+      for (; j + 1 < ng; j += 2) {             // blocks 1 .. ng-1 never touch a sequence end; two per trip for ILP
+        uint32_t c1[4], c2[4];
+        act_sample_block<0>(xaddr0 + (uint32_t)j * (8 * PITCH), bu, a0, a1, ib0, ib1, lane, c1);
+        act_sample_block<0>(xaddr0 + (uint32_t)(j + 1) * (8 * PITCH), bu, a0, a1, ib0, ib1, lane, c2);
+        act_out_group(oaddr0 + (uint32_t)(j - 1) * (8 * PITCH), sp, c1, bd);
+        act_out_group(oaddr0 + (uint32_t)j * (8 * PITCH), c1, c2, bd);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sp[e] = c2[e];
+      }
+      if (j < ng) {
+        uint32_t c1[4];
+        act_sample_block<0>(xaddr0 + (uint32_t)j * (8 * PITCH), bu, a0, a1, ib0, ib1, lane, c1);
+        act_out_group(oaddr0 + (uint32_t)(j - 1) * (8 * PITCH), sp, c1, bd);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sp[e] = c1[e];
+        ++j;
+      }
+      {                                        // block ng closes the segment
+        uint32_t c1[4];
+        if (at_end) act_sample_block<2>(xaddr0 + (uint32_t)ng * (8 * PITCH), bu, a0, a1, ib0, ib1, lane, c1);
+        else act_sample_block<0>(xaddr0 + (uint32_t)ng * (8 * PITCH), bu, a0, a1, ib0, ib1, lane, c1);
+        act_out_group(oaddr0 + (uint32_t)(ng - 1) * (8 * PITCH), sp, c1, bd);
+      }
+    }
+    fence_proxy_async_smem();                  // stmatrix results -> visible to the TMA store
+    __syncthreads();                           // output tile complete, input buffer `buf` released
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 0; i < TSPLIT; ++i)
+        if (tb0 + i * S < T) tma_store_3d(&p.tout, out_base + i * (S * PITCH), c0, tb0 + i * S, b);
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait0();
+}
+
 static DeviceOnce g_filter_set;   // the taps live in __constant__ memory: one copy per device
 
 }  // namespace ma3
 
 using namespace ma3;
 
+static int g_act_version = 0;   // 0 = default (TMA-staged tensor-core kernel where eligible), 1 = first-generation kernel
+
 extern "C" {
+
+int ma3_debug_set_act_version(int v) {
+  g_act_version = v;
+  return 0;
+}
 
 // 12 taps of the Kaiser-sinc low-pass (filter.py:28-57 with cutoff 0.25, half-width 0.3); set once per process.
 int ma3_act1d_set_filter(const float* taps12, void* stream) {
@@ -487,8 +729,53 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
   MA3_REQUIRE(aligned16(x) && aligned16(out), "act1d: pointers must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const bool no_mma = getenv("MA3_ACT_FP32") != nullptr && getenv("MA3_ACT_FP32")[0] == '1';
+  if (!no_mma && g_act_version != 1 && in_dtype == MA3_F16 && out_dtype == MA3_F16 && T % 8 == 0) {
+    // tensor-core variant, tiles staged by TMA
+    const int CT = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
+    const int TB = (kTmaWarps / (CT / 16)) * kTmaSeg;
+    const int boxr = CT == 16 ? 160 : 144;
+    Act1dTmaParams p;
+    memset(&p, 0, sizeof(p));
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)T, (uint64_t)B};
+    const uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)T * C * 2};
+    const uint32_t box_in[3] = {(uint32_t)CT, (uint32_t)boxr, 1}, box_out[3] = {(uint32_t)CT, (uint32_t)kTmaSeg, 1};
+    int rc = encode_tmap(&p.tin, x, 2, 3, dims, str, box_in, CT * 2);
+    if (rc == 0) rc = encode_tmap(&p.tout, out, 2, 3, dims, str, box_out, CT * 2);
+    if (rc != 0) return rc;
+    p.alpha = alpha;
+    p.beta = beta;
+    p.B = B;
+    p.T = T;
+    p.C = C;
+    p.tiles_c = C / CT;
+    p.tiles_t = (T + TB - 1) / TB;
+    p.logscale = logscale;
+    const long long total = (long long)p.tiles_c * p.tiles_t * B;
+    MA3_REQUIRE(total < (1ll << 31), "act1d: too many tiles");
+    const size_t in_bytes = (size_t)((kTmaWarps / (CT / 16) - 1) * kTmaSeg + boxr) * CT * 2;
+    const size_t smem = 2 * in_bytes + (size_t)TB * CT * 2 + 16 + 1024;   // + barriers + 1024-byte alignment slack
+    long long gridl = 4LL * num_sms();
+    if (gridl > total) gridl = total;
+    cudaError_t le = cudaSuccess;
+#define ACT_TMA_CASE(CTV)                                                                                            \
+  do {                                                                                                               \
+    static DeviceOnce configured;                                                                                    \
+    if (configured.pending()) {                                                                                      \
+      cudaFuncSetAttribute(act1d_tma_kernel<CTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);           \
+      configured.mark();                                                                                             \
+    }                                                                                                                \
+    le = launch_pdl(act1d_tma_kernel<CTV>, dim3((unsigned)gridl), dim3(kTmaWarps * 32), smem, st, 1, p);             \
+  } while (0)
+    if (CT == 64) ACT_TMA_CASE(64);
+    else if (CT == 32) ACT_TMA_CASE(32);
+    else ACT_TMA_CASE(16);
+#undef ACT_TMA_CASE
+    if (le != cudaSuccess) MA3_FAIL((int)le, "act1d launch: %s", cudaGetErrorString(le));
+    MA3_LAUNCH_CHECK("act1d");
+    return 0;
+  }
   if (!no_mma && in_dtype == MA3_F16 && out_dtype == MA3_F16 && T % 8 == 0) {
-    // tensor-core variant (filters as banded-Toeplitz MMAs)
+    // first-generation tensor-core variant (cp.async staging); kept selectable: ma3_debug_set_act_version(1)
     const int CT = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
     const int TB = (kMmaWarps / (CT / 16)) * kMmaTS;
     const int tiles_c = C / CT, tiles_t = (T + TB - 1) / TB;

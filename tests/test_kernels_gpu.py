@@ -447,6 +447,35 @@ def test_act1d(ops, B, Cc, T, dt_in):
     assert rel(out.transpose(1, 2), ref2) < 2e-3
 
 
+@pytest.mark.parametrize("B,Cc,T", [(2, 64, 9984), (1, 384, 1256), (2, 96, 520), (1, 48, 2048), (2, 16, 1544), (1, 32, 8),
+                                    (3, 64, 128), (1, 128, 136), (2, 32, 256), (1, 48, 512), (1, 768, 2496)])
+def test_act1d_tma_staged(ops, B, Cc, T):
+    """fp16 -> fp16, T % 8 == 0: the TMA-staged tensor-core kernel (channel tiles of 64 / 32 / 16, sequence ends inside,
+    at and beyond segment and tile boundaries) against the oracle and against the first-generation kernel."""
+    from ma3_b200 import lib as L_
+    lib = L_.require_device()
+    gg = g(51)
+    x = (torch.randn(B, Cc, T, generator=gg) * 1.5).half()
+    al = torch.randn(Cc, generator=gg) * 0.3
+    be = torch.randn(Cc, generator=gg) * 0.3
+    ref = O.activation1d(x.float(), {"a.act.alpha": al, "a.act.beta": be}, "a",
+                         dict(activation="snakebeta", snake_logscale=True))
+    xin = x.transpose(1, 2).contiguous().cuda()
+    out = torch.full((B, T, Cc), float("nan"), device="cuda", dtype=torch.float16)
+    ops.act1d(xin, out, al.cuda(), be.cuda(), logscale=True)
+    assert rel(out.transpose(1, 2), ref) < 2e-3
+    again = torch.full_like(out, float("nan"))
+    ops.act1d(xin, again, al.cuda(), be.cuda(), logscale=True)
+    assert torch.equal(out, again)
+    lib.ma3_debug_set_act_version(1)
+    try:
+        old = torch.empty_like(out)
+        ops.act1d(xin, old, al.cuda(), be.cuda(), logscale=True)
+    finally:
+        lib.ma3_debug_set_act_version(0)
+    assert rel(out.float(), old.float()) < 1e-3
+
+
 def test_act1d_golden(ops, golden):
     x, al, be = Cs.act_inputs()
     xp = torch.zeros(2, 50, 32)

@@ -1,6 +1,4 @@
 # scratch: the command list of the next gpurun call (rewritten per call)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -4 > gpurun_out/r02n_tests_gpu.log; cat gpurun_out/r02n_tests_gpu.log
-timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/r02n_bench_default.json 2> gpurun_out/r02n_bench_default.err; tail -c 300 gpurun_out/r02n_bench_default.json
-timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/r02n_bench_reference.json 2> gpurun_out/r02n_bench_reference.err; tail -c 300 gpurun_out/r02n_bench_reference.json
-for c in 1 3 4 5; do timeout 600 python bench.py --config $c --steps 3 --warmup 3 --no-cpu-baseline --no-lib-baseline > gpurun_out/r02n_bench_config$c.json 2> gpurun_out/r02n_bench_config$c.err; tail -c 200 gpurun_out/r02n_bench_config$c.json; done
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "act1d" -x 2>&1 | tail -15 > gpurun_out/r02s_tests_act.log; cat gpurun_out/r02s_tests_act.log
+timeout 300 python tools/probe_act1d.py > gpurun_out/r02s_probe_act1d.log 2>&1; cat gpurun_out/r02s_probe_act1d.log
