@@ -465,6 +465,9 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __ha
 //     fp32 instruction: no register shuffling), and the sequence-end handling is peeled out of the steady-state loop.
 // Per 16 channels x 16 samples the loop is 1 ldmatrix + 4 MMAs + 8 MUFU.SIN (+ 8 range-reduction FMULs) + 12 packed
 // fp32 + 6 packs + 1 stmatrix; MUFU (16 results / clk / SM) then bounds the kernel at ~0.75 of the HBM time.
+#ifndef MA3_ACT_ILP4
+#define MA3_ACT_ILP4 1
+#endif
 constexpr int kTmaWarps = 4;
 constexpr int kTmaSeg = 128;               // outputs per warp and tile
 
@@ -473,6 +476,9 @@ struct Act1dTmaParams {
   const float* alpha;
   const float* beta;
   int B, T, C, tiles_c, tiles_t, logscale;
+  int seg;                                 // outputs per warp and tile (multiple of 8, <= kTmaSeg; host picks it so that
+                                           // the tiles divide evenly over the persistent grid)
+  int boxr;                                // rows of a load box (>= seg + 16)
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
@@ -538,16 +544,17 @@ template <int CT>
 __global__ void __launch_bounds__(kTmaWarps * 32, 4) act1d_tma_kernel(const __grid_constant__ Act1dTmaParams p) {
   constexpr int CGS = CT / 16;                       // 16-channel groups per tile
   constexpr int TSPLIT = kTmaWarps / CGS;            // 128-output time segments per tile
-  constexpr int S = kTmaSeg;
-  constexpr int TB = TSPLIT * S;
+  constexpr int SMAX = kTmaSeg;
+  const int S = p.seg;
+  const int TB = TSPLIT * S;
   constexpr uint32_t PITCH = CT * 2;                 // bytes per tile row = the swizzle span of the tensor maps
   constexpr int BOXR = CT == 16 ? 160 : 144;         // rows per load box: S + 16 halo rows, rounded up so that a box is
                                                      // a multiple of 1024 bytes (swizzle pattern period x 8 rows)
-  constexpr int IN_ROWS = (TSPLIT - 1) * S + BOXR;
+  constexpr int IN_ROWS = (TSPLIT - 1) * SMAX + BOXR;
   constexpr uint32_t IN_BYTES = IN_ROWS * PITCH;
-  constexpr uint32_t OUT_BYTES = TB * PITCH;
+  constexpr uint32_t OUT_BYTES = TSPLIT * SMAX * PITCH;
   constexpr uint32_t SWZ = CT == 64 ? 0x70u : (CT == 32 ? 0x30u : 0x10u);
-  static_assert(IN_BYTES % 1024 == 0 && OUT_BYTES % 1024 == 0 && (S * PITCH) % 1024 == 0, "tile alignment");
+  static_assert(IN_BYTES % 1024 == 0 && OUT_BYTES % 1024 == 0 && (SMAX * PITCH) % 1024 == 0, "tile alignment");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle patterns are functions of the address bits
   const uint32_t out_base = base + 2 * IN_BYTES;
@@ -594,21 +601,27 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 4) act1d_tma_kernel(const __gr
     int b, tb0, c0;
     decode(item, b, tb0, c0);
     const uint32_t bar = bar0 + 8 * buf;
-    mbar_arrive_expect_tx_u32(bar, (uint32_t)TSPLIT * BOXR * PITCH);
+    mbar_arrive_expect_tx_u32(bar, (uint32_t)(TSPLIT * p.boxr) * PITCH);
 #pragma unroll
     for (int i = 0; i < TSPLIT; ++i)
       tma_load_3d_u32(base + buf * IN_BYTES + i * (S * PITCH), &p.tin, bar, c0, tb0 - 6 + i * S, b);
   };
 
-  if (tid == 0 && (int)blockIdx.x < total) issue_load(blockIdx.x, 0);
-  int it = 0;
-  for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+  // Tiles of this block: item = blockIdx + i * grid.  The hardware hands consecutive block indices to different SMs, so
+  // the total % grid blocks that run one tile more are spread one (or two) per SM; moving them to every (grid / rem)-th
+  // block index instead measured 12 % slower (35.6 vs 31.8 us at C = 384, T = 9984, B = 8).
+  const int grid = (int)gridDim.x, bid = (int)blockIdx.x;
+  const int n_items = bid < total ? (total - bid + grid - 1) / grid : 0;
+  auto item_of = [&](int i) { return bid + i * grid; };
+  if (tid == 0 && n_items > 0) issue_load(item_of(0), 0);
+  for (int it = 0; it < n_items; ++it) {
     const int buf = it & 1;
+    const int item = item_of(it);
     if (tid == 0) {
       // the other buffer was released by the barrier that closed the previous iteration
-      if (item + (int)gridDim.x < total) {
+      if (it + 1 < n_items) {
         fence_proxy_async_smem();
-        issue_load(item + gridDim.x, buf ^ 1);
+        issue_load(item_of(it + 1), buf ^ 1);
       }
       bulk_wait_read0();                       // the previous tile's store has drained the output tile
     }
@@ -652,6 +665,24 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 4) act1d_tma_kernel(const __gr
       if (at_start) act_sample_block<1>(xaddr0, bu, a0, a1, ib0, ib1, lane, sp);
       else act_sample_block<0>(xaddr0, bu, a0, a1, ib0, ib1, lane, sp);
       int j = 1;
+#if MA3_ACT_ILP4
+      {                                        // four blocks per trip: independent chains
+#pragma unroll 1
+        for (; j + 3 < ng; j += 4) {
+          uint32_t c1[4], c2[4], c3[4], c4[4];
+          act_sample_block<0>(xaddr0 + (uint32_t)j * (8 * PITCH), bu, a0, a1, ib0, ib1, lane, c1);
+          act_sample_block<0>(xaddr0 + (uint32_t)(j + 1) * (8 * PITCH), bu, a0, a1, ib0, ib1, lane, c2);
+          act_sample_block<0>(xaddr0 + (uint32_t)(j + 2) * (8 * PITCH), bu, a0, a1, ib0, ib1, lane, c3);
+          act_sample_block<0>(xaddr0 + (uint32_t)(j + 3) * (8 * PITCH), bu, a0, a1, ib0, ib1, lane, c4);
+          act_out_group(oaddr0 + (uint32_t)(j - 1) * (8 * PITCH), sp, c1, bd);
+          act_out_group(oaddr0 + (uint32_t)j * (8 * PITCH), c1, c2, bd);
+          act_out_group(oaddr0 + (uint32_t)(j + 1) * (8 * PITCH), c2, c3, bd);
+          act_out_group(oaddr0 + (uint32_t)(j + 2) * (8 * PITCH), c3, c4, bd);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sp[e] = c4[e];
+        }
+      }
+#endif
 #pragma unroll 2
       for (; j + 1 < ng; j += 2) {             // blocks 1 .. ng-1 never touch a sequence end; two per trip for ILP
         uint32_t c1[4], c2[4];
@@ -732,13 +763,29 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
   if (!no_mma && g_act_version != 1 && in_dtype == MA3_F16 && out_dtype == MA3_F16 && T % 8 == 0) {
     // tensor-core variant, tiles staged by TMA
     const int CT = C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16);
-    const int TB = (kTmaWarps / (CT / 16)) * kTmaSeg;
-    const int boxr = CT == 16 ? 160 : 144;
+    const int tsplit = kTmaWarps / (CT / 16);
+    const int boxr_max = CT == 16 ? 160 : 144, row_align = 1024 / (CT * 2);
+    const long long grid_max = 4LL * num_sms();
+    // outputs per warp and tile: a segment of S outputs costs S / 8 + 1 sample blocks and the slowest block of the
+    // persistent grid runs ceil(tiles / grid) tiles, so a slightly shorter segment can remove a mostly idle last round
+    int seg = kTmaSeg;
+    static const bool seg_auto = getenv("MA3_ACT_SEG_AUTO") != nullptr && getenv("MA3_ACT_SEG_AUTO")[0] == '1';
+    if (seg_auto) {   // measured slower at the BigVGAN shapes (33.1 vs 31.8 us at C=384): off by default
+      long long best = -1;
+      for (int sc = kTmaSeg; sc >= 96; sc -= 8) {
+        const long long tiles = (long long)(C / CT) * ((T + tsplit * sc - 1) / (tsplit * sc)) * B;
+        const long long cost = ((tiles + grid_max - 1) / grid_max) * (sc / 8 + 1);
+        if (best < 0 || cost < best) { best = cost; seg = sc; }
+      }
+    }
+    const int TB = tsplit * seg;
+    int boxr = (seg + 16 + row_align - 1) / row_align * row_align;
+    if (boxr > boxr_max) boxr = boxr_max;
     Act1dTmaParams p;
     memset(&p, 0, sizeof(p));
     const uint64_t dims[3] = {(uint64_t)C, (uint64_t)T, (uint64_t)B};
     const uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)T * C * 2};
-    const uint32_t box_in[3] = {(uint32_t)CT, (uint32_t)boxr, 1}, box_out[3] = {(uint32_t)CT, (uint32_t)kTmaSeg, 1};
+    const uint32_t box_in[3] = {(uint32_t)CT, (uint32_t)boxr, 1}, box_out[3] = {(uint32_t)CT, (uint32_t)seg, 1};
     int rc = encode_tmap(&p.tin, x, 2, 3, dims, str, box_in, CT * 2);
     if (rc == 0) rc = encode_tmap(&p.tout, out, 2, 3, dims, str, box_out, CT * 2);
     if (rc != 0) return rc;
@@ -750,11 +797,13 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
     p.tiles_c = C / CT;
     p.tiles_t = (T + TB - 1) / TB;
     p.logscale = logscale;
+    p.seg = seg;
+    p.boxr = boxr;
     const long long total = (long long)p.tiles_c * p.tiles_t * B;
     MA3_REQUIRE(total < (1ll << 31), "act1d: too many tiles");
-    const size_t in_bytes = (size_t)((kTmaWarps / (CT / 16) - 1) * kTmaSeg + boxr) * CT * 2;
-    const size_t smem = 2 * in_bytes + (size_t)TB * CT * 2 + 16 + 1024;   // + barriers + 1024-byte alignment slack
-    long long gridl = 4LL * num_sms();
+    const size_t in_bytes = (size_t)((tsplit - 1) * kTmaSeg + boxr_max) * CT * 2;
+    const size_t smem = 2 * in_bytes + (size_t)tsplit * kTmaSeg * CT * 2 + 16 + 1024;   // + barriers + 1024-byte alignment slack
+    long long gridl = grid_max;
     if (gridl > total) gridl = total;
     cudaError_t le = cudaSuccess;
 #define ACT_TMA_CASE(CTV)                                                                                            \
