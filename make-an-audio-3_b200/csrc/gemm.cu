@@ -53,6 +53,7 @@ struct GemmKParams {
   int debug_mode;    // diagnostics: 1 = no TMA loads, 2 = no MMAs
   // narrow-conv kernel (conv_narrow_kernel): rows of the staged A tile, smallest tap shift, padded N, A stages
   int cn_rows_a, cn_min_shift, cn_bnp, cn_stages;
+  int cn_lin, cn_tap_step;   // taps equally spaced (a_shift[t] = a_shift[0] + t * cn_tap_step): descriptor increments
   // fused RMSNorm (see ma3_gemm_t): producer outputs of GATE_RES, consumer pre-op of any epilogue
   void* norm_out;
   const float* norm_w;
@@ -1157,6 +1158,96 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tap_gemm_kernel(const __grid_
 //     flight.
 constexpr int kCnAcc = 4;   // accumulator stages of 64 columns
 
+// Lean epilogue of the narrow-conv kernel for the layers that make up the vocoder (16-bit channels-last output, whole
+// 8-column groups, per-column bias or none, residual and previous output of the output's type, no activation):
+// out = (acc + bias + res) * alpha (+ out).  The generic row-direct code serves every epilogue option at run time and
+// is ~8000 instructions; at two epilogue warps per scheduler the kernel then waits on instruction fetch and branches
+// (profiles/r02_ncu_full_convn_summary.txt: stall reasons no_instruction 2.1, branch_resolving 1.3 per issue).
+template <bool kBf16>
+__device__ __forceinline__ uint4 cn_lean_group(const uint32_t* r, const float* sb, bool has_res, uint4 rv, float alpha,
+                                               bool has_acc, uint4 av) {
+  const float4 b0 = lds_f4(sb), b1 = lds_f4(sb + 4);
+  float v[8] = {__uint_as_float(r[0]) + b0.x, __uint_as_float(r[1]) + b0.y, __uint_as_float(r[2]) + b0.z,
+                __uint_as_float(r[3]) + b0.w, __uint_as_float(r[4]) + b1.x, __uint_as_float(r[5]) + b1.y,
+                __uint_as_float(r[6]) + b1.z, __uint_as_float(r[7]) + b1.w};
+  if (has_res) {
+    float x[8];
+    unpack16(rv, kBf16 ? MA3_BF16 : MA3_F16, x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += x[e];
+  }
+  if (has_acc) {
+    float x[8];
+    unpack16(av, kBf16 ? MA3_BF16 : MA3_F16, x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], alpha, x[e]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= alpha;
+  }
+  if (kBf16) return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  return make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
+}
+
+template <bool kBf16>
+__device__ __forceinline__ void cn_lean_epilogue(const GemmKParams& p, int z, int m, uint32_t taddr, uint64_t* t_full,
+                                                 uint32_t t_parity, uint64_t* t_empty, const float* sbias, int lane) {
+  const int ngr = p.N >> 3;                 // whole 8-column groups (host guarantees N % 8 == 0, N <= 64)
+  const bool valid = m < p.M, has_res = p.res != nullptr, has_acc = p.accumulate != 0;
+  const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
+  const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res) + (long long)z * p.res_batch_stride + orow * p.res_ld;
+  uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)z * p.out_batch_stride + orow * p.out_ld;
+  uint4 rr[8], ro[8];
+#pragma unroll
+  for (int gq = 0; gq < 8; ++gq) {
+    rr[gq] = make_uint4(0u, 0u, 0u, 0u);
+    ro[gq] = make_uint4(0u, 0u, 0u, 0u);
+    if (valid && gq < ngr) {
+      if (has_res) rr[gq] = *reinterpret_cast<const uint4*>(rp + gq * 8);
+      if (has_acc) ro[gq] = *reinterpret_cast<const uint4*>(op + gq * 8);
+    }
+  }
+  mbar_wait(t_full, t_parity);
+  tc_fence_after();
+  uint32_t r[4][16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    if (c * 16 < p.cn_bnp) tmem_ld16(taddr + c * 16, r[c]);
+  tmem_ld_wait();
+  // the accumulator stage is free as soon as it is in registers: the MMA warp gets it back before the stores go out
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_relaxed(t_empty);
+  if (!valid) return;
+#pragma unroll
+  for (int gq = 0; gq < 8; ++gq) {
+    if (gq < ngr) {
+      const uint4 o = cn_lean_group<kBf16>(&r[gq >> 1][(gq & 1) * 8], sbias + gq * 8, has_res, rr[gq], p.alpha, has_acc, ro[gq]);
+      *reinterpret_cast<uint4*>(op + gq * 8) = o;
+    }
+  }
+}
+
+// All MMAs of one output tile when the taps are equally spaced: the operand descriptors advance by constant increments,
+// so the single issuing thread spends two integer adds per MMA.  (Looking every tap's shift up in the parameter block
+// cost ~75 dependent uniform-datapath instructions per tap: the issuing thread, not the tensor pipe (12 % busy), the
+// loads or the epilogue, set the tile rate of the 32- and 48-channel layers at ~2000 clocks per tile.)
+template <int KS>
+__device__ __forceinline__ void cn_issue_tile(uint32_t d_tmem, uint32_t at, uint32_t wt, uint32_t a_step, uint32_t w_step,
+                                              int taps, uint32_t dhi, uint32_t idesc) {
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) umma_f16_lohi<1>(d_tmem, at + 2 * ks, wt + 2 * ks, dhi, idesc, ks != 0 ? 1u : 0u);
+#pragma unroll 1
+  for (int tap = 1; tap < taps; ++tap) {
+    at += a_step;
+    wt += w_step;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) umma_f16_lohi<1>(d_tmem, at + 2 * ks, wt + 2 * ks, dhi, idesc, 1u);
+  }
+}
+
+// kLean: 0 = generic row-direct epilogue, 1 = lean fp16, 2 = lean bf16
+template <int kLean>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1232,6 +1323,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
       const uint32_t dhi = (uint32_t)(d0 >> 32), a_lo0 = (uint32_t)d0;
       const uint32_t w_lo0 = (uint32_t)umma_desc_kmajor(smem_u32(sW), 128);
       const uint32_t a_stage16 = a_stage >> 4, w_tap16 = w_tap_bytes >> 4;
+      const uint32_t a_first = (uint32_t)(p.a_shift[0] - p.cn_min_shift) * 8u;
       mbar_wait(w_full, 0);
       int s = 0, lt = 0;
       uint32_t ph = 0;
@@ -1242,11 +1334,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 64;
         const uint32_t a_lo = a_lo0 + (uint32_t)s * a_stage16;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const uint32_t at = a_lo + (uint32_t)(p.a_shift[tap] - p.cn_min_shift) * 8u;   // 128-byte rows = 8 x 16 B
-          const uint32_t wt = w_lo0 + (uint32_t)tap * w_tap16;
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_f16_lohi<1>(d_tmem, at + 2 * ks, wt + 2 * ks, dhi, idesc, (tap | ks) != 0 ? 1u : 0u);
+        if (p.cn_lin) {
+          const uint32_t at0 = a_lo + a_first, a_step = (uint32_t)(p.cn_tap_step * 8);
+          if (ksteps == 1) cn_issue_tile<1>(d_tmem, at0, w_lo0, a_step, w_tap16, p.taps, dhi, idesc);
+          else if (ksteps == 2) cn_issue_tile<2>(d_tmem, at0, w_lo0, a_step, w_tap16, p.taps, dhi, idesc);
+          else if (ksteps == 3) cn_issue_tile<3>(d_tmem, at0, w_lo0, a_step, w_tap16, p.taps, dhi, idesc);
+          else cn_issue_tile<4>(d_tmem, at0, w_lo0, a_step, w_tap16, p.taps, dhi, idesc);
+        } else {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const uint32_t at = a_lo + (uint32_t)(p.a_shift[tap] - p.cn_min_shift) * 8u;   // 128-byte rows = 8 x 16 B
+            const uint32_t wt = w_lo0 + (uint32_t)tap * w_tap16;
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_f16_lohi<1>(d_tmem, at + 2 * ks, wt + 2 * ks, dhi, idesc, (tap | ks) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&a_empty[s]);
         umma_commit(&t_full[as]);
@@ -1261,6 +1361,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
       const int m_t = tile % p.tiles_m, z = tile / p.tiles_m;
       const int as = lt & (kCnAcc - 1);
       const int m = m_t * kBM + q * 32 + lane;
+      if constexpr (kLean != 0) {
+        cn_lean_epilogue<kLean == 2>(p, z, m, tmem_base + ((uint32_t)(q * 32) << 16) + as * 64, &t_full[as],
+                                     (uint32_t)((lt / kCnAcc) & 1), &t_empty[as], sbias, lane);
+        continue;
+      }
       RowRes<8> rr;
       rowdirect_prefetch(p, z, m, 0, p.cn_bnp, rr);
       RowRes<8> ro;
@@ -1313,6 +1418,10 @@ static int try_conv_narrow(const ma3_gemm_t* g, GemmKParams& kp, cudaStream_t st
   if (stages < 2) return 1;
   if (stages > 4) stages = 4;
   kp.cn_rows_a = rows_a; kp.cn_min_shift = lo; kp.cn_bnp = bnp; kp.cn_stages = stages;
+  kp.cn_tap_step = g->a_shift[1] - g->a_shift[0];
+  kp.cn_lin = 1;
+  for (int i = 2; i < g->taps; ++i)
+    if (g->a_shift[i] - g->a_shift[i - 1] != kp.cn_tap_step) kp.cn_lin = 0;
   kp.BN = bnp; kp.BK = 64;
   kp.tiles_m = (g->M + kBM - 1) / kBM; kp.tiles_n = 1;
   const bool a_batched = g->a_batch_stride != 0;
@@ -1333,15 +1442,25 @@ static int try_conv_narrow(const ma3_gemm_t* g, GemmKParams& kp, cudaStream_t st
   const size_t smem = 1024 + w_bytes + stages * a_stage + tail;
   static DeviceOnce configured;
   if (configured.pending()) {
-    cudaError_t e = cudaFuncSetAttribute(conv_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(conv_narrow_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_narrow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_narrow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(conv_narrow): %s", cudaGetErrorString(e));
     configured.mark();
   }
   const int total_tiles = kp.tiles_m * g->batch;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  // lean epilogue: 16-bit output in whole 8-column groups, residual / previous output of the same type, column bias or
+  // none, no activation (MA3_CONV_LEAN=0 keeps the generic epilogue)
+  static const bool lean_off = getenv("MA3_CONV_LEAN") != nullptr && getenv("MA3_CONV_LEAN")[0] == '0';
+  const bool lean = !lean_off && kp.vec_ok && g->out_dtype != MA3_F32 && g->N % 8 == 0 && g->act == 0 &&
+                    !(g->bias && g->bias_per_row) && (!g->res || g->res_dtype == g->out_dtype);
+  const size_t smem_l = smem < 120 * 1024 ? 120 * 1024 : smem;
   // at least half of the SM's shared memory so that one CTA (and its 256 TMEM columns) lives per SM
-  cudaError_t e = launch_pdl(conv_narrow_kernel, dim3((unsigned)grid), dim3(kGemmThreads), smem < 120 * 1024 ? 120 * 1024 : smem,
-                             st, 1, kp);
+  cudaError_t e;
+  if (!lean) e = launch_pdl(conv_narrow_kernel<0>, dim3((unsigned)grid), dim3(kGemmThreads), smem_l, st, 1, kp);
+  else if (g->out_dtype == MA3_F16) e = launch_pdl(conv_narrow_kernel<1>, dim3((unsigned)grid), dim3(kGemmThreads), smem_l, st, 1, kp);
+  else e = launch_pdl(conv_narrow_kernel<2>, dim3((unsigned)grid), dim3(kGemmThreads), smem_l, st, 1, kp);
   if (e != cudaSuccess) MA3_FAIL((int)e, "conv_narrow launch: %s", cudaGetErrorString(e));
   MA3_LAUNCH_CHECK("conv_narrow");
   return 0;

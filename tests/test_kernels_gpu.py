@@ -139,6 +139,28 @@ def test_gemm_narrow_conv_epilogue(ops, C, k, dil, T):
     assert rel(o32, torch.tanh(ref[..., :1])) < 1e-3
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_gemm_narrow_conv_lean_variants(ops, dt):
+    """Lean epilogue of the narrow-conv kernel: no bias, bf16 as well as fp16, output rows written with a row stride
+    (ConvTranspose phases: out_row_mul / out_row_off), ragged last tile; the rows in between must stay untouched."""
+    B, T, C, k = 2, 333, 48, 3
+    x = torch.randn(B, T, C, generator=g(70)).to(dt).cuda()
+    w = (torch.randn(C, C, k, generator=g(71)) / (C * k) ** .5).to(dt).cuda()
+    wp = w.permute(2, 0, 1).contiguous().view(k * C, C)
+    taps = [(j - 1, j * C) for j in range(k)]
+    ref = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.float(), None, padding=1).transpose(1, 2)
+    tol = 2e-3 if dt == torch.float16 else 1e-2
+    y = torch.empty(B, T, C, device="cuda", dtype=dt)
+    ops.gemm(x, wp, M=T, N=C, K=C, batch=B, a_rows=T, a_batch_stride=T * C, b_rows=k * C, taps=taps, out=y,
+             out_batch_stride=T * C)
+    assert rel(y, ref) < tol
+    y2 = torch.full((B, 2 * T, C), 7.0, device="cuda", dtype=dt)
+    ops.gemm(x, wp, M=T, N=C, K=C, batch=B, a_rows=T, a_batch_stride=T * C, b_rows=k * C, taps=taps, out=y2,
+             out_batch_stride=2 * T * C, out_row_mul=2, out_row_off=1, alpha=0.5)
+    assert rel(y2[:, 1::2], 0.5 * ref) < tol
+    assert bool((y2[:, 0::2] == 7.0).all())
+
+
 def test_gemm_gate_residual_and_swiglu(ops):
     from ma3_b200 import lib as L
     M, N, K, T = 624, 768, 768, 312

@@ -1,4 +1,5 @@
 # scratch: the command list of the next gpurun call (rewritten per call)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "act1d" -x 2>&1 | tail -3 > gpurun_out/r02t_tests_act.log; cat gpurun_out/r02t_tests_act.log
-timeout 300 python tools/probe_act1d.py > gpurun_out/r02t_probe_act1d.log 2>&1; grep v0 gpurun_out/r02t_probe_act1d.log
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "narrow or conv" -x 2>&1 | tail -3 > gpurun_out/r02u_tests_conv.log; cat gpurun_out/r02u_tests_conv.log
+timeout 600 python -m pytest tests/test_modules_gpu.py -q -m gpu -k "bigvgan or vocode" -x 2>&1 | tail -3
+timeout 300 python tools/probe_vocoder.py > gpurun_out/r02u_probe_vocoder.log 2>&1; grep "conv" gpurun_out/r02u_probe_vocoder.log | grep "C96\|C48\|C32"
