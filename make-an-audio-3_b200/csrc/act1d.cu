@@ -540,8 +540,12 @@ __device__ __forceinline__ void act_out_group(uint32_t oaddr, const uint32_t (&l
   stmatrix_x2_trans(oaddr, pack_f16(o[0], o[1]), pack_f16(o[2], o[3]));
 }
 
-template <int CT>
-__global__ void __launch_bounds__(kTmaWarps * 32, 4) act1d_tma_kernel(const __grid_constant__ Act1dTmaParams p) {
+// INPLACE: every 128-output segment has its own (outputs + 16 halo) row region of the input buffer and a warp writes
+// output group g over rows 8g+8 .. 8g+15 of its region -- rows whose last readers (sample blocks g and g+1) are the very
+// operands of that group, so the ordering is a true register dependency -- and the TMA store reads the tile back from
+// the input buffer: no output tile, 37-42 KB instead of 54 KB per CTA, five CTAs (20 warps) per SM instead of four.
+template <int CT, bool INPLACE>
+__global__ void __launch_bounds__(kTmaWarps * 32, INPLACE ? 5 : 4) act1d_tma_kernel(const __grid_constant__ Act1dTmaParams p) {
   constexpr int CGS = CT / 16;                       // 16-channel groups per tile
   constexpr int TSPLIT = kTmaWarps / CGS;            // 128-output time segments per tile
   constexpr int SMAX = kTmaSeg;
@@ -550,9 +554,9 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 4) act1d_tma_kernel(const __gr
   constexpr uint32_t PITCH = CT * 2;                 // bytes per tile row = the swizzle span of the tensor maps
   constexpr int BOXR = CT == 16 ? 160 : 144;         // rows per load box: S + 16 halo rows, rounded up so that a box is
                                                      // a multiple of 1024 bytes (swizzle pattern period x 8 rows)
-  constexpr int IN_ROWS = (TSPLIT - 1) * SMAX + BOXR;
+  constexpr int IN_ROWS = INPLACE ? TSPLIT * BOXR : (TSPLIT - 1) * SMAX + BOXR;
   constexpr uint32_t IN_BYTES = IN_ROWS * PITCH;
-  constexpr uint32_t OUT_BYTES = TSPLIT * SMAX * PITCH;
+  constexpr uint32_t OUT_BYTES = INPLACE ? 0 : TSPLIT * SMAX * PITCH;
   constexpr uint32_t SWZ = CT == 64 ? 0x70u : (CT == 32 ? 0x30u : 0x10u);
   static_assert(IN_BYTES % 1024 == 0 && OUT_BYTES % 1024 == 0 && (SMAX * PITCH) % 1024 == 0, "tile alignment");
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -604,8 +608,9 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 4) act1d_tma_kernel(const __gr
     mbar_arrive_expect_tx_u32(bar, (uint32_t)(TSPLIT * p.boxr) * PITCH);
 #pragma unroll
     for (int i = 0; i < TSPLIT; ++i)
-      tma_load_3d_u32(base + buf * IN_BYTES + i * (S * PITCH), &p.tin, bar, c0, tb0 - 6 + i * S, b);
+      tma_load_3d_u32(base + buf * IN_BYTES + i * ((INPLACE ? BOXR : S) * PITCH), &p.tin, bar, c0, tb0 - 6 + i * S, b);
   };
+  const int seg_row = seg * (INPLACE ? BOXR : S);   // first buffer row of this warp's segment
 
   // Tiles of this block: item = blockIdx + i * grid.  The hardware hands consecutive block indices to different SMs, so
   // the total % grid blocks that run one tile more are spread one (or two) per SM; moving them to every (grid / rem)-th
@@ -618,12 +623,14 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 4) act1d_tma_kernel(const __gr
     const int buf = it & 1;
     const int item = item_of(it);
     if (tid == 0) {
-      // the other buffer was released by the barrier that closed the previous iteration
+      // the other buffer was released by the barrier that closed the previous iteration; in place, the previous tile's
+      // store still reads its outputs from that buffer
+      if constexpr (INPLACE) bulk_wait_read0();
       if (it + 1 < n_items) {
         fence_proxy_async_smem();
         issue_load(item_of(it + 1), buf ^ 1);
       }
-      bulk_wait_read0();                       // the previous tile's store has drained the output tile
+      if constexpr (!INPLACE) bulk_wait_read0();   // the previous tile's store has drained the output tile
     }
     int b, tb0, c0;
     decode(item, b, tb0, c0);
@@ -636,7 +643,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 4) act1d_tma_kernel(const __gr
     const float2 ib0 = make_float2(i0, i0), ib1 = make_float2(i1, i1);
     while (!mbar_try_wait(bar0 + 8 * buf, (uint32_t)((it >> 1) & 1))) {
     }
-    __syncthreads();                           // nobody writes the output tile before its previous store has read it
+    if constexpr (!INPLACE) __syncthreads();   // nobody writes the output tile before its previous store has read it
     const int tw0 = tb0 + seg * S;             // first output of this warp's segment
     if (tw0 < T) {
       const uint32_t in0 = base + buf * IN_BYTES;
@@ -651,16 +658,17 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 4) act1d_tma_kernel(const __gr
       if (at_end && lane >= 8 && lane < 14) {
         const int l = lane - 8;
         const uint32_t col = (uint32_t)(cgi * 32 + (l & 1) * 16);
-        const uint32_t rlast = (uint32_t)(T - 1 - tb0 + 6);
+        const uint32_t rlast = (uint32_t)(seg_row + T - 1 - tw0 + 6);
         sts128(in0 + swz((rlast + 1 + (l >> 1)) * PITCH + col), lds128(in0 + swz(rlast * PITCH + col)));
       }
       __syncwarp();
       // ldmatrix / stmatrix row addresses of this lane for block / group 0: matrix mi = lane / 8 -> rows (mi / 2) * 8 +
       // lane % 8, channels (mi % 2) * 8 of the warp's group.  Later blocks are 8 rows on: the swizzle term is unchanged.
       const uint32_t xaddr0 =
-          in0 + swz((uint32_t)(seg * S + ((lane >> 4) << 3) + (lane & 7)) * PITCH + (uint32_t)(cgi * 32 + ((lane >> 3) & 1) * 16));
+          in0 + swz((uint32_t)(seg_row + ((lane >> 4) << 3) + (lane & 7)) * PITCH + (uint32_t)(cgi * 32 + ((lane >> 3) & 1) * 16));
       const uint32_t oaddr0 =
-          out_base + swz((uint32_t)(seg * S + (lane & 7)) * PITCH + (uint32_t)(cgi * 32 + ((lane >> 3) & 1) * 16));
+          (INPLACE ? in0 : out_base) +
+          swz((uint32_t)(seg_row + (INPLACE ? 8 : 0) + (lane & 7)) * PITCH + (uint32_t)(cgi * 32 + ((lane >> 3) & 1) * 16));
       uint32_t sp[4];
       if (at_start) act_sample_block<1>(xaddr0, bu, a0, a1, ib0, ib1, lane, sp);
       else act_sample_block<0>(xaddr0, bu, a0, a1, ib0, ib1, lane, sp);
@@ -713,7 +721,9 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 4) act1d_tma_kernel(const __gr
     if (tid == 0) {
 #pragma unroll
       for (int i = 0; i < TSPLIT; ++i)
-        if (tb0 + i * S < T) tma_store_3d(&p.tout, out_base + i * (S * PITCH), c0, tb0 + i * S, b);
+        if (tb0 + i * S < T)
+          tma_store_3d(&p.tout, INPLACE ? base + buf * IN_BYTES + (uint32_t)(i * BOXR + 8) * PITCH : out_base + i * (S * PITCH), c0,
+                       tb0 + i * S, b);
       bulk_commit();
     }
   }
@@ -801,23 +811,34 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
     p.boxr = boxr;
     const long long total = (long long)p.tiles_c * p.tiles_t * B;
     MA3_REQUIRE(total < (1ll << 31), "act1d: too many tiles");
-    const size_t in_bytes = (size_t)((tsplit - 1) * kTmaSeg + boxr_max) * CT * 2;
-    const size_t smem = 2 * in_bytes + (size_t)tsplit * kTmaSeg * CT * 2 + 16 + 1024;   // + barriers + 1024-byte alignment slack
-    long long gridl = grid_max;
+    // in-place outputs (five CTAs per SM instead of four): measured equal (32.9 vs 32.5 us at C = 384, T = 9984, B = 8:
+    // 4.2 instead of 3.7 warps per scheduler issue the same 0.48 instructions per clock), so the simpler layout is default
+    static const bool inplace = getenv("MA3_ACT_INPLACE") != nullptr && getenv("MA3_ACT_INPLACE")[0] == '1';
+    const size_t in_bytes = (size_t)(inplace ? tsplit * boxr_max : (tsplit - 1) * kTmaSeg + boxr_max) * CT * 2;
+    // + output tile (not in place) + barriers + 1024-byte alignment slack
+    const size_t smem = 2 * in_bytes + (inplace ? 0 : (size_t)tsplit * kTmaSeg * CT * 2) + 16 + 1024;
+    const long long grid_cap = (inplace ? 5LL : 4LL) * num_sms();
+    long long gridl = grid_cap;
     if (gridl > total) gridl = total;
     cudaError_t le = cudaSuccess;
-#define ACT_TMA_CASE(CTV)                                                                                            \
+#define ACT_TMA_CASE(CTV, IP)                                                                                        \
   do {                                                                                                               \
     static DeviceOnce configured;                                                                                    \
     if (configured.pending()) {                                                                                      \
-      cudaFuncSetAttribute(act1d_tma_kernel<CTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);           \
+      cudaFuncSetAttribute(act1d_tma_kernel<CTV, IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);       \
       configured.mark();                                                                                             \
     }                                                                                                                \
-    le = launch_pdl(act1d_tma_kernel<CTV>, dim3((unsigned)gridl), dim3(kTmaWarps * 32), smem, st, 1, p);             \
+    le = launch_pdl(act1d_tma_kernel<CTV, IP>, dim3((unsigned)gridl), dim3(kTmaWarps * 32), smem, st, 1, p);         \
   } while (0)
-    if (CT == 64) ACT_TMA_CASE(64);
-    else if (CT == 32) ACT_TMA_CASE(32);
-    else ACT_TMA_CASE(16);
+    if (inplace) {
+      if (CT == 64) ACT_TMA_CASE(64, true);
+      else if (CT == 32) ACT_TMA_CASE(32, true);
+      else ACT_TMA_CASE(16, true);
+    } else {
+      if (CT == 64) ACT_TMA_CASE(64, false);
+      else if (CT == 32) ACT_TMA_CASE(32, false);
+      else ACT_TMA_CASE(16, false);
+    }
 #undef ACT_TMA_CASE
     if (le != cudaSuccess) MA3_FAIL((int)le, "act1d launch: %s", cudaGetErrorString(le));
     MA3_LAUNCH_CHECK("act1d");
