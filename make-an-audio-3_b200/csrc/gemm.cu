@@ -54,6 +54,9 @@ struct GemmKParams {
   // narrow-conv kernel (conv_narrow_kernel): rows of the staged A tile, smallest tap shift, padded N, A stages
   int cn_rows_a, cn_min_shift, cn_bnp, cn_stages;
   int cn_lin, cn_tap_step;   // taps equally spaced (a_shift[t] = a_shift[0] + t * cn_tap_step): descriptor increments
+  // 65..128 channels: two 64-wide k-chunks per staged tile (cn_kchunks), and the output columns split over cn_nsplit
+  // CTAs of cn_ncols columns each, so that a CTA keeps only its share of the weights resident
+  int cn_kchunks, cn_nsplit, cn_ncols, cn_rows_a8;
   // fused RMSNorm (see ma3_gemm_t): producer outputs of GATE_RES, consumer pre-op of any epilogue
   void* norm_out;
   const float* norm_w;
@@ -1190,13 +1193,13 @@ __device__ __forceinline__ uint4 cn_lean_group(const uint32_t* r, const float* s
 }
 
 template <bool kBf16>
-__device__ __forceinline__ void cn_lean_epilogue(const GemmKParams& p, int z, int m, uint32_t taddr, uint64_t* t_full,
+__device__ __forceinline__ void cn_lean_epilogue(const GemmKParams& p, int z, int m, int n0, uint32_t taddr, uint64_t* t_full,
                                                  uint32_t t_parity, uint64_t* t_empty, const float* sbias, int lane) {
-  const int ngr = p.N >> 3;                 // whole 8-column groups (host guarantees N % 8 == 0, N <= 64)
+  const int ngr = p.cn_ncols >> 3;          // whole 8-column groups of this CTA (host: multiple of 8, <= 64), from column n0
   const bool valid = m < p.M, has_res = p.res != nullptr, has_acc = p.accumulate != 0;
   const long long orow = (long long)m * p.out_row_mul + p.out_row_off;
-  const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res) + (long long)z * p.res_batch_stride + orow * p.res_ld;
-  uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)z * p.out_batch_stride + orow * p.out_ld;
+  const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res) + (long long)z * p.res_batch_stride + orow * p.res_ld + n0;
+  uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)z * p.out_batch_stride + orow * p.out_ld + n0;
   uint4 rr[8], ro[8];
 #pragma unroll
   for (int gq = 0; gq < 8; ++gq) {
@@ -1232,17 +1235,21 @@ __device__ __forceinline__ void cn_lean_epilogue(const GemmKParams& p, int z, in
 // so the single issuing thread spends two integer adds per MMA.  (Looking every tap's shift up in the parameter block
 // cost ~75 dependent uniform-datapath instructions per tap: the issuing thread, not the tensor pipe (12 % busy), the
 // loads or the epilogue, set the tile rate of the 32- and 48-channel layers at ~2000 clocks per tile.)
-template <int KS>
+template <int KS, int KS1>   // k-steps of the first and (channels 64..127) second k-chunk
 __device__ __forceinline__ void cn_issue_tile(uint32_t d_tmem, uint32_t at, uint32_t wt, uint32_t a_step, uint32_t w_step,
-                                              int taps, uint32_t dhi, uint32_t idesc) {
+                                              int taps, uint32_t dhi, uint32_t idesc, uint32_t a_c1, uint32_t w_c1) {
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) umma_f16_lohi<1>(d_tmem, at + 2 * ks, wt + 2 * ks, dhi, idesc, ks != 0 ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < KS1; ++ks) umma_f16_lohi<1>(d_tmem, at + a_c1 + 2 * ks, wt + w_c1 + 2 * ks, dhi, idesc, 1u);
 #pragma unroll 1
   for (int tap = 1; tap < taps; ++tap) {
     at += a_step;
     wt += w_step;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) umma_f16_lohi<1>(d_tmem, at + 2 * ks, wt + 2 * ks, dhi, idesc, 1u);
+#pragma unroll
+    for (int ks = 0; ks < KS1; ++ks) umma_f16_lohi<1>(d_tmem, at + a_c1 + 2 * ks, wt + w_c1 + 2 * ks, dhi, idesc, 1u);
   }
 }
 
@@ -1251,10 +1258,14 @@ template <int kLean>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t w_tap_bytes = (uint32_t)p.cn_bnp * 128u;
+  const uint32_t w_chunk = (uint32_t)p.cn_bnp * 128u, a_chunk = (uint32_t)p.cn_rows_a8 * 128u;   // one 64-wide k-chunk
+  const uint32_t w_tap_bytes = (uint32_t)p.cn_kchunks * w_chunk;
   const uint32_t w_bytes = (uint32_t)p.taps * w_tap_bytes;
-  const uint32_t a_bytes = (uint32_t)p.cn_rows_a * 128u;
-  const uint32_t a_stage = (a_bytes + 1023u) & ~1023u;
+  const uint32_t a_bytes = (uint32_t)(p.cn_kchunks * p.cn_rows_a) * 128u;    // bytes the loads of one tile deliver
+  const uint32_t a_stage = ((uint32_t)p.cn_kchunks * a_chunk + 1023u) & ~1023u;
+  // CTA -> (column slice, worker): the CTAs of a slice share the tiles of that slice
+  const int ns = (int)blockIdx.x % p.cn_nsplit, worker = (int)blockIdx.x / p.cn_nsplit;
+  const int n_workers = (int)gridDim.x / p.cn_nsplit, n0 = ns * p.cn_ncols;
   uint8_t* sW = base;
   uint8_t* sA = base + ((w_bytes + 1023u) & ~1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)p.cn_stages * a_stage);
@@ -1274,7 +1285,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
   const bool col_bias = p.bias != nullptr && !p.bias_per_row;
   if (warp >= 2 && threadIdx.x - 64 < 64) {
     const int c = threadIdx.x - 64;
-    sbias[c] = (col_bias && c < p.N) ? p.bias[c] : 0.f;
+    sbias[c] = (col_bias && c < p.cn_ncols && n0 + c < p.N) ? p.bias[n0 + c] : 0.f;
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -1305,14 +1316,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
   if (warp == 0) {
     if (elect_one()) {
       mbar_arrive_expect_tx(w_full, w_bytes);
-      for (int tap = 0; tap < p.taps; ++tap) tma_load_3d(sW + (size_t)tap * w_tap_bytes, &p.tmB, w_full, 0, p.b_row[tap], 0);
+      for (int tap = 0; tap < p.taps; ++tap)
+        for (int c = 0; c < p.cn_kchunks; ++c)
+          tma_load_3d(sW + (size_t)tap * w_tap_bytes + (size_t)c * w_chunk, &p.tmB, w_full, c * 64, p.b_row[tap] + n0, 0);
       int s = 0;
       uint32_t ph = 1;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
         const int m_t = tile % p.tiles_m, z = tile / p.tiles_m;
         mbar_wait(&a_empty[s], ph);
         mbar_arrive_expect_tx(&a_full[s], a_bytes);
-        tma_load_3d(sA + (size_t)s * a_stage, &p.tmA, &a_full[s], 0, m_t * kBM + p.cn_min_shift, p.a_batched ? z : 0);
+        for (int c = 0; c < p.cn_kchunks; ++c)
+          tma_load_3d(sA + (size_t)s * a_stage + (size_t)c * a_chunk, &p.tmA, &a_full[s], c * 64, m_t * kBM + p.cn_min_shift,
+                      p.a_batched ? z : 0);
         if (++s == p.cn_stages) { s = 0; ph ^= 1; }
       }
     }
@@ -1324,10 +1339,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
       const uint32_t w_lo0 = (uint32_t)umma_desc_kmajor(smem_u32(sW), 128);
       const uint32_t a_stage16 = a_stage >> 4, w_tap16 = w_tap_bytes >> 4;
       const uint32_t a_first = (uint32_t)(p.a_shift[0] - p.cn_min_shift) * 8u;
+      const uint32_t a_c1 = a_chunk >> 4, w_c1 = w_chunk >> 4;
+      const int ks0 = p.cn_kchunks > 1 ? 4 : ksteps, ks1 = p.cn_kchunks > 1 ? ksteps - 4 : 0;
       mbar_wait(w_full, 0);
       int s = 0, lt = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers, ++lt) {
         const int as = lt & (kCnAcc - 1);
         mbar_wait(&t_empty[as], ((lt / kCnAcc) & 1) ^ 1);
         mbar_wait(&a_full[s], ph);
@@ -1336,16 +1353,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
         const uint32_t a_lo = a_lo0 + (uint32_t)s * a_stage16;
         if (p.cn_lin) {
           const uint32_t at0 = a_lo + a_first, a_step = (uint32_t)(p.cn_tap_step * 8);
-          if (ksteps == 1) cn_issue_tile<1>(d_tmem, at0, w_lo0, a_step, w_tap16, p.taps, dhi, idesc);
-          else if (ksteps == 2) cn_issue_tile<2>(d_tmem, at0, w_lo0, a_step, w_tap16, p.taps, dhi, idesc);
-          else if (ksteps == 3) cn_issue_tile<3>(d_tmem, at0, w_lo0, a_step, w_tap16, p.taps, dhi, idesc);
-          else cn_issue_tile<4>(d_tmem, at0, w_lo0, a_step, w_tap16, p.taps, dhi, idesc);
+#define CN_ISSUE(A, B) cn_issue_tile<A, B>(d_tmem, at0, w_lo0, a_step, w_tap16, p.taps, dhi, idesc, a_c1, w_c1)
+          switch (ksteps) {
+            case 1: CN_ISSUE(1, 0); break;
+            case 2: CN_ISSUE(2, 0); break;
+            case 3: CN_ISSUE(3, 0); break;
+            case 4: CN_ISSUE(4, 0); break;
+            case 5: CN_ISSUE(4, 1); break;
+            case 6: CN_ISSUE(4, 2); break;
+            case 7: CN_ISSUE(4, 3); break;
+            default: CN_ISSUE(4, 4); break;
+          }
+#undef CN_ISSUE
         } else {
           for (int tap = 0; tap < p.taps; ++tap) {
             const uint32_t at = a_lo + (uint32_t)(p.a_shift[tap] - p.cn_min_shift) * 8u;   // 128-byte rows = 8 x 16 B
             const uint32_t wt = w_lo0 + (uint32_t)tap * w_tap16;
-            for (int ks = 0; ks < ksteps; ++ks)
+            for (int ks = 0; ks < ks0; ++ks)
               umma_f16_lohi<1>(d_tmem, at + 2 * ks, wt + 2 * ks, dhi, idesc, (tap | ks) != 0 ? 1u : 0u);
+            for (int ks = 0; ks < ks1; ++ks) umma_f16_lohi<1>(d_tmem, at + a_c1 + 2 * ks, wt + w_c1 + 2 * ks, dhi, idesc, 1u);
           }
         }
         umma_commit(&a_empty[s]);
@@ -1356,13 +1382,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
   } else {
     const int q = warp & 3, ew = warp - 2, set = ew >> 2;
     int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = worker; tile < total_tiles; tile += n_workers, ++lt) {
       if ((lt & 1) != set) continue;
       const int m_t = tile % p.tiles_m, z = tile / p.tiles_m;
       const int as = lt & (kCnAcc - 1);
       const int m = m_t * kBM + q * 32 + lane;
       if constexpr (kLean != 0) {
-        cn_lean_epilogue<kLean == 2>(p, z, m, tmem_base + ((uint32_t)(q * 32) << 16) + as * 64, &t_full[as],
+        cn_lean_epilogue<kLean == 2>(p, z, m, n0, tmem_base + ((uint32_t)(q * 32) << 16) + as * 64, &t_full[as],
                                      (uint32_t)((lt / kCnAcc) & 1), &t_empty[as], sbias, lane);
         continue;
       }
@@ -1403,21 +1429,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_narrow_kernel(const __gr
 // host side of the narrow-conv path; returns 1 when the problem is not eligible (caller falls back to the tap-GEMM)
 static int try_conv_narrow(const ma3_gemm_t* g, GemmKParams& kp, cudaStream_t st) {
   static const bool off = getenv("MA3_CONV_NARROW") != nullptr && getenv("MA3_CONV_NARROW")[0] == '0';
-  if (off || g->epi != MA3_EPI_STORE || g->K > 64 || g->N > 64 || g->taps < 2 || g->cta_group == 2 || g->tile_n > 0 ||
+  static const bool wide_off = getenv("MA3_CONV_NARROW_WIDE") != nullptr && getenv("MA3_CONV_NARROW_WIDE")[0] == '0';
+  if (off || g->epi != MA3_EPI_STORE || g->K > 128 || g->N > 128 || g->taps < 2 || g->cta_group == 2 || g->tile_n > 0 ||
       g_gemm_debug_mode != 0 || g_trace != nullptr || g->b_batch_stride != 0)
     return 1;
+  // lean epilogue: 16-bit output in whole 8-column groups, residual / previous output of the same type, column bias or
+  // none, no activation (MA3_CONV_LEAN=0 keeps the generic epilogue)
+  static const bool lean_off = getenv("MA3_CONV_LEAN") != nullptr && getenv("MA3_CONV_LEAN")[0] == '0';
+  const bool lean = !lean_off && kp.vec_ok && g->out_dtype != MA3_F32 && g->N % 8 == 0 && g->act == 0 &&
+                    !(g->bias && g->bias_per_row) && (!g->res || g->res_dtype == g->out_dtype);
+  // 65..128 channels (the 96-channel stage of BigVGAN): two k-chunks per staged tile, output columns split over two
+  // CTAs so that each keeps only its half of the weights resident; lean epilogue only
+  const int kchunks = g->K > 64 ? 2 : 1, nsplit = g->N > 64 ? 2 : 1;
+  if ((kchunks > 1 || nsplit > 1) && (wide_off || !lean || g->N % (16 * nsplit) != 0)) return 1;
+  const int ncols = g->N / nsplit;
   int lo = g->a_shift[0], hi = g->a_shift[0];
   for (int i = 1; i < g->taps; ++i) { lo = g->a_shift[i] < lo ? g->a_shift[i] : lo; hi = g->a_shift[i] > hi ? g->a_shift[i] : hi; }
-  const int rows_a = kBM + (hi - lo);
-  const int bnp = (g->N + 15) / 16 * 16;
+  const int rows_a = kBM + (hi - lo), rows_a8 = (rows_a + 7) / 8 * 8;
+  const int bnp = nsplit > 1 ? ncols : (g->N + 15) / 16 * 16;
   if (rows_a > 256) return 1;
-  const size_t w_bytes = ((size_t)g->taps * bnp * 128 + 1023) & ~(size_t)1023;
-  const size_t a_stage = ((size_t)rows_a * 128 + 1023) & ~(size_t)1023;
+  const size_t w_bytes = ((size_t)g->taps * kchunks * bnp * 128 + 1023) & ~(size_t)1023;
+  const size_t a_stage = ((size_t)kchunks * rows_a8 * 128 + 1023) & ~(size_t)1023;
   const size_t tail = 512;
-  int stages = (int)((200 * 1024 - w_bytes - tail) / a_stage);
-  if (stages < 2) return 1;
+  // single-chunk layers keep the 200 KB budget they were tuned with; the two-chunk ones may use the whole SM
+  const size_t budget = (kchunks > 1 ? 225 : 200) * 1024;
+  if (w_bytes + tail + 2 * a_stage > budget) return 1;
+  int stages = (int)((budget - w_bytes - tail) / a_stage);
   if (stages > 4) stages = 4;
   kp.cn_rows_a = rows_a; kp.cn_min_shift = lo; kp.cn_bnp = bnp; kp.cn_stages = stages;
+  kp.cn_kchunks = kchunks; kp.cn_nsplit = nsplit; kp.cn_ncols = ncols; kp.cn_rows_a8 = rows_a8;
   kp.cn_tap_step = g->a_shift[1] - g->a_shift[0];
   kp.cn_lin = 1;
   for (int i = 2; i < g->taps; ++i)
@@ -1448,13 +1488,9 @@ static int try_conv_narrow(const ma3_gemm_t* g, GemmKParams& kp, cudaStream_t st
     if (e != cudaSuccess) MA3_FAIL((int)e, "cudaFuncSetAttribute(conv_narrow): %s", cudaGetErrorString(e));
     configured.mark();
   }
-  const int total_tiles = kp.tiles_m * g->batch;
-  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  // lean epilogue: 16-bit output in whole 8-column groups, residual / previous output of the same type, column bias or
-  // none, no activation (MA3_CONV_LEAN=0 keeps the generic epilogue)
-  static const bool lean_off = getenv("MA3_CONV_LEAN") != nullptr && getenv("MA3_CONV_LEAN")[0] == '0';
-  const bool lean = !lean_off && kp.vec_ok && g->out_dtype != MA3_F32 && g->N % 8 == 0 && g->act == 0 &&
-                    !(g->bias && g->bias_per_row) && (!g->res || g->res_dtype == g->out_dtype);
+  const int total_tiles = kp.tiles_m * g->batch;      // per column slice
+  int grid = total_tiles * nsplit < num_sms() ? total_tiles * nsplit : num_sms();
+  grid -= grid % nsplit;
   const size_t smem_l = smem < 120 * 1024 ? 120 * 1024 : smem;
   // at least half of the SM's shared memory so that one CTA (and its 256 TMEM columns) lives per SM
   cudaError_t e;

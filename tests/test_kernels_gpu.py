@@ -110,10 +110,12 @@ def test_gemm_as_conv1d(ops, k, dil):
     assert rel(y, ref.transpose(1, 2)) < 8e-3
 
 
-@pytest.mark.parametrize("C,k,dil,T", [(48, 7, 5, 1000), (32, 11, 3, 300), (96, 7, 1, 513), (16, 3, 1, 129), (64, 7, 3, 2048)])
+@pytest.mark.parametrize("C,k,dil,T", [(48, 7, 5, 1000), (32, 11, 3, 300), (96, 7, 1, 513), (16, 3, 1, 129), (64, 7, 3, 2048),
+                                       (96, 11, 3, 700), (96, 11, 5, 300), (128, 3, 1, 257), (96, 3, 1, 40000), (112, 7, 1, 400)])
 def test_gemm_narrow_conv_epilogue(ops, C, k, dil, T):
-    """Narrow conv layers of the vocoder (C <= 96): ragged 64-wide k-chunks (TMA zero fill beyond K) and, for
-    N <= 64, the row-direct STORE epilogue with prefetched residual, scaling and accumulation (fp16)."""
+    """Narrow conv layers of the vocoder (C <= 128): ragged 64-wide k-chunks (TMA zero fill beyond K), the row-direct STORE
+    epilogue with prefetched residual, scaling and accumulation (fp16), and for 65..128 channels the staged-once kernel
+    with two k-chunks and the output columns split over two CTAs (112 channels: not splittable, generic tap-GEMM)."""
     B = 2
     pad = (k * dil - dil) // 2
     x = (torch.randn(B, T, C, generator=g(60))).half().cuda()
