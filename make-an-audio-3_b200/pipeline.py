@@ -142,6 +142,8 @@ class Txt2AudioPipeline:
         launches of the two stages are captured once per latent shape and replayed (as the sampler does for its step
         loop), so no host launch latency sits between the short kernels of the VAE and of the early vocoder stages."""
         L.auto_pdl(2 * z.shape[0] * z.shape[-1])   # same rule as the sampler (whose batch is CFG-doubled)
+        if os.environ.get("MA3_PDL_TAIL") in ("0", "1"):   # experiment: pin it for the decode / vocode tail only
+            L.load().ma3_set_pdl(int(os.environ["MA3_PDL_TAIL"]))
         if not self.use_graph:
             with stage_range("ma3.decode_first_stage"):
                 mel = self.decode_first_stage(z)

@@ -1,5 +1,5 @@
 # scratch: the command list of the next gpurun call (rewritten per call)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "gemm or conv" -x 2>&1 | tail -3
-timeout 600 python -m pytest tests/test_modules_gpu.py tests/test_parity_full_size_gpu.py -q -m gpu -k "bigvgan or vocode or vae" -x 2>&1 | tail -3
-timeout 300 python tools/probe_vocoder.py > gpurun_out/r02z2_probe_vocoder.log 2>&1; grep "acc" gpurun_out/r02z2_probe_vocoder.log
+for v in 0 1 0 1; do MA3_PDL_TAIL=$v timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-lib-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('PDL_TAIL=$v', round(d['value'],1), round(d['ms_per_step'],2), d['stage_ms'], d['clocks']['sm_mhz'])"; done | tee gpurun_out/r02z_pdl_tail.log
