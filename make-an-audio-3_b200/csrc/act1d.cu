@@ -468,6 +468,12 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) act1d_mma_kernel(const __ha
 #ifndef MA3_ACT_ILP4
 #define MA3_ACT_ILP4 1
 #endif
+#ifndef MA3_ACT_NBUF
+#define MA3_ACT_NBUF 2   // input buffers of the in-place variant: 3 = loads issued two tiles ahead (experiment)
+#endif
+#ifndef MA3_ACT_KO
+#define MA3_ACT_KO 0   // knock-out builds for diagnostics only (1 = no MUFU.SIN, 2 = no low-pass MMAs, 3 = no stmatrix)
+#endif
 constexpr int kTmaWarps = 4;
 constexpr int kTmaSeg = 128;               // outputs per warp and tile
 
@@ -510,10 +516,16 @@ __device__ __forceinline__ void act_sample_block(uint32_t xaddr, const uint32_t 
   float ul[4] = {0.f, 0.f, 0.f, 0.f}, uh[4] = {0.f, 0.f, 0.f, 0.f};
   mma_f16(ul, xa, bu[0][0], bu[0][1]);     // samples 0..7:  [0],[1] = channel g, samples 2tq, 2tq+1; [2],[3] = channel g+8
   mma_f16(uh, xa, bu[1][0], bu[1][1]);     // samples 8..15
+#if MA3_ACT_KO == 1   // diagnostics (tools/probe_act1d_ko.sh): no MUFU.SIN, same packed arithmetic around it; wrong results
+  auto snake_ko = [](float2 u, float2 a, float2 ib) { const float2 g = fmul2(u, a); return ffma2(fmul2(ib, g), g, u); };
+  float2 p0 = snake_ko(make_float2(ul[0], ul[1]), a0, ib0), p1 = snake_ko(make_float2(ul[2], ul[3]), a1, ib1);
+  float2 p2 = snake_ko(make_float2(uh[0], uh[1]), a0, ib0), p3 = snake_ko(make_float2(uh[2], uh[3]), a1, ib1);
+#else
   float2 p0 = snake2(make_float2(ul[0], ul[1]), a0, ib0);
   float2 p1 = snake2(make_float2(ul[2], ul[3]), a1, ib1);
   float2 p2 = snake2(make_float2(uh[0], uh[1]), a0, ib0);
   float2 p3 = snake2(make_float2(uh[2], uh[3]), a1, ib1);
+#endif
   if constexpr (EDGE == 1) {
     const float v0 = __shfl_sync(0xffffffffu, p0.x, (lane & ~3) | 3);
     const float v1 = __shfl_sync(0xffffffffu, p1.x, (lane & ~3) | 3);
@@ -534,10 +546,19 @@ __device__ __forceinline__ void act_sample_block(uint32_t xaddr, const uint32_t 
 
 __device__ __forceinline__ void act_out_group(uint32_t oaddr, const uint32_t (&lo)[4], const uint32_t (&hi)[4],
                                               const uint32_t (&bd)[2][2]) {
+#if MA3_ACT_KO == 2   // diagnostics: no low-pass MMAs (the activated samples are stored as they are); wrong results
+  stmatrix_x2_trans(oaddr, lo[0] ^ hi[2], lo[1] ^ hi[3]);
+#elif MA3_ACT_KO == 3  // diagnostics: no stmatrix (one lane keeps the value alive through a never-taken store); wrong results
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  mma_f16(o, lo, bd[0][0], bd[0][1]);
+  mma_f16(o, hi, bd[1][0], bd[1][1]);
+  if (o[0] == 1.2345e30f) stmatrix_x2_trans(oaddr, pack_f16(o[0], o[1]), pack_f16(o[2], o[3]));
+#else
   float o[4] = {0.f, 0.f, 0.f, 0.f};
   mma_f16(o, lo, bd[0][0], bd[0][1]);
   mma_f16(o, hi, bd[1][0], bd[1][1]);
   stmatrix_x2_trans(oaddr, pack_f16(o[0], o[1]), pack_f16(o[2], o[3]));
+#endif
 }
 
 // INPLACE: every 128-output segment has its own (outputs + 16 halo) row region of the input buffer and a warp writes
@@ -545,7 +566,7 @@ __device__ __forceinline__ void act_out_group(uint32_t oaddr, const uint32_t (&l
 // operands of that group, so the ordering is a true register dependency -- and the TMA store reads the tile back from
 // the input buffer: no output tile, 37-42 KB instead of 54 KB per CTA, five CTAs (20 warps) per SM instead of four.
 template <int CT, bool INPLACE>
-__global__ void __launch_bounds__(kTmaWarps * 32, INPLACE ? 5 : 4) act1d_tma_kernel(const __grid_constant__ Act1dTmaParams p) {
+__global__ void __launch_bounds__(kTmaWarps * 32, (INPLACE && MA3_ACT_NBUF == 2) ? 5 : 4) act1d_tma_kernel(const __grid_constant__ Act1dTmaParams p) {
   constexpr int CGS = CT / 16;                       // 16-channel groups per tile
   constexpr int TSPLIT = kTmaWarps / CGS;            // 128-output time segments per tile
   constexpr int SMAX = kTmaSeg;
@@ -561,8 +582,9 @@ __global__ void __launch_bounds__(kTmaWarps * 32, INPLACE ? 5 : 4) act1d_tma_ker
   static_assert(IN_BYTES % 1024 == 0 && OUT_BYTES % 1024 == 0 && (SMAX * PITCH) % 1024 == 0, "tile alignment");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle patterns are functions of the address bits
-  const uint32_t out_base = base + 2 * IN_BYTES;
-  const uint32_t bar0 = out_base + OUT_BYTES;                    // two 8-byte "tile landed" barriers
+  constexpr int NB = INPLACE ? MA3_ACT_NBUF : 2;                 // input buffers; loads run NB - 1 tiles ahead
+  const uint32_t out_base = base + NB * IN_BYTES;
+  const uint32_t bar0 = out_base + OUT_BYTES;                    // NB 8-byte "tile landed" barriers
   auto swz = [](uint32_t off) { return off ^ ((off >> 3) & SWZ); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -572,8 +594,8 @@ __global__ void __launch_bounds__(kTmaWarps * 32, INPLACE ? 5 : 4) act1d_tma_ker
   const int T = p.T;
 
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+#pragma unroll
+    for (int i = 0; i < NB; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
     fence_barrier_init();
     prefetch_tmap(&p.tin);
     prefetch_tmap(&p.tout);
@@ -618,17 +640,21 @@ __global__ void __launch_bounds__(kTmaWarps * 32, INPLACE ? 5 : 4) act1d_tma_ker
   const int grid = (int)gridDim.x, bid = (int)blockIdx.x;
   const int n_items = bid < total ? (total - bid + grid - 1) / grid : 0;
   auto item_of = [&](int i) { return bid + i * grid; };
-  if (tid == 0 && n_items > 0) issue_load(item_of(0), 0);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NB - 1; ++i)
+      if (i < n_items) issue_load(item_of(i), i);
+  }
   for (int it = 0; it < n_items; ++it) {
-    const int buf = it & 1;
+    const int buf = it % NB;
     const int item = item_of(it);
     if (tid == 0) {
-      // the other buffer was released by the barrier that closed the previous iteration; in place, the previous tile's
-      // store still reads its outputs from that buffer
+      // the buffer of tile it - 1 was released by the barrier that closed the previous iteration; in place, that tile's
+      // store still reads its outputs from it
       if constexpr (INPLACE) bulk_wait_read0();
-      if (it + 1 < n_items) {
+      if (it + NB - 1 < n_items) {
         fence_proxy_async_smem();
-        issue_load(item_of(it + 1), buf ^ 1);
+        issue_load(item_of(it + NB - 1), (it + NB - 1) % NB);
       }
       if constexpr (!INPLACE) bulk_wait_read0();   // the previous tile's store has drained the output tile
     }
@@ -641,7 +667,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32, INPLACE ? 5 : 4) act1d_tma_ker
     const float i0 = 1.f / (be0 + 1e-9f), i1 = 1.f / (be1 + 1e-9f);
     const float2 a0 = make_float2(al0, al0), a1 = make_float2(al1, al1);
     const float2 ib0 = make_float2(i0, i0), ib1 = make_float2(i1, i1);
-    while (!mbar_try_wait(bar0 + 8 * buf, (uint32_t)((it >> 1) & 1))) {
+    while (!mbar_try_wait(bar0 + 8 * buf, (uint32_t)((it / NB) & 1))) {
     }
     if constexpr (!INPLACE) __syncthreads();   // nobody writes the output tile before its previous store has read it
     const int tw0 = tb0 + seg * S;             // first output of this warp's segment
@@ -816,8 +842,9 @@ int ma3_act1d(const void* x, int in_dtype, void* out, int out_dtype, const float
     static const bool inplace = getenv("MA3_ACT_INPLACE") != nullptr && getenv("MA3_ACT_INPLACE")[0] == '1';
     const size_t in_bytes = (size_t)(inplace ? tsplit * boxr_max : (tsplit - 1) * kTmaSeg + boxr_max) * CT * 2;
     // + output tile (not in place) + barriers + 1024-byte alignment slack
-    const size_t smem = 2 * in_bytes + (inplace ? 0 : (size_t)tsplit * kTmaSeg * CT * 2) + 16 + 1024;
-    const long long grid_cap = (inplace ? 5LL : 4LL) * num_sms();
+    const int nbuf = inplace ? MA3_ACT_NBUF : 2;
+    const size_t smem = nbuf * in_bytes + (inplace ? 0 : (size_t)tsplit * kTmaSeg * CT * 2) + 32 + 1024;
+    const long long grid_cap = ((inplace && nbuf == 2) ? 5LL : 4LL) * num_sms();
     long long gridl = grid_cap;
     if (gridl > total) gridl = total;
     cudaError_t le = cudaSuccess;

@@ -1,5 +1,7 @@
 # scratch: the command list of the next gpurun call (rewritten per call)
 mkdir -p gpurun_out
-for v in 0 1 0 1; do MA3_PDL_TAIL=$v timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-lib-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('PDL_TAIL=$v', round(d['value'],1), round(d['ms_per_step'],2), d['stage_ms'], d['clocks']['sm_mhz'])"; done | tee gpurun_out/r02z_pdl_tail.log
+NB3=$PWD/make-an-audio-3_b200/csrc/build/libma3b200_nb3.so
+MA3_LIB=$NB3 MA3_ACT_INPLACE=1 timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "act1d" -x 2>&1 | tail -2
+( echo "== product"; python tools/probe_act1d.py | grep "v0"
+echo "== in place, 2 buffers"; MA3_ACT_INPLACE=1 python tools/probe_act1d.py | grep "v0"
+echo "== in place, 3 buffers"; MA3_LIB=$NB3 MA3_ACT_INPLACE=1 python tools/probe_act1d.py | grep "v0" ) 2>&1 | tee gpurun_out/r02z_act1d_nbuf.log
