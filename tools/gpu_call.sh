@@ -1,7 +1,6 @@
 # scratch: the command list of the next gpurun call (rewritten per call)
 mkdir -p gpurun_out
-NB3=$PWD/make-an-audio-3_b200/csrc/build/libma3b200_nb3.so
-MA3_LIB=$NB3 MA3_ACT_INPLACE=1 timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "act1d" -x 2>&1 | tail -2
-( echo "== product"; python tools/probe_act1d.py | grep "v0"
-echo "== in place, 2 buffers"; MA3_ACT_INPLACE=1 python tools/probe_act1d.py | grep "v0"
-echo "== in place, 3 buffers"; MA3_LIB=$NB3 MA3_ACT_INPLACE=1 python tools/probe_act1d.py | grep "v0" ) 2>&1 | tee gpurun_out/r02z_act1d_nbuf.log
+timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -3 > gpurun_out/r02zz_tests_gpu.log; cat gpurun_out/r02zz_tests_gpu.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-lib-baseline > gpurun_out/r02zz_bench_default.json 2> gpurun_out/r02zz_bench_default.err; python -c "
+import json; d=json.loads(open('gpurun_out/r02zz_bench_default.json').read().strip().splitlines()[-1]); print(round(d['value'],1), round(d['ms_per_step'],2), d['e2e']['value'], d['stage_ms'], d['clocks']['sm_mhz'], d['gpu_launches'])"
