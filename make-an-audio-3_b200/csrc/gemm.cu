@@ -1627,6 +1627,9 @@ extern "C" int ma3_gemm(const ma3_gemm_t* g, void* stream) {
       for (int cg = 1; cg <= 2; ++cg) {
         if (g->cta_group != 0 && cg != g->cta_group) continue;
         if (cg == 2 && (bn % 32 != 0 || bn < 64 || g->M < 256)) continue;
+        // (a 3 % bonus for the CTA pair on 3-tap convolutions, suggested by the isolated probe
+        // profiles/r02z_probe_conv_tiles.log, measured WORSE inside the step: 84 -> 110 us at 384 channels, 78 -> 103 us
+        // at 192, 62 -> 76 us at 768; in-step A/B runs decide, not the isolated probe)
         const double c = tile_cost(g, bn, cg, BK);
         if (best < 0 || c < best) { best = c; bBN = bn; bCG = cg; }
       }
