@@ -281,25 +281,16 @@ __device__ __forceinline__ void unpack16(uint4 u, int dtype, float (&v)[8]);
 // before the accumulator chunk is loaded and staged so that their global-memory latency overlaps that work.
 struct ResPre {
   uint4 v[4];
-  uint4 a[4];     // previous output values (accumulate, 16-bit output), requested together with the residual
-  bool on, acc_on;
+  bool on;
 };
 __device__ __forceinline__ void res_pre_issue(const GemmKParams& p, int n0, int w, int lane, const RowCtx& rc, ResPre& rp) {
   const int cg = (lane & 3) * 8, col = n0 + cg;
   rp.on = p.res != nullptr && p.vec_ok && p.res_dtype != MA3_F32 && cg < w && col + 8 <= p.N;
-  rp.acc_on = p.accumulate && p.vec_ok && p.out_dtype != MA3_F32 && cg < w && col + 8 <= p.N;
-  if (rp.on) {
-    const uint16_t* res = reinterpret_cast<const uint16_t*>(p.res);
+  if (!rp.on) return;
+  const uint16_t* res = reinterpret_cast<const uint16_t*>(p.res);
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass)
-      if (rc.off[pass] >= 0) rp.v[pass] = *reinterpret_cast<const uint4*>(res + rc.aux[pass] + col);
-  }
-  if (rp.acc_on) {
-    const uint16_t* outp = reinterpret_cast<const uint16_t*>(p.out);
-#pragma unroll
-    for (int pass = 0; pass < 4; ++pass)
-      if (rc.off[pass] >= 0) rp.a[pass] = *reinterpret_cast<const uint4*>(outp + rc.off[pass] + col);
-  }
+  for (int pass = 0; pass < 4; ++pass)
+    if (rc.off[pass] >= 0) rp.v[pass] = *reinterpret_cast<const uint4*>(res + rc.aux[pass] + col);
 }
 // Fused-RMSNorm producer (GATE_RES with norm_out; instantiated as its own epilogue kind so that the row bookkeeping of
 // the reduction path does not occupy registers here).  Row-wise mapping as GATE_RES: 8 lanes x float4 cover the 32
@@ -506,11 +497,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int m0, int
       }
       if (p.accumulate) {
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-          if (rc.off[pass] < 0) continue;
-          if (rp != nullptr && rp->acc_on) unpack16(rp->a[pass], p.out_dtype, ov[pass]);
-          else load8(p.out, p.out_dtype, rc.off[pass] + col, vec, n, ov[pass]);
-        }
+        for (int pass = 0; pass < 4; ++pass)
+          if (rc.off[pass] >= 0) load8(p.out, p.out_dtype, rc.off[pass] + col, vec, n, ov[pass]);
       }
       const float* sp = stg + (lane >> 2) * kStagePitch + cg;
 #pragma unroll
